@@ -220,8 +220,81 @@ static bool run_case(const Problem& P, const Dev& d, bool bwd, bool nf4, bool lo
   return ok;
 }
 
+
+// ---------------------------------------------------------------------------------------------- timing mode
+static void fill_random(void* d, size_t bytes) {
+  std::vector<uint32_t> h(bytes / 4 + 1);
+  for (auto& x : h) x = (uint32_t)rand() * 2654435761u + (uint32_t)rand();
+  CK(cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice));
+}
+static void fill_bf16(__nv_bfloat16* d, size_t n, float amp) {
+  std::vector<__nv_bfloat16> h(n);
+  for (auto& x : h) x = __float2bfloat16_rn(frand() * amp);
+  CK(cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice));
+}
+static int bench_main(int only_k, int only_n, int only_bwd, int only_nf4, int only_lora, int only_bn, int iters_arg) {
+  const int M = 21120;
+  const int shapes[][2] = {{768, 768}, {768, 2048}, {2048, 768}, {1024, 1024}, {1024, 2752}, {2752, 1024}};  // {K, N}
+  const int maxd = 2752;
+  __nv_bfloat16 *X, *dY, *W, *down, *up, *bias, *out, *side;
+  uint8_t *packed, *qabs;
+  float *nested, *ncode, *code;
+  CK(cudaMalloc(&X, (size_t)M * maxd * 2)); CK(cudaMalloc(&dY, (size_t)M * maxd * 2));
+  CK(cudaMalloc(&out, (size_t)M * maxd * 2)); CK(cudaMalloc(&side, (size_t)M * 16 * 2));
+  CK(cudaMalloc(&W, (size_t)maxd * maxd * 2)); CK(cudaMalloc(&down, 16 * maxd * 2)); CK(cudaMalloc(&up, 16 * maxd * 2));
+  CK(cudaMalloc(&bias, maxd * 2)); CK(cudaMalloc(&packed, (size_t)maxd * maxd / 2)); CK(cudaMalloc(&qabs, (size_t)maxd * maxd / 64));
+  CK(cudaMalloc(&nested, 4 * ((size_t)maxd * maxd / 64 / 256 + 1))); CK(cudaMalloc(&ncode, 1024)); CK(cudaMalloc(&code, 64));
+  fill_bf16(X, (size_t)M * maxd, 1.f); fill_bf16(dY, (size_t)M * maxd, 1.f); fill_bf16(W, (size_t)maxd * maxd, 0.05f);
+  fill_bf16(down, 16 * maxd, 0.1f); fill_bf16(up, 16 * maxd, 0.1f); fill_bf16(bias, maxd, 1.f);
+  fill_random(packed, (size_t)maxd * maxd / 2); fill_random(qabs, (size_t)maxd * maxd / 64);
+  {
+    std::vector<float> h((size_t)maxd * maxd / 64 / 256 + 1, 0.01f), nc(256), c(kNF4, kNF4 + 16);
+    for (int i = 0; i < 256; ++i) nc[i] = (i - 127.5f) / 127.5f;
+    CK(cudaMemcpy(nested, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ncode, nc.data(), 1024, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(code, c.data(), 64, cudaMemcpyHostToDevice));
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  printf("M=%d; time per launch (us) and TFLOP/s (2*M*K*N + LoRA 2*M*16*(K+N))\n", M);
+  for (auto& sh : shapes) {
+    const int K = sh[0], N = sh[1];
+    if (only_k > 0 && (K != only_k || N != only_n)) continue;
+    for (int bwd = 0; bwd < 2; ++bwd)
+      for (int nf4 = 0; nf4 < 2; ++nf4)
+        for (int lora = 0; lora < 2; ++lora)
+          for (int bn : {128, 192}) {
+            if (only_k > 0 && (bwd != only_bwd || nf4 != only_nf4 || lora != only_lora || bn != only_bn)) continue;
+            const int NO = bwd ? K : N, R = bwd ? N : K;
+            GemmLaunch g{};
+            g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = bn;
+            g.act = bwd ? dY : X; g.lda = R; g.w_bf16 = W;
+            g.p.M = M; g.p.NO = NO; g.p.R = R; g.p.D = out; g.p.ldd = NO; g.p.bias = bwd ? nullptr : bias;
+            g.p.w = Nf4Weight{packed, qabs, nested, ncode, code, 0.02f, N, K};
+            g.p.lora_down = down; g.p.lora_up = up; g.p.scale = 0.0625f; g.p.side = side;
+            for (int i = 0; i < 3; ++i) if (launch_gemm(g, 0)) { printf("launch failed %s\n", last_error().c_str()); return 1; }
+            CK(cudaDeviceSynchronize());
+            const int iters = iters_arg;
+            CK(cudaEventRecord(e0));
+            for (int i = 0; i < iters; ++i) launch_gemm(g, 0);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double us = ms * 1000.0 / iters;
+            const double fl = 2.0 * M * K * N + (lora ? 2.0 * M * 16 * (K + N) : 0.0);
+            printf("  K=%4d N=%4d %s %s %s BN=%d : %8.1f us  %7.1f TF\n", K, N, bwd ? "bwd" : "fwd", nf4 ? "nf4 " : "bf16",
+                   lora ? "lora" : "----", bn, us, fl / us * 1e-6);
+          }
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   srand(1234);
+  if (argc > 1 && strcmp(argv[1], "bench") == 0) return bench_main(0, 0, 0, 0, 0, 0, 20);
+  if (argc > 8 && strcmp(argv[1], "one") == 0)
+    return bench_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
   int dev_count = 0;
   CK(cudaGetDeviceCount(&dev_count));
   cudaDeviceProp prop;

@@ -1,0 +1,91 @@
+// Host launchers for the attention kernels.
+#pragma once
+#include "attention.cuh"
+#include "host.cuh"
+
+namespace vpt {
+
+struct AttnTensor {
+  const void* ptr;
+  long sb, sl, sh;   // element strides of (batch, token, head); head_dim is contiguous
+};
+
+inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int L) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(kAttnHD), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(t.sl) * 2, static_cast<uint64_t>(t.sh) * 2,
+                               static_cast<uint64_t>(t.sb) * 2};
+  const uint32_t box[4] = {kAttnHD, kAttnTile, 1, 1};
+  return make_tmap_bf16_4d(m, t.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,
+                           int H, int Lq, int Lk, const int* seqlens_k, float scale, float* lse2,
+                           cudaStream_t stream) {
+  CUtensorMap tq, tk, tv;
+  if (make_attn_tmap(&tq, q, B, H, Lq) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk))
+    return 1;
+  if ((o.sl | o.sh | o.sb) & 7) return fail("attention output strides must be multiples of 8 elements");
+  AttnFwdParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.seqlens_k = seqlens_k;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.o = static_cast<__nv_bfloat16*>(const_cast<void*>(o.ptr));
+  p.o_sb = o.sb; p.o_sl = o.sl; p.o_sh = o.sh;
+  p.lse2 = lse2;
+  static bool attr = false;
+  if (!attr) {
+    VPT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
+    attr = true;
+  }
+  dim3 grid((Lq + kAttnTile - 1) / kAttnTile, H, B);
+  attn_fwd_kernel<<<grid, 192, AttnFwdSmem::kTotal, stream>>>(tq, tk, tv, p);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// dq_f32 must be zero on entry (fp32, same (b, l, h) element strides as given); delta is a [B,H,Lq] fp32 workspace.
+inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o,
+                           const AttnTensor& d_o, const AttnTensor& dq_f32, const AttnTensor& dk, const AttnTensor& dv,
+                           int B, int H, int Lq, int Lk, const int* seqlens_k, float scale, const float* lse2,
+                           float* delta, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv, tdo;
+  if (make_attn_tmap(&tq, q, B, H, Lq) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk) ||
+      make_attn_tmap(&tdo, d_o, B, H, Lq))
+    return 1;
+  AttnDeltaParams dp{};
+  dp.B = B; dp.H = H; dp.Lq = Lq;
+  dp.o = static_cast<const __nv_bfloat16*>(o.ptr);
+  dp.d_o = static_cast<const __nv_bfloat16*>(d_o.ptr);
+  dp.o_sb = o.sb; dp.o_sl = o.sl; dp.o_sh = o.sh;
+  dp.do_sb = d_o.sb; dp.do_sl = d_o.sl; dp.do_sh = d_o.sh;
+  dp.delta = delta;
+  const long groups = static_cast<long>(B) * H * Lq;
+  attn_bwd_delta_kernel<<<static_cast<unsigned>((groups * 8 + 255) / 256), 256, 0, stream>>>(dp);
+  VPT_CUDA_OK(cudaGetLastError());
+
+  AttnBwdParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.seqlens_k = seqlens_k;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse2 = lse2;
+  p.delta = delta;
+  p.dq = static_cast<float*>(const_cast<void*>(dq_f32.ptr));
+  p.dq_sb = dq_f32.sb; p.dq_sl = dq_f32.sl; p.dq_sh = dq_f32.sh;
+  p.dk = static_cast<__nv_bfloat16*>(const_cast<void*>(dk.ptr));
+  p.dv = static_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr));
+  p.dk_sb = dk.sb; p.dk_sl = dk.sl; p.dk_sh = dk.sh;
+  p.dv_sb = dv.sb; p.dv_sl = dv.sl; p.dv_sh = dv.sh;
+  static bool attr = false;
+  if (!attr) {
+    VPT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdSmem::kTotal));
+    attr = true;
+  }
+  dim3 grid((Lk + kAttnTile - 1) / kAttnTile, H, B);
+  attn_bwd_kernel<<<grid, 192, AttnBwdSmem::kTotal, stream>>>(tq, tk, tv, tdo, p);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vpt

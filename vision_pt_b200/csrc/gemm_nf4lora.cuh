@@ -70,7 +70,7 @@ struct GemmSmem {
   static constexpr int kOffTs = kStages * kStageBytes;
   static constexpr int kOffQ = kOffTs + kTsBytes;
   static constexpr int kOffBias = kOffQ + kQBytes;
-  static constexpr int kOffCode = kOffBias + kBiasBytes;
+  static constexpr int kOffCode = (kOffBias + kBiasBytes + 63) / 64 * 64;
   static constexpr int kOffBars = kOffCode + kCodeBytes;
   static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 1;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
@@ -80,7 +80,13 @@ struct GemmSmem {
 // Dequantises 32 consecutive weights (one uint4 of packed codes) and writes them as four 16B chunks of a
 // 128B-swizzled row.  w = bf16_rn( fl32( code[nibble] * absmax ) ): the same two roundings as bitsandbytes'
 // kDequantizeBlockwise<bf16, NF4>.
-__device__ __forceinline__ void nf4_dequant32_to_swizzled(const uint4& pk, float am, const float* s_code,
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+// `code_saddr` = shared address of the 16-entry fp32 code table, 64-byte aligned so that "| base" replaces "+ base".
+__device__ __forceinline__ void nf4_dequant32_to_swizzled(const uint4& pk, float am, uint32_t code_saddr,
                                                           uint32_t row_saddr, int half, int row_in_atom) {
   const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
@@ -89,9 +95,11 @@ __device__ __forceinline__ void nf4_dequant32_to_swizzled(const uint4& pk, float
     uint32_t o[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const uint32_t byte = (x >> (8 * b)) & 0xffu;
-      const float hi = __fmul_rn(s_code[byte >> 4], am);   // even element
-      const float lo = __fmul_rn(s_code[byte & 15u], am);  // odd element
+      // byte b holds elements (2b: high nibble, 2b+1: low nibble); table offset = nibble * 4
+      const uint32_t a_hi = ((x >> (8 * b + 2)) & 0x3cu) | code_saddr;
+      const uint32_t a_lo = (b == 0 ? ((x << 2) & 0x3cu) : ((x >> (8 * b - 2)) & 0x3cu)) | code_saddr;
+      const float hi = __fmul_rn(lds_f32(a_hi), am);   // even element
+      const float lo = __fmul_rn(lds_f32(a_lo), am);   // odd element
       o[b] = pack_bf16x2(hi, lo);
     }
     const uint32_t chunk = static_cast<uint32_t>((half * 4 + i) ^ row_in_atom);
@@ -135,7 +143,6 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* ts_full = tmem_empty + 2;             // [1] Ts/Q operands are in smem
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kOffTmemSlot);
   float* s_code = reinterpret_cast<float*>(smem + S::kOffCode);
-  float* s_ncode = s_code + 16;
   float* s_bias = reinterpret_cast<float*>(smem + S::kOffBias);
 
   const int warp = threadIdx.x >> 5;
@@ -379,6 +386,7 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     };
 
+    const uint32_t code_s = smem_u32(s_code);
     uint32_t it = 0;
     int tile = blockIdx.x;
     int ks = 0;
@@ -394,7 +402,7 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         cpk[u] = pk[u];
         cvalid[u] = valid[u];
         // double-quant decode, two separately rounded fp32 ops exactly like dequantize_blockwise followed by "+= offset"
-        cam[u] = valid[u] ? __fadd_rn(__fmul_rn(s_ncode[qa[u]], nest[u]), p.w.offset) : 0.f;
+        cam[u] = valid[u] ? __fadd_rn(__fmul_rn(lds_f32(code_s + 64 + qa[u] * 4), nest[u]), p.w.offset) : 0.f;
       }
       const int cur_tile = tile, cur_ks = ks;
       if (++ks == ksteps) {
@@ -423,7 +431,7 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             rin = r & 7;
           }
           if (cvalid[u]) {
-            nf4_dequant32_to_swizzled(cpk[u], cam[u], s_code, row_s, half, rin);
+            nf4_dequant32_to_swizzled(cpk[u], cam[u], code_s, row_s, half, rin);
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) st_shared_zero16(row_s + (((half * 4 + i) ^ rin) * 16));
