@@ -1,0 +1,143 @@
+/* vptb200 -- C ABI of the B200-native JiT/DiT NF4-QLoRA block kernels.
+ *
+ * The reference (p1atdev/vision-pt) is pure Python and has no FFI of its own; on this path it reaches native code
+ * through third-party wheels.  Each entry point below names the reference call it replaces (paths under
+ * /root/reference).  All pointers are DEVICE pointers unless noted, every call is asynchronous on `stream`
+ * (a cudaStream_t), never allocates or frees, and never synchronises the host.  Return value: 0 = ok, non-zero =
+ * error (message from vpt_last_error(), thread-local).  bf16 activations, fp32 statistics.
+ *
+ * Build: vision_pt_b200/csrc/build.py -> vision_pt_b200/libvptb200.so (nvcc, sm_100a only).
+ */
+#ifndef VPTB200_H_
+#define VPTB200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vpt_stream_t; /* cudaStream_t */
+
+enum { VPT_BF16 = 0, VPT_F16 = 1, VPT_F32 = 2 };
+
+const char* vpt_last_error(void);
+int vpt_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------ NF4 weight format
+ * The tensors bitsandbytes stores for one Linear4bit weight (quant_type nf4, blocksize 64, compress_statistics):
+ * `weight` (packed), `weight.absmax` (uint8), `weight.nested_absmax`, `weight.nested_quant_map`, `weight.quant_map`
+ * and the nested_offset scalar of `weight.quant_state.bitsandbytes__nf4`
+ * (src/modules/quant/bnb.py:76-129, src/modules/quant/functional.py:361-368). */
+typedef struct {
+  const uint8_t* packed;        /* [(N*K+1)/2]  high nibble = even element of the flattened [N,K] weight */
+  const uint8_t* qabsmax;       /* [N*K/64] */
+  const float* nested_absmax;   /* [ceil(N*K/64/256)] */
+  const float* nested_code;     /* [256] */
+  const float* code;            /* [16] */
+  float offset;
+  int32_t N, K;                 /* out_features, in_features */
+} vpt_nf4_weight;
+
+/* bitsandbytes.functional.dequantize_4bit (called from bnb.nn.Linear4bit.forward -> MatMul4Bit, inherited by
+ * BnbLinear4bit, src/modules/quant/bnb.py:37).  out: n elements of out_dtype.  Bit-exact. */
+int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream);
+
+/* bitsandbytes.functional.quantize_4bit(A, quant_type="nf4") with compress_statistics=True, as called by
+ * quantize_state_dict (src/modules/quant/functional.py:362-368) and Params4bit._quantize on .cuda()
+ * (src/modules/quant/bnb.py:122-129).  n % 64 == 0.  absmax_ws: [n/64] fp32 workspace.  offset_out: 1 fp32 (device). */
+int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const float* nested_code, uint8_t* packed,
+                     uint8_t* qabsmax, float* nested_absmax, float* offset_out, float* absmax_ws, vpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ NF4 + LoRA linear
+ * LoRALinear.forward over a BnbLinear4bit base (src/modules/peft/lora.py:92-104):
+ *   y = x W^T + bias + Ts lora_up^T (+ residual),   Ts = bf16(scale * x lora_down^T),   scale = alpha / rank
+ * and the activation gradient of the same (MatMul4Bit.backward + autograd of the LoRA branch):
+ *   dx = dy W + dTs lora_down (+ residual),         dTs = bf16(scale * dy lora_up)
+ * rank is 16 (pad smaller ranks with zero rows/columns).  K % 64 == 0.  x/dy/y/dx are row-major with the given
+ * leading dimensions (multiples of 8 elements).  `side` receives Ts / dTs ([M,16] bf16) for the parameter gradients. */
+typedef struct {
+  vpt_nf4_weight w;
+  const void* w_bf16;          /* optional: [N,K] bf16 weight used instead of the NF4 tensors (unquantised Linear) */
+  const void* bias;            /* [N] bf16 or NULL (forward only) */
+  const void* lora_down;       /* [16,K] bf16 or NULL (LoRA disabled) */
+  const void* lora_up;         /* [N,16] bf16 */
+  float scale;
+  const void* in;              /* fwd: x [M,K];  bwd: dy [M,N] */
+  int64_t ld_in;
+  void* out;                   /* fwd: y [M,N];  bwd: dx [M,K] */
+  int64_t ld_out;
+  const void* residual;        /* optional, same shape as out */
+  int64_t ld_res;
+  void* side;                  /* [M,16] bf16 or NULL */
+  int32_t M;
+  int32_t tile_n;              /* 0 = auto (128 or 192) */
+} vpt_linear_args;
+
+int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream);
+int vpt_nf4lora_linear_bwd_dx(const vpt_linear_args* a, vpt_stream_t stream);
+
+/* autograd of lora_down / lora_up (src/modules/peft/lora.py:100-104):  out += src^T small, fp32.
+ *   lora_up.weight.grad   [N,16]: src = dy [M,N], small = Ts,  transposed = 0
+ *   lora_down.weight.grad [16,K]: src = x  [M,K], small = dTs, transposed = 1 (ld_out = K) */
+int vpt_lora_grad(const void* src, int64_t ld_src, const void* small, float* out, int32_t M, int32_t P,
+                  int32_t transposed, int64_t ld_out, vpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ attention
+ * scaled_dot_product_attention(q, k, v, mask=key padding) (src/modules/attention.py:98-129) as used by
+ * Attention.forward (src/models/jit/denoiser.py:351-397); head_dim 64; the bool key-padding mask is given as
+ * seqlens_k[b] = number of leading valid keys (NULL = all).  Tensors are (batch, token, head, 64) with element
+ * strides (sb, sl, sh); both [B,H,L,64] and [B,L,H,64] memory layouts are accepted. */
+typedef struct {
+  const void* ptr;
+  int64_t sb, sl, sh;
+} vpt_attn_tensor;
+int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v, const vpt_attn_tensor* o,
+                 int32_t B, int32_t H, int32_t Lq, int32_t Lk, const int32_t* seqlens_k, float scale,
+                 float* lse2 /* [B,H,Lq] */, vpt_stream_t stream);
+/* dq is fp32 and must be zero on entry; delta_ws: [B,H,Lq] fp32 workspace. */
+int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v, const vpt_attn_tensor* o,
+                 const vpt_attn_tensor* d_o, const vpt_attn_tensor* dq_f32, const vpt_attn_tensor* dk,
+                 const vpt_attn_tensor* dv, int32_t B, int32_t H, int32_t Lq, int32_t Lk, const int32_t* seqlens_k,
+                 float scale, const float* lse2, float* delta_ws, vpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ norms etc.
+ * FP32RMSNorm.forward (src/modules/norm.py:20-27). rstd_out may be NULL. w may be NULL (no affine). */
+int vpt_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int64_t rows, int32_t D, int64_t ldx,
+                    int64_t ldy, float eps, vpt_stream_t stream);
+/* dx = rmsnorm_bwd(dy) (+ dres); dw (fp32 [D], accumulated) may be NULL; rstd may be NULL (recomputed). */
+int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                    float* dw, int64_t rows, int32_t D, int64_t ld, float eps, vpt_stream_t stream);
+/* q_norm/k_norm + apply_rope (src/models/jit/denoiser.py:98-111,365-373) on [tokens, H, 64]; cos_sin: [L,32,2] fp32 */
+int vpt_qknorm_rope_fwd(const void* x, const void* w, const float* cos_sin, void* y, int64_t tokens, int32_t H,
+                        int32_t L, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream);
+int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void* x, const void* w, const float* cos_sin,
+                        void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int64_t lddy, int64_t ldx,
+                        int64_t lddx, float eps, vpt_stream_t stream);
+/* SwiGLU.forward gate: a = silu(g) * u (src/models/jit/denoiser.py:502) */
+int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t rows, int32_t F, int64_t ldg, int64_t ldu,
+                   int64_t lda, vpt_stream_t stream);
+int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void* dg, void* du, int64_t rows, int32_t F,
+                   int64_t ldda, int64_t ldg, int64_t ldu, int64_t lddg, int64_t lddu, vpt_stream_t stream);
+/* AdaLayerNormZero modulate: LN(x)*(1+scale[b])+shift[b] (src/models/cogview4/denoiser.py:182-187,
+ * src/modules/norm.py:75-83); x [B*L, D] contiguous, scale/shift [B, D]. mean/rstd: [B*L] fp32 saved for backward. */
+int vpt_ln_modulate_fwd(const void* x, const void* scale, const void* shift, void* y, float* mean, float* rstd,
+                        int64_t rows, int32_t L, int32_t D, float eps, vpt_stream_t stream);
+int vpt_ln_modulate_bwd(const void* dy, const void* x, const void* scale, const float* mean, const float* rstd,
+                        void* dx, float* dscale, float* dshift, int64_t rows, int32_t L, int32_t D,
+                        vpt_stream_t stream);
+/* x + h * gate[b] (src/models/cogview4/denoiser.py:401-420) */
+int vpt_gate_residual_fwd(const void* x, const void* h, const void* gate, void* y, int64_t rows, int32_t L, int32_t D,
+                          vpt_stream_t stream);
+int vpt_gate_residual_bwd(const void* dy, const void* h, const void* gate, void* dh, float* dgate, int64_t rows,
+                          int32_t L, int32_t D, vpt_stream_t stream);
+/* patchify / unpatchify (src/modules/patch.py:17-115; JiT._unpatchify src/models/jit/denoiser.py:828-860).
+ * order 0 = (c,py,px), order 1 = (py,px,c); 2-byte elements. */
+int vpt_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, int32_t order,
+                 vpt_stream_t stream);
+int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                   int32_t order, vpt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPTB200_H_ */

@@ -1,0 +1,87 @@
+"""ctypes binding of libvptb200.so (include/vptb200.h).  There is no fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvptb200.so")
+
+VPT_BF16, VPT_F16, VPT_F32 = 0, 1, 2
+
+
+class Nf4WeightC(C.Structure):
+    _fields_ = [
+        ("packed", C.c_void_p), ("qabsmax", C.c_void_p), ("nested_absmax", C.c_void_p), ("nested_code", C.c_void_p),
+        ("code", C.c_void_p), ("offset", C.c_float), ("N", C.c_int32), ("K", C.c_int32),
+    ]
+
+
+class LinearArgsC(C.Structure):
+    _fields_ = [
+        ("w", Nf4WeightC), ("w_bf16", C.c_void_p), ("bias", C.c_void_p), ("lora_down", C.c_void_p),
+        ("lora_up", C.c_void_p), ("scale", C.c_float), ("inp", C.c_void_p), ("ld_in", C.c_int64), ("out", C.c_void_p),
+        ("ld_out", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64), ("side", C.c_void_p), ("M", C.c_int32),
+        ("tile_n", C.c_int32),
+    ]
+
+
+class AttnTensorC(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sl", C.c_int64), ("sh", C.c_int64)]
+
+
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_AT = C.POINTER(AttnTensorC)
+
+# name -> argtypes (the stream is always last); every function returns int
+SIGNATURES: dict[str, list] = {
+    "vpt_nf4_dequant": [C.POINTER(Nf4WeightC), _I64, C.c_int, _P, _P],
+    "vpt_nf4_quantize": [_P, C.c_int, _I64, _P, _P, _P, _P, _P, _P, _P],
+    "vpt_nf4lora_linear_fwd": [C.POINTER(LinearArgsC), _P],
+    "vpt_nf4lora_linear_bwd_dx": [C.POINTER(LinearArgsC), _P],
+    "vpt_lora_grad": [_P, _I64, _P, _P, _I32, _I32, _I32, _I64, _P],
+    "vpt_attn_fwd": [_AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P],
+    "vpt_attn_bwd": [_AT, _AT, _AT, _AT, _AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P],
+    "vpt_rmsnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _F, _P],
+    "vpt_rmsnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I64, _F, _P],
+    "vpt_qknorm_rope_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _I64, _I64, _F, _P],
+    "vpt_qknorm_rope_bwd": [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _I64, _I64, _F, _P],
+    "vpt_swiglu_fwd": [_P, _P, _P, _I64, _I32, _I64, _I64, _I64, _P],
+    "vpt_swiglu_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _I64, _I64, _I64, _I64, _I64, _P],
+    "vpt_ln_modulate_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
+    "vpt_ln_modulate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
+    "vpt_gate_residual_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P],
+    "vpt_gate_residual_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
+    "vpt_patchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "vpt_unpatchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the CUDA library; raises if it has not been built (python vision_pt_b200/csrc/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python vision_pt_b200/csrc/build.py` "
+            "(vision_pt_b200 has no CPU or eager fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.vpt_last_error.restype = C.c_char_p
+    lib.vpt_last_error.argtypes = []
+    lib.vpt_abi_version.restype = C.c_int
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {lib.vpt_last_error().decode()}")

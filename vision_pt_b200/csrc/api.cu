@@ -1,0 +1,216 @@
+// extern "C" entry points declared in include/vptb200.h.  Thin argument checking + kernel launches.
+#include "../../include/vptb200.h"
+
+#include "attn_launch.cuh"
+#include "elementwise.cuh"
+#include "gemm_launch.cuh"
+#include "lora_grad.cuh"
+#include "nf4.cuh"
+
+using namespace vpt;
+
+static inline cudaStream_t S(vpt_stream_t s) { return static_cast<cudaStream_t>(s); }
+static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
+  long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return static_cast<unsigned>(b);
+}
+
+extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
+extern "C" int vpt_abi_version(void) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------- NF4
+extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
+  VPT_REQUIRE(w && out && n > 0, "vpt_nf4_dequant: bad arguments");
+  const unsigned grid = blocks_for((n + 7) / 8, 256, 148 * 16);
+  switch (out_dtype) {
+    case VPT_BF16:
+      nf4_dequant_kernel<kDtBf16><<<grid, 256, 0, S(stream)>>>(w->packed, w->qabsmax, w->nested_absmax, w->nested_code, w->code, w->offset, out, n);
+      break;
+    case VPT_F16:
+      nf4_dequant_kernel<kDtF16><<<grid, 256, 0, S(stream)>>>(w->packed, w->qabsmax, w->nested_absmax, w->nested_code, w->code, w->offset, out, n);
+      break;
+    case VPT_F32:
+      nf4_dequant_kernel<kDtF32><<<grid, 256, 0, S(stream)>>>(w->packed, w->qabsmax, w->nested_absmax, w->nested_code, w->code, w->offset, out, n);
+      break;
+    default:
+      return fail("vpt_nf4_dequant: unknown out_dtype");
+  }
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const float* nested_code, uint8_t* packed,
+                                uint8_t* qabsmax, float* nested_absmax, float* offset_out, float* absmax_ws,
+                                vpt_stream_t stream) {
+  VPT_REQUIRE(w && packed && qabsmax && nested_absmax && offset_out && absmax_ws, "vpt_nf4_quantize: null pointer");
+  VPT_REQUIRE(n > 0 && n % 64 == 0, "vpt_nf4_quantize: element count must be a multiple of 64");
+  const long nb = n / 64;
+  const unsigned grid = blocks_for(nb * 8, 256);
+  switch (w_dtype) {
+    case VPT_BF16: nf4_quantize_kernel<kDtBf16><<<grid, 256, 0, S(stream)>>>(w, packed, absmax_ws, nb); break;
+    case VPT_F16: nf4_quantize_kernel<kDtF16><<<grid, 256, 0, S(stream)>>>(w, packed, absmax_ws, nb); break;
+    case VPT_F32: nf4_quantize_kernel<kDtF32><<<grid, 256, 0, S(stream)>>>(w, packed, absmax_ws, nb); break;
+    default: return fail("vpt_nf4_quantize: unknown dtype");
+  }
+  nf4_mean_kernel<<<1, 1024, 0, S(stream)>>>(absmax_ws, nb, offset_out);
+  nf4_nested_quantize_kernel<<<static_cast<unsigned>((nb + 255) / 256), 256, 0, S(stream)>>>(absmax_ws, offset_out, nested_code, qabsmax,
+                                                                                              nested_absmax, nb);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- linear
+static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream) {
+  VPT_REQUIRE(a && a->in && a->out, "vpt_nf4lora_linear: null pointer");
+  const int N = a->w.N, K = a->w.K;
+  VPT_REQUIRE(N > 0 && K > 0 && a->M > 0, "vpt_nf4lora_linear: bad shape");
+  VPT_REQUIRE(K % 64 == 0, "vpt_nf4lora_linear: in_features must be a multiple of 64 (repack ragged weights first)");
+  VPT_REQUIRE(a->ld_in % 8 == 0 && a->ld_out % 8 == 0, "vpt_nf4lora_linear: leading dimensions must be multiples of 8");
+  const bool nf4 = a->w_bf16 == nullptr;
+  if (nf4) VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
+  const bool lora = a->lora_down != nullptr;
+  if (lora) VPT_REQUIRE(a->lora_up != nullptr, "vpt_nf4lora_linear: lora_up missing");
+  if (bwd) VPT_REQUIRE(N % 8 == 0, "vpt_nf4lora_linear_bwd_dx: out_features must be a multiple of 8");
+  GemmLaunch g{};
+  g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = a->tile_n;
+  g.act = a->in; g.lda = static_cast<int>(a->ld_in); g.w_bf16 = a->w_bf16;
+  g.p.M = a->M; g.p.NO = bwd ? K : N; g.p.R = bwd ? N : K;
+  g.p.D = static_cast<__nv_bfloat16*>(a->out); g.p.ldd = static_cast<int>(a->ld_out);
+  g.p.bias = bwd ? nullptr : static_cast<const __nv_bfloat16*>(a->bias);
+  g.p.residual = static_cast<const __nv_bfloat16*>(a->residual); g.p.ldr = static_cast<int>(a->ld_res);
+  g.p.w = Nf4Weight{a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, N, K};
+  g.p.lora_down = static_cast<const __nv_bfloat16*>(a->lora_down);
+  g.p.lora_up = static_cast<const __nv_bfloat16*>(a->lora_up);
+  g.p.scale = a->scale;
+  g.p.side = static_cast<__nv_bfloat16*>(a->side);
+  return launch_gemm(g, stream);
+}
+extern "C" int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream) { return linear_common(a, false, S(stream)); }
+extern "C" int vpt_nf4lora_linear_bwd_dx(const vpt_linear_args* a, vpt_stream_t stream) { return linear_common(a, true, S(stream)); }
+
+extern "C" int vpt_lora_grad(const void* src, int64_t ld_src, const void* small, float* out, int32_t M, int32_t P,
+                             int32_t transposed, int64_t ld_out, vpt_stream_t stream) {
+  VPT_REQUIRE(src && small && out && M > 0 && P > 0, "vpt_lora_grad: bad arguments");
+  VPT_REQUIRE(ld_src % 8 == 0, "vpt_lora_grad: leading dimension must be a multiple of 8");
+  return launch_lora_grad(src, static_cast<int>(ld_src), small, out, M, P, transposed, static_cast<int>(ld_out), S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------- attention
+static inline AttnTensor AT(const vpt_attn_tensor* t) { return AttnTensor{t->ptr, static_cast<long>(t->sb), static_cast<long>(t->sl), static_cast<long>(t->sh)}; }
+extern "C" int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v,
+                            const vpt_attn_tensor* o, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                            const int32_t* seqlens_k, float scale, float* lse2, vpt_stream_t stream) {
+  VPT_REQUIRE(q && k && v && o && lse2 && B > 0 && H > 0 && Lq > 0 && Lk > 0, "vpt_attn_fwd: bad arguments");
+  return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream));
+}
+extern "C" int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v,
+                            const vpt_attn_tensor* o, const vpt_attn_tensor* d_o, const vpt_attn_tensor* dq_f32,
+                            const vpt_attn_tensor* dk, const vpt_attn_tensor* dv, int32_t B, int32_t H, int32_t Lq,
+                            int32_t Lk, const int32_t* seqlens_k, float scale, const float* lse2, float* delta_ws,
+                            vpt_stream_t stream) {
+  VPT_REQUIRE(q && k && v && o && d_o && dq_f32 && dk && dv && lse2 && delta_ws, "vpt_attn_bwd: null pointer");
+  return launch_attn_bwd(AT(q), AT(k), AT(v), AT(o), AT(d_o), AT(dq_f32), AT(dk), AT(dv), B, H, Lq, Lk, seqlens_k, scale, lse2,
+                         delta_ws, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------- elementwise
+#define BF(p) static_cast<const __nv_bfloat16*>(p)
+#define BFM(p) static_cast<__nv_bfloat16*>(p)
+extern "C" int vpt_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int64_t rows, int32_t D, int64_t ldx,
+                               int64_t ldy, float eps, vpt_stream_t stream) {
+  VPT_REQUIRE(x && y && rows > 0 && D > 0 && D % 8 == 0 && D <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_rmsnorm_fwd: bad arguments");
+  rmsnorm_fwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(w), BFM(y), rstd_out, rows, D, ldx, ldy, eps);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                               float* dw, int64_t rows, int32_t D, int64_t ld, float eps, vpt_stream_t stream) {
+  VPT_REQUIRE(dy && x && dx && rows > 0 && D % 8 == 0 && D <= 2048 && ld % 8 == 0, "vpt_rmsnorm_bwd: bad arguments");
+  rmsnorm_bwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(w), rstd, BF(dres), BFM(dx), dw, rows, D, ld, eps);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_qknorm_rope_fwd(const void* x, const void* w, const float* cos_sin, void* y, int64_t tokens, int32_t H,
+                                   int32_t L, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream) {
+  VPT_REQUIRE(x && w && cos_sin && y && tokens > 0 && H > 0 && L > 0 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_qknorm_rope_fwd: bad arguments");
+  qknorm_rope_fwd_kernel<<<blocks_for(tokens * H * 8, 256, 1L << 30), 256, 0, S(stream)>>>(BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void* x, const void* w, const float* cos_sin,
+                                   void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int64_t lddy, int64_t ldx,
+                                   int64_t lddx, float eps, vpt_stream_t stream) {
+  VPT_REQUIRE(dy && x && w && cos_sin && dx && tokens > 0 && H > 0 && L > 0, "vpt_qknorm_rope_bwd: bad arguments");
+  const unsigned grid = blocks_for(tokens * H * 8, 256, 1L << 30);
+  if (dy_is_f32)
+    qknorm_rope_bwd_kernel<true><<<grid, 256, 0, S(stream)>>>(dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps);
+  else
+    qknorm_rope_bwd_kernel<false><<<grid, 256, 0, S(stream)>>>(dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t rows, int32_t F, int64_t ldg, int64_t ldu,
+                              int64_t lda, vpt_stream_t stream) {
+  VPT_REQUIRE(g && u && a && rows > 0 && F % 8 == 0 && ldg % 8 == 0 && ldu % 8 == 0 && lda % 8 == 0, "vpt_swiglu_fwd: bad arguments");
+  swiglu_fwd_kernel<<<blocks_for(rows * (F / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(g), BF(u), BFM(a), rows, F, ldg, ldu, lda);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void* dg, void* du, int64_t rows, int32_t F,
+                              int64_t ldda, int64_t ldg, int64_t ldu, int64_t lddg, int64_t lddu, vpt_stream_t stream) {
+  VPT_REQUIRE(da && g && u && dg && du && rows > 0 && F % 8 == 0, "vpt_swiglu_bwd: bad arguments");
+  swiglu_bwd_kernel<<<blocks_for(rows * (F / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(da), BF(g), BF(u), BFM(dg), BFM(du), rows, F, ldda, ldg, ldu, lddg, lddu);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_ln_modulate_fwd(const void* x, const void* scale, const void* shift, void* y, float* mean, float* rstd,
+                                   int64_t rows, int32_t L, int32_t D, float eps, vpt_stream_t stream) {
+  VPT_REQUIRE(x && scale && shift && y && rows > 0 && L > 0 && D % 8 == 0 && D <= 2048, "vpt_ln_modulate_fwd: bad arguments");
+  ln_modulate_fwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(scale), BF(shift), BFM(y), mean, rstd, rows, L, D, eps);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_ln_modulate_bwd(const void* dy, const void* x, const void* scale, const float* mean, const float* rstd,
+                                   void* dx, float* dscale, float* dshift, int64_t rows, int32_t L, int32_t D,
+                                   vpt_stream_t stream) {
+  VPT_REQUIRE(dy && x && scale && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 2048, "vpt_ln_modulate_bwd: bad arguments");
+  VPT_REQUIRE((dscale == nullptr) == (dshift == nullptr), "vpt_ln_modulate_bwd: dscale and dshift go together");
+  ln_modulate_bwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(scale), mean, rstd, BFM(dx), dscale, dshift, rows, L, D);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_gate_residual_fwd(const void* x, const void* h, const void* gate, void* y, int64_t rows, int32_t L,
+                                     int32_t D, vpt_stream_t stream) {
+  VPT_REQUIRE(x && h && gate && y && rows > 0 && D % 8 == 0, "vpt_gate_residual_fwd: bad arguments");
+  gate_residual_fwd_kernel<<<blocks_for(rows * (D / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(x), BF(h), BF(gate), BFM(y), rows, L, D);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_gate_residual_bwd(const void* dy, const void* h, const void* gate, void* dh, float* dgate, int64_t rows,
+                                     int32_t L, int32_t D, vpt_stream_t stream) {
+  VPT_REQUIRE(dy && h && gate && dh && rows > 0 && D % 8 == 0, "vpt_gate_residual_bwd: bad arguments");
+  gate_residual_bwd_kernel<<<blocks_for(rows * (D / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(dy), BF(h), BF(gate), BFM(dh), dgate, rows, L, D);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int patch_common(const void* src, void* dst, int B, int C, int H, int W, int p, int order, bool to_patches, cudaStream_t s) {
+  VPT_REQUIRE(src && dst && B > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0 && (order == 0 || order == 1), "patchify: bad arguments");
+  const long total = static_cast<long>(B) * C * H * W;
+  const unsigned grid = blocks_for(total, 256, 148 * 64);
+  if (to_patches)
+    patch_permute_kernel<true><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), B, C, H, W, p, order);
+  else
+    patch_permute_kernel<false><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), B, C, H, W, p, order);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, int32_t order,
+                            vpt_stream_t stream) {
+  return patch_common(img, patches, B, C, H, W, p, order, true, S(stream));
+}
+extern "C" int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                              int32_t order, vpt_stream_t stream) {
+  return patch_common(patches, img, B, C, H, W, p, order, false, S(stream));
+}

@@ -1,0 +1,470 @@
+// HBM-bound kernels of the JiT / DiT block: RMSNorm, QK-norm + RoPE, SwiGLU, LayerNorm + adaLN modulate,
+// gate-residual, patchify / unpatchify.  All are one pass over the activation with 16-byte accesses; rows are
+// handled by a warp (hidden width) or by an 8-lane group (one 64-wide head), statistics in fp32.
+//
+// Reference semantics (file:line under /root/reference):
+//   FP32RMSNorm / FP32LayerNorm            src/modules/norm.py:9-27
+//   q_norm/k_norm + apply_rope             src/models/jit/denoiser.py:98-111, 365-373
+//   SwiGLU gate                            src/models/jit/denoiser.py:498-506
+//   adaLN modulate / gate                  src/models/cogview4/denoiser.py:182-187, 401-420; src/modules/norm.py:75-83
+//   patchify / unpatchify                  src/modules/patch.py:17-115; src/models/jit/denoiser.py:828-860
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpt {
+
+__device__ __forceinline__ float ew_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float ew_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t ew_pack(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ew_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void ew_unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = ew_lo(v.x); f[1] = ew_hi(v.x); f[2] = ew_lo(v.y); f[3] = ew_hi(v.y);
+  f[4] = ew_lo(v.z); f[5] = ew_hi(v.z); f[6] = ew_lo(v.w); f[7] = ew_hi(v.w);
+}
+__device__ __forceinline__ uint4 ew_pack8(const float (&f)[8]) {
+  return make_uint4(ew_pack(f[0], f[1]), ew_pack(f[2], f[3]), ew_pack(f[4], f[5]), ew_pack(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+constexpr int kEwMaxChunks = 8;   // 16B chunks per lane -> rows up to 2048 bf16 elements
+constexpr int kEwThreads = 256;   // 8 rows per CTA
+
+// ------------------------------------------------------------------------------------------- RMSNorm
+// y = bf16( (x * rstd) * w ),  rstd = rsqrt(mean(x^2) + eps)   [rows, D], D % 8 == 0, D <= 2048
+__global__ void __launch_bounds__(kEwThreads)
+rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                   float* __restrict__ rstd_out, long rows, int D, long ldx, long ldy, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nch = D >> 3;
+  uint4 v[kEwMaxChunks];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      v[i] = ld_stream(x + row * ldx + c * 8);
+      float f[8];
+      ew_unpack8(v[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / static_cast<float>(D) + eps);
+  if (lane == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      float f[8], g[8];
+      ew_unpack8(v[i], f);
+      if (w != nullptr) {
+        ew_unpack8(*reinterpret_cast<const uint4*>(w + c * 8), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = (f[e] * rstd) * g[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = f[e] * rstd;
+      }
+      st_stream(y + row * ldy + c * 8, ew_pack8(f));
+    }
+  }
+}
+
+// dx = w*dy*rstd - x * rstd^3 * mean(w*dy*x)  (+ dres);  optional dw[D] += sum_rows dy * x * rstd (fp32 atomics)
+__global__ void __launch_bounds__(kEwThreads)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                   const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
+                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
+                   long rows, int D, long ld, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
+  const int nch = D >> 3;
+  const bool live = row < rows;
+  uint4 vx[kEwMaxChunks], vg[kEwMaxChunks];
+  float dot = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (live && c < nch) {
+      vx[i] = ld_stream(x + row * ld + c * 8);
+      vg[i] = ld_stream(dy + row * ld + c * 8);
+      float fx[8], fg[8], fw[8];
+      ew_unpack8(vx[i], fx);
+      ew_unpack8(vg[i], fg);
+      if (w != nullptr) ew_unpack8(*reinterpret_cast<const uint4*>(w + c * 8), fw);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dot += fg[e] * (w != nullptr ? fw[e] : 1.f) * fx[e];
+        ss += fx[e] * fx[e];
+      }
+    }
+  }
+  dot = warp_sum(dot);
+  ss = warp_sum(ss);
+  const float rstd = !live ? 0.f : (rstd_in != nullptr ? rstd_in[row] : rsqrtf(ss / static_cast<float>(D) + eps));
+  const float coef = dot * rstd * rstd * rstd / static_cast<float>(D);
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (live && c < nch) {
+      float fx[8], fg[8], fw[8], fr[8], o[8];
+      ew_unpack8(vx[i], fx);
+      ew_unpack8(vg[i], fg);
+      if (w != nullptr) ew_unpack8(*reinterpret_cast<const uint4*>(w + c * 8), fw);
+      if (dres != nullptr) ew_unpack8(ld_stream(dres + row * ld + c * 8), fr);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o[e] = fg[e] * (w != nullptr ? fw[e] : 1.f) * rstd - fx[e] * coef;
+        if (dres != nullptr) o[e] += fr[e];
+      }
+      st_stream(dx + row * ld + c * 8, ew_pack8(o));
+      if (dw != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(dw + c * 8 + e, fg[e] * fx[e] * rstd);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- QK-norm + RoPE
+// x: [tokens = B*L, H, 64] (row pitch ld elements); per head: n = bf16(rmsnorm(x) * w); rotate interleaved pairs
+// (n[2i], n[2i+1]) by (cos, sin)[l, i]; l = token % L.  One 8-lane group per (token, head).
+__global__ void __launch_bounds__(256)
+qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                       const float* __restrict__ cs /* [L, 32, 2] */, __nv_bfloat16* __restrict__ y, long tokens, int H,
+                       int L, long ldx, long ldy, float eps) {
+  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool live = g < tokens * H;
+  const long tok = live ? g / H : 0;
+  const int h = live ? static_cast<int>(g % H) : 0;
+  float f[8];
+  float ss = 0.f;
+  if (live) {
+    ew_unpack8(ld_stream(x + tok * ldx + h * 64 + sub * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  if (!live) return;
+  const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+  float fw[8];
+  ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
+  const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
+  const float4 t0 = t[0], t1 = t[1];
+  const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = ew_round((f[2 * i] * rstd) * fw[2 * i]);       // the reference rounds to bf16 between norm and rope
+    const float b = ew_round((f[2 * i + 1] * rstd) * fw[2 * i + 1]);
+    o[2 * i] = a * c[i] - b * s[i];
+    o[2 * i + 1] = a * s[i] + b * c[i];
+  }
+  st_stream(y + tok * ldy + h * 64 + sub * 8, ew_pack8(o));
+}
+
+// dy is fp32 (the attention dQ accumulator) or bf16.  dn = R^T dy ; dx = rmsnorm_bwd(dn) with weight w.
+template <bool kDyF32>
+__global__ void __launch_bounds__(256)
+qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                       const float* __restrict__ cs, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, long tokens,
+                       int H, int L, long lddy, long ldx, long lddx, float eps) {
+  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool live = g < tokens * H;
+  const long tok = live ? g / H : 0;
+  const int h = live ? static_cast<int>(g % H) : 0;
+  float f[8], d[8], fw[8], dn[8];
+  float ss = 0.f, dot = 0.f;
+  if (live) {
+    ew_unpack8(ld_stream(x + tok * ldx + h * 64 + sub * 8), f);
+    if (kDyF32) {
+      const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + tok * lddy + h * 64 + sub * 8);
+      const float4 a = p[0], b = p[1];
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+    } else {
+      ew_unpack8(ld_stream(static_cast<const __nv_bfloat16*>(dy_) + tok * lddy + h * 64 + sub * 8), d);
+    }
+    ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
+    const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
+    const float4 t0 = t[0], t1 = t[1];
+    const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dn[2 * i] = d[2 * i] * c[i] + d[2 * i + 1] * s[i];
+      dn[2 * i + 1] = -d[2 * i] * s[i] + d[2 * i + 1] * c[i];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ss += f[e] * f[e];
+      dot += dn[e] * fw[e] * f[e];
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  if (!live) return;
+  const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+  const float coef = dot * rstd * rstd * rstd * (1.f / 64.f);
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = dn[e] * fw[e] * rstd - f[e] * coef;
+  st_stream(dx + tok * lddx + h * 64 + sub * 8, ew_pack8(o));
+  if (dw != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dw + sub * 8 + e, dn[e] * f[e] * rstd);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- SwiGLU gate
+// a = bf16( bf16(silu(g)) * u )     [rows, F] with row pitches; F % 8 == 0
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ a,
+                  long rows, int F, long ldg, long ldu, long lda) {
+  const int nch = F >> 3;
+  const long total = rows * nch;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / nch;
+    const int c = static_cast<int>(i % nch);
+    float fg[8], fu[8], o[8];
+    ew_unpack8(ld_stream(g + r * ldg + c * 8), fg);
+    ew_unpack8(ld_stream(u + r * ldu + c * 8), fu);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = ew_round(fg[e] / (1.f + __expf(-fg[e]))) * fu[e];
+    st_stream(a + r * lda + c * 8, ew_pack8(o));
+  }
+}
+// dg = da * u * silu'(g),  du = da * silu(g)
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ u,
+                  __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ du, long rows, int F, long ldda, long ldg,
+                  long ldu, long lddg, long lddu) {
+  const int nch = F >> 3;
+  const long total = rows * nch;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / nch;
+    const int c = static_cast<int>(i % nch);
+    float fa[8], fg[8], fu[8], og[8], ou[8];
+    ew_unpack8(ld_stream(da + r * ldda + c * 8), fa);
+    ew_unpack8(ld_stream(g + r * ldg + c * 8), fg);
+    ew_unpack8(ld_stream(u + r * ldu + c * 8), fu);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sg = 1.f / (1.f + __expf(-fg[e]));
+      const float silu = fg[e] * sg;
+      ou[e] = fa[e] * silu;
+      og[e] = fa[e] * fu[e] * (sg * (1.f + fg[e] * (1.f - sg)));
+    }
+    st_stream(dg + r * lddg + c * 8, ew_pack8(og));
+    st_stream(du + r * lddu + c * 8, ew_pack8(ou));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm + adaLN
+// n = bf16(LN_noaffine(x)); y = bf16( bf16(n * bf16(1 + scale[b])) + shift[b] );  x [B*L, D], scale/shift [B, D]
+__global__ void __launch_bounds__(kEwThreads)
+ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ scale,
+                       const __nv_bfloat16* __restrict__ shift, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                       float* __restrict__ rstd_out, long rows, int L, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long b = row / L;
+  const int nch = D >> 3;
+  uint4 v[kEwMaxChunks];
+  float s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      v[i] = ld_stream(x + row * D + c * 8);
+      float f[8];
+      ew_unpack8(v[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s1 += f[e];
+    }
+  }
+  const float mean = warp_sum(s1) / static_cast<float>(D);
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      float f[8];
+      ew_unpack8(v[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s2 += (f[e] - mean) * (f[e] - mean);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(D) + eps);
+  if (lane == 0 && mean_out != nullptr) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      float f[8], sc[8], sh[8], o[8];
+      ew_unpack8(v[i], f);
+      ew_unpack8(*reinterpret_cast<const uint4*>(scale + b * D + c * 8), sc);
+      ew_unpack8(*reinterpret_cast<const uint4*>(shift + b * D + c * 8), sh);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float n = ew_round((f[e] - mean) * rstd);
+        o[e] = ew_round(n * ew_round(1.f + sc[e])) + sh[e];
+      }
+      st_stream(y + row * D + c * 8, ew_pack8(o));
+    }
+  }
+}
+// dx = LN_bwd(dy * (1 + scale));  dscale[b] += sum_l dy * n;  dshift[b] += sum_l dy   (fp32 atomics, [B, D])
+__global__ void __launch_bounds__(kEwThreads)
+ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                       const __nv_bfloat16* __restrict__ scale, const float* __restrict__ mean_in,
+                       const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
+                       float* __restrict__ dshift, long rows, int L, int D) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long b = row / L;
+  const int nch = D >> 3;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  uint4 vx[kEwMaxChunks], vg[kEwMaxChunks];
+  float sa = 0.f, sb = 0.f;   // sum(dn), sum(dn * n)
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      vx[i] = ld_stream(x + row * D + c * 8);
+      vg[i] = ld_stream(dy + row * D + c * 8);
+      float fx[8], fg[8], sc[8];
+      ew_unpack8(vx[i], fx);
+      ew_unpack8(vg[i], fg);
+      ew_unpack8(*reinterpret_cast<const uint4*>(scale + b * D + c * 8), sc);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float n = (fx[e] - mean) * rstd;
+        const float dn = fg[e] * (1.f + sc[e]);
+        sa += dn;
+        sb += dn * n;
+        if (dscale != nullptr) {
+          atomicAdd(dscale + b * D + c * 8 + e, fg[e] * n);
+          atomicAdd(dshift + b * D + c * 8 + e, fg[e]);
+        }
+      }
+    }
+  }
+  sa = warp_sum(sa) / static_cast<float>(D);
+  sb = warp_sum(sb) / static_cast<float>(D);
+#pragma unroll
+  for (int i = 0; i < kEwMaxChunks; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      float fx[8], fg[8], sc[8], o[8];
+      ew_unpack8(vx[i], fx);
+      ew_unpack8(vg[i], fg);
+      ew_unpack8(*reinterpret_cast<const uint4*>(scale + b * D + c * 8), sc);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float n = (fx[e] - mean) * rstd;
+        o[e] = rstd * (fg[e] * (1.f + sc[e]) - sa - n * sb);
+      }
+      st_stream(dx + row * D + c * 8, ew_pack8(o));
+    }
+  }
+}
+
+// y = bf16( x + bf16(h * gate[b]) )
+__global__ void __launch_bounds__(256)
+gate_residual_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ h,
+                         const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ y, long rows, int L, int D) {
+  const int nch = D >> 3;
+  const long total = rows * nch;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / nch;
+    const int c = static_cast<int>(i % nch);
+    float fx[8], fh[8], fg[8], o[8];
+    ew_unpack8(ld_stream(x + r * D + c * 8), fx);
+    ew_unpack8(ld_stream(h + r * D + c * 8), fh);
+    ew_unpack8(*reinterpret_cast<const uint4*>(gate + (r / L) * D + c * 8), fg);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = fx[e] + ew_round(fh[e] * fg[e]);
+    st_stream(y + r * D + c * 8, ew_pack8(o));
+  }
+}
+// dh = dy * gate[b];  dgate[b] += sum_l dy * h  (fp32 atomics);  dx = dy is the caller's alias
+__global__ void __launch_bounds__(kEwThreads)
+gate_residual_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
+                         const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ dh, float* __restrict__ dgate,
+                         long rows, int L, int D) {
+  const int nch = D >> 3;
+  const long total = rows * nch;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / nch;
+    const int c = static_cast<int>(i % nch);
+    const long b = r / L;
+    float fd[8], fh[8], fg[8], o[8];
+    ew_unpack8(ld_stream(dy + r * D + c * 8), fd);
+    ew_unpack8(ld_stream(h + r * D + c * 8), fh);
+    ew_unpack8(*reinterpret_cast<const uint4*>(gate + b * D + c * 8), fg);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = fd[e] * fg[e];
+      if (dgate != nullptr) atomicAdd(dgate + b * D + c * 8 + e, fd[e] * fh[e]);
+    }
+    st_stream(dh + r * D + c * 8, ew_pack8(o));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- patchify
+// img [B, C, Himg, Wimg]  <->  patches [B, (Himg/p)*(Wimg/p), C*p*p]
+//   order 0: patch vector ordered (c, py, px)   src/modules/patch.py:39-54 and the conv patch-embed weight
+//   order 1: patch vector ordered (py, px, c)   JiT._unpatchify, src/models/jit/denoiser.py:845-858
+// One thread per patch element of 2 bytes x `vec` contiguous pixels along px when order 0 (vec = gcd(p, 8)).
+template <bool kToPatches>
+__global__ void __launch_bounds__(256)
+patch_permute_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int B, int C, int Himg, int Wimg, int p,
+                     int order) {
+  const int hp = Himg / p, wp = Wimg / p;
+  const long total = static_cast<long>(B) * C * Himg * Wimg;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    // i enumerates the image in [B, C, Himg, Wimg] order (coalesced on the image side)
+    const int xw = static_cast<int>(i % Wimg);
+    const int yh = static_cast<int>((i / Wimg) % Himg);
+    const int c = static_cast<int>((i / (static_cast<long>(Wimg) * Himg)) % C);
+    const long b = i / (static_cast<long>(Wimg) * Himg * C);
+    const int py = yh % p, px = xw % p;
+    const long n = static_cast<long>(yh / p) * wp + xw / p;
+    const long e = order == 0 ? (static_cast<long>(c) * p + py) * p + px : (static_cast<long>(py) * p + px) * C + c;
+    const long j = (b * hp * wp + n) * (static_cast<long>(C) * p * p) + e;
+    if (kToPatches) dst[j] = src[i]; else dst[i] = src[j];
+  }
+}
+
+}  // namespace vpt

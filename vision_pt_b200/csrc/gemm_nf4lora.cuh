@@ -47,6 +47,8 @@ struct GemmParams {
   __nv_bfloat16* D;
   int ldd;
   const __nv_bfloat16* bias;    // [NO] or nullptr
+  const __nv_bfloat16* residual;  // [M, NO] (pitch ldr) added in the epilogue, or nullptr
+  int ldr;
   Nf4Weight w;
   const __nv_bfloat16* lora_down;  // [16, K]
   const __nv_bfloat16* lora_up;    // [N, 16]
@@ -317,14 +319,25 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_wait_ld();
         if (m < p.M) {
           __nv_bfloat16* drow = p.D + static_cast<size_t>(m) * p.ldd + o0 + c * 32;
+          const __nv_bfloat16* rrow = p.residual ? p.residual + static_cast<size_t>(m) * p.ldr + o0 + c * 32 : nullptr;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = o0 + c * 32 + g * 8;
+            uint32_t rr[4] = {0, 0, 0, 0};
+            if (rrow != nullptr) {
+              if (col + 8 <= p.NO) {
+                const uint4 t4 = *reinterpret_cast<const uint4*>(rrow + g * 8);
+                rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
+              } else {
+                for (int e = 0; e < 8 && col + e < p.NO; ++e)
+                  rr[e >> 1] |= static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(rrow)[g * 8 + e]) << (16 * (e & 1));
+              }
+            }
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a = __uint_as_float(v[g * 8 + 2 * e]) + s_bias[c * 32 + g * 8 + 2 * e];
-              const float b = __uint_as_float(v[g * 8 + 2 * e + 1]) + s_bias[c * 32 + g * 8 + 2 * e + 1];
+              const float a = __uint_as_float(v[g * 8 + 2 * e]) + s_bias[c * 32 + g * 8 + 2 * e] + bf16lo(rr[e]);
+              const float b = __uint_as_float(v[g * 8 + 2 * e + 1]) + s_bias[c * 32 + g * 8 + 2 * e + 1] + bf16hi(rr[e]);
               o[e] = pack_bf16x2(a, b);
             }
             if (col + 8 <= p.NO) {

@@ -1,0 +1,175 @@
+// Standalone NF4 kernels: bit-exact dequantisation (what bitsandbytes' dequantize_blockwise + dequantize_4bit produce
+// for `BnbLinear4bit`, /root/reference/src/modules/quant/bnb.py:37-129) and setup-time quantisation
+// (quantize_4bit with compress_statistics=True, /root/reference/src/modules/quant/functional.py:342-371).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpt {
+
+enum { kDtBf16 = 0, kDtF16 = 1, kDtF32 = 2 };
+
+// absmax[i] = fl32( fl32(nested_code[q[i]] * nested_absmax[i / 256]) + offset )
+__global__ void nf4_absmax_kernel(const uint8_t* __restrict__ q, const float* __restrict__ nested_absmax,
+                                  const float* __restrict__ nested_code, float offset, float* __restrict__ absmax, long nb) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < nb) absmax[i] = __fadd_rn(__fmul_rn(nested_code[q[i]], nested_absmax[i >> 8]), offset);
+}
+
+template <int kDt>
+__device__ __forceinline__ void nf4_store2(void* out, long idx, float a, float b) {
+  if (kDt == kDtBf16) {
+    reinterpret_cast<__nv_bfloat162*>(out)[idx >> 1] = __floats2bfloat162_rn(a, b);
+  } else if (kDt == kDtF16) {
+    reinterpret_cast<__half2*>(out)[idx >> 1] = __floats2half2_rn(a, b);
+  } else {
+    reinterpret_cast<float2*>(out)[idx >> 1] = make_float2(a, b);
+  }
+}
+
+// One thread per packed byte pair group: 4 bytes -> 8 weights.  n = number of weights (even).
+template <int kDt>
+__global__ void __launch_bounds__(256)
+nf4_dequant_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ qabsmax,
+                   const float* __restrict__ nested_absmax, const float* __restrict__ nested_code,
+                   const float* __restrict__ code, float offset, void* __restrict__ out, long n) {
+  __shared__ float s_code[16];
+  __shared__ float s_ncode[256];
+  if (threadIdx.x < 16) s_code[threadIdx.x] = code[threadIdx.x];
+  s_ncode[threadIdx.x] = nested_code[threadIdx.x];
+  __syncthreads();
+  const long nbytes = (n + 1) >> 1;
+  for (long byte0 = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; byte0 < nbytes;
+       byte0 += static_cast<long>(gridDim.x) * blockDim.x * 4) {
+    const long e0 = byte0 * 2;                       // 8 weights, all in one 64-block (e0 % 8 == 0)
+    const long blk = e0 >> 6;
+    const float am = __fadd_rn(__fmul_rn(s_ncode[qabsmax[blk]], nested_absmax[blk >> 8]), offset);
+    uint32_t w;
+    if (byte0 + 4 <= nbytes) {
+      w = *reinterpret_cast<const uint32_t*>(packed + byte0);
+    } else {
+      w = 0;
+      for (int b = 0; byte0 + b < nbytes; ++b) w |= static_cast<uint32_t>(packed[byte0 + b]) << (8 * b);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const long e = e0 + 2 * b;
+      if (e >= n) break;
+      const uint32_t byte = (w >> (8 * b)) & 0xffu;
+      const float hi = __fmul_rn(s_code[byte >> 4], am);
+      const float lo = __fmul_rn(s_code[byte & 15u], am);
+      if (e + 1 < n) {
+        nf4_store2<kDt>(out, e, hi, lo);
+      } else {
+        if (kDt == kDtBf16) reinterpret_cast<__nv_bfloat16*>(out)[e] = __float2bfloat16_rn(hi);
+        else if (kDt == kDtF16) reinterpret_cast<__half*>(out)[e] = __float2half_rn(hi);
+        else reinterpret_cast<float*>(out)[e] = hi;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- quantise
+template <int kDt>
+__device__ __forceinline__ float nf4_load(const void* w, long i) {
+  if (kDt == kDtBf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(w)[i]);
+  if (kDt == kDtF16) return __half2float(reinterpret_cast<const __half*>(w)[i]);
+  return reinterpret_cast<const float*>(w)[i];
+}
+// dQuantizeNF4: strict ">" against the midpoints of neighbouring code values
+__device__ __forceinline__ uint32_t nf4_code_of(float x) {
+  const float t[15] = {-0.8480964004993439f, -0.6106329262256622f, -0.4599952697753906f, -0.33967943489551544f,
+                       -0.23460740596055984f, -0.13791173323988914f, -0.045525018125772476f, 0.03979014977812767f,
+                       0.1202552504837513f, 0.2035212516784668f, 0.2920137718319893f, 0.3893125355243683f,
+                       0.5016634166240692f, 0.6427869200706482f, 0.8614784181118011f};
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 15; ++i) c += x > t[i] ? 1u : 0u;
+  return c;
+}
+// 8 lanes per 64-weight block: absmax, then 8 codes per lane -> 4 packed bytes.  n % 64 == 0.
+template <int kDt>
+__global__ void __launch_bounds__(256)
+nf4_quantize_kernel(const void* __restrict__ w, uint8_t* __restrict__ packed, float* __restrict__ absmax, long nblocks) {
+  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool live = g < nblocks;
+  float v[8];
+  float m = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v[e] = live ? nf4_load<kDt>(w, g * 64 + sub * 8 + e) : 0.f;
+    m = fmaxf(m, fabsf(v[e]));
+  }
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+  if (!live) return;
+  if (sub == 0) absmax[g] = m;
+  const float inv = __fdiv_rn(1.0f, m);
+  uint32_t out = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const uint32_t hi = nf4_code_of(__fmul_rn(v[2 * b], inv)), lo = nf4_code_of(__fmul_rn(v[2 * b + 1], inv));
+    out |= ((hi << 4) | lo) << (8 * b);
+  }
+  *reinterpret_cast<uint32_t*>(packed + g * 32 + sub * 4) = out;
+}
+// offset = mean(absmax) with a fixed summation order (single CTA, double accumulation)
+__global__ void __launch_bounds__(1024) nf4_mean_kernel(const float* __restrict__ absmax, long nb, float* __restrict__ offset) {
+  __shared__ double s[1024];
+  double acc = 0.0;
+  for (long i = threadIdx.x; i < nb; i += 1024) acc += static_cast<double>(absmax[i]);
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *offset = static_cast<float>(s[0] / static_cast<double>(nb));
+}
+// dQuantize<0>: binary search in the sorted 256-entry code, then the midpoint rule
+__device__ __forceinline__ uint8_t nf4_nearest8(const float* code, float x) {
+  int pivot = 127, upper_pivot = 255, lower_pivot = 0;
+  float lower = -1.0f, upper = 1.0f, val = code[pivot];
+  for (int i = 64; i > 0; i >>= 1) {
+    if (x > val) {
+      lower_pivot = pivot;
+      lower = val;
+      pivot += i;
+    } else {
+      upper_pivot = pivot;
+      upper = val;
+      pivot -= i;
+    }
+    val = code[pivot];
+  }
+  if (upper_pivot == 255) upper = code[upper_pivot];
+  if (lower_pivot == 0) lower = code[lower_pivot];
+  if (x > val) return x > (upper + val) * 0.5f ? upper_pivot : pivot;
+  return x < (lower + val) * 0.5f ? lower_pivot : pivot;
+}
+// one CTA of 256 threads per nested block of 256 statistics
+__global__ void __launch_bounds__(256)
+nf4_nested_quantize_kernel(const float* __restrict__ absmax, const float* __restrict__ offset_p,
+                           const float* __restrict__ nested_code, uint8_t* __restrict__ q, float* __restrict__ nested_absmax,
+                           long nb) {
+  __shared__ float s_code[256];
+  __shared__ float s_red[256];
+  s_code[threadIdx.x] = nested_code[threadIdx.x];
+  const long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
+  const float v = i < nb ? __fsub_rn(absmax[i], *offset_p) : 0.f;
+  s_red[threadIdx.x] = fabsf(v);
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] = fmaxf(s_red[threadIdx.x], s_red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const float m = s_red[0];
+  if (threadIdx.x == 0) nested_absmax[blockIdx.x] = m;
+  if (i < nb) q[i] = nf4_nearest8(s_code, __fmul_rn(v, __fdiv_rn(1.0f, m)));
+}
+
+}  // namespace vpt

@@ -1,0 +1,547 @@
+"""Torch-facing wrappers of the C ABI: raw launches (no autograd) and the autograd Functions built from them.
+
+PyTorch only owns memory and streams here; every computation is a kernel of libvptb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import AttnTensorC, LinearArgsC, Nf4WeightC
+
+RANK = 16  # LoRA rank of the fused kernels; smaller ranks are zero-padded
+
+_DT = {torch.bfloat16: _lib.VPT_BF16, torch.float16: _lib.VPT_F16, torch.float32: _lib.VPT_F32}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: torch.Tensor | None) -> C.c_void_p | None:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts: torch.Tensor | None) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vision_pt_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """[..., D] -> 2-D [rows, D] view with unit inner stride and a row pitch that is a multiple of 8 elements."""
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(1) != 1 or (t2.shape[0] > 1 and t2.stride(0) % 8 != 0) or t2.data_ptr() % 16 != 0:
+        t2 = t2.contiguous()
+    return t2
+
+
+# ------------------------------------------------------------------------------------------------------- NF4
+@dataclass
+class Nf4Tensors:
+    """Device tensors of one bitsandbytes NF4 weight (see include/vptb200.h: vpt_nf4_weight)."""
+    packed: torch.Tensor         # uint8 [(N*K+1)//2, 1]
+    absmax: torch.Tensor         # uint8 [N*K/64]
+    nested_absmax: torch.Tensor  # fp32
+    nested_code: torch.Tensor    # fp32 [256]
+    code: torch.Tensor           # fp32 [16]
+    offset: float
+    shape: tuple[int, int]
+    dtype: torch.dtype
+
+    def c_struct(self) -> Nf4WeightC:
+        return Nf4WeightC(_p(self.packed), _p(self.absmax), _p(self.nested_absmax), _p(self.nested_code), _p(self.code),
+                          float(self.offset), int(self.shape[0]), int(self.shape[1]))
+
+    def to(self, device) -> "Nf4Tensors":
+        return Nf4Tensors(self.packed.to(device), self.absmax.to(device), self.nested_absmax.to(device),
+                          self.nested_code.to(device), self.code.to(device), self.offset, self.shape, self.dtype)
+
+
+def nf4_dequantize(w: Nf4Tensors, out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    _need_cuda(w.packed)
+    dt = out_dtype or w.dtype
+    n = w.shape[0] * w.shape[1]
+    out = torch.empty(w.shape, dtype=dt, device=w.packed.device)
+    ws = w.c_struct()
+    _lib.call("vpt_nf4_dequant", C.byref(ws), n, _DT[dt], _p(out), _stream())
+    return out
+
+
+def nf4_quantize(weight: torch.Tensor, nested_code: torch.Tensor, code: torch.Tensor) -> Nf4Tensors:
+    """quantize_4bit(weight, quant_type='nf4', blocksize=64, compress_statistics=True) on the GPU."""
+    _need_cuda(weight)
+    w = weight.detach().contiguous()
+    n = w.numel()
+    if n % 64 != 0:
+        raise ValueError("NF4 quantisation needs a multiple of 64 elements")
+    dev = w.device
+    nb = n // 64
+    packed = torch.empty((n // 2, 1), dtype=torch.uint8, device=dev)
+    qabs = torch.empty(nb, dtype=torch.uint8, device=dev)
+    nested = torch.empty((nb + 255) // 256, dtype=torch.float32, device=dev)
+    offset = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = torch.empty(nb, dtype=torch.float32, device=dev)
+    ncode = nested_code.to(device=dev, dtype=torch.float32).contiguous()
+    _lib.call("vpt_nf4_quantize", _p(w), _DT[w.dtype], n, _p(ncode), _p(packed), _p(qabs), _p(nested), _p(offset), _p(ws),
+              _stream())
+    return Nf4Tensors(packed, qabs, nested, ncode, code.to(device=dev, dtype=torch.float32).contiguous(),
+                      float(offset.item()), (int(weight.shape[0]), int(weight.shape[1])), weight.dtype)
+
+
+# ------------------------------------------------------------------------------------------------------- linear
+def _pad_rank(down: torch.Tensor | None, up: torch.Tensor | None):
+    if down is None:
+        return None, None
+    r = down.shape[0]
+    if r == RANK:
+        return down.contiguous(), up.contiguous()
+    if r > RANK:
+        raise NotImplementedError(f"the fused NF4-LoRA kernel handles rank <= {RANK}, got {r}")
+    d = down.new_zeros(RANK, down.shape[1])
+    d[:r] = down
+    u = up.new_zeros(up.shape[0], RANK)
+    u[:, :r] = up
+    return d, u
+
+
+def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, scale: float, residual=None,
+               want_side: bool = False, backward: bool = False, tile_n: int = 0):
+    """One launch of the fused kernel.  forward: x2 [M,K] -> y [M,N]; backward: x2 = dy [M,N] -> dx [M,K].
+    `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None)."""
+    _need_cuda(x2)
+    if x2.dtype != torch.bfloat16:
+        raise TypeError("fused linear runs in bfloat16")
+    args = LinearArgsC()
+    if isinstance(w, Nf4Tensors):
+        args.w = w.c_struct()
+        N, K = w.shape
+        args.w_bf16 = None
+    else:
+        N, K = w.shape
+        args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K))
+        args.w_bf16 = _p(w)
+    M = x2.shape[0]
+    n_out = K if backward else N
+    ld_out = (n_out + 7) // 8 * 8
+    out_full = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x2.device)
+    out = out_full[:, :n_out] if ld_out != n_out else out_full
+    side = torch.empty((M, RANK), dtype=torch.bfloat16, device=x2.device) if (want_side and down is not None) else None
+    args.bias = _p(bias)
+    args.lora_down = _p(down)
+    args.lora_up = _p(up)
+    args.scale = float(scale)
+    args.inp = _p(x2)
+    args.ld_in = x2.stride(0) if M > 1 else x2.shape[1]
+    args.out = _p(out_full)
+    args.ld_out = ld_out
+    args.residual = _p(residual)
+    args.ld_res = residual.stride(0) if residual is not None and M > 1 else n_out
+    args.side = _p(side)
+    args.M = M
+    args.tile_n = tile_n
+    _lib.call("vpt_nf4lora_linear_bwd_dx" if backward else "vpt_nf4lora_linear_fwd", C.byref(args), _stream())
+    return out, side
+
+
+def lora_grad_raw(src2: torch.Tensor, small: torch.Tensor, out_f32: torch.Tensor, transposed: bool) -> None:
+    """out_f32 += src2^T small   ([P,16], or [16,P] when transposed)."""
+    M, P = src2.shape
+    ld_out = out_f32.shape[1] if transposed else RANK
+    _lib.call("vpt_lora_grad", _p(src2), src2.stride(0) if M > 1 else P, _p(small), _p(out_f32), M, P, int(transposed),
+              ld_out, _stream())
+
+
+class NF4LoRALinearFn(torch.autograd.Function):
+    """y = x W^T + b + (alpha/r) (x A^T) B^T with W in NF4 (or bf16) -- LoRALinear over BnbLinear4bit."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, down, up, scale, residual):
+        K = x.shape[-1]
+        in_dtype = x.dtype
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        x2 = _rows(xb)
+        rank = 0 if down is None else down.shape[0]
+        dpad, upad = _pad_rank(down, up)
+        res2 = _rows(residual) if residual is not None else None
+        bias_b = None if bias is None else bias.to(torch.bfloat16)
+        y, side = linear_raw(x2, w, bias_b, dpad, upad, scale, res2, want_side=down is not None)
+        ctx.w, ctx.scale, ctx.rank, ctx.in_dtype = w, scale, rank, in_dtype
+        ctx.has_res = residual is not None
+        ctx.bias_grad = bias is not None and bias.requires_grad
+        ctx.save_for_backward(x2, side, dpad, upad)
+        N = y.shape[1]
+        y = y.reshape(*x.shape[:-1], N)
+        return y if in_dtype == torch.bfloat16 else y.to(in_dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, side, dpad, upad = ctx.saved_tensors
+        N = dy.shape[-1]
+        dy2 = _rows(dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16))
+        dx = ddown = dup = dbias = None
+        lora = dpad is not None
+        need_lora_grad = lora and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        dside = None
+        if ctx.needs_input_grad[0] or need_lora_grad:
+            dx2, dside = linear_raw(dy2, ctx.w, None, dpad, upad, ctx.scale, None, want_side=lora, backward=True)
+            if ctx.needs_input_grad[0]:
+                dx = dx2.reshape(*dy.shape[:-1], x2.shape[1])
+                if ctx.in_dtype != torch.bfloat16:
+                    dx = dx.to(ctx.in_dtype)
+        if need_lora_grad:
+            K = x2.shape[1]
+            gup = torch.zeros((N, RANK), dtype=torch.float32, device=dy2.device)
+            gdown = torch.zeros((RANK, K), dtype=torch.float32, device=dy2.device)
+            lora_grad_raw(dy2, side, gup, transposed=False)
+            lora_grad_raw(x2, dside, gdown, transposed=True)
+            dup = gup[:, :ctx.rank].to(upad.dtype)
+            ddown = gdown[:ctx.rank].to(dpad.dtype)
+        if ctx.bias_grad:
+            dbias = dy2.float().sum(0).to(dy.dtype)
+        dres = dy if ctx.has_res else None
+        return dx, None, dbias, ddown, dup, None, dres
+
+
+def nf4_lora_linear(x, w, bias=None, lora_down=None, lora_up=None, scale: float = 1.0, residual=None):
+    return NF4LoRALinearFn.apply(x, w, bias, lora_down, lora_up, scale, residual)
+
+
+# ------------------------------------------------------------------------------------------------------- attention
+def _at(t: torch.Tensor) -> AttnTensorC:
+    # logical layout (B, H, L, 64); any strides with a contiguous last dimension
+    return AttnTensorC(_p(t), t.stride(0), t.stride(2), t.stride(1))
+
+
+def _attn_ok(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.bfloat16:
+        raise TypeError("attention kernels run in bfloat16")
+    if t.shape[-1] != 64:
+        raise NotImplementedError("the sm_100a attention kernels are built for head_dim 64")
+    if t.stride(3) != 1 or any(s % 8 for s in t.stride()[:3]) or t.data_ptr() % 16:
+        t = t.contiguous()
+    return t
+
+
+def attn_fwd_raw(q, k, v, seqlens_k, scale: float):
+    """q,k,v: [B,H,L,64] views.  Returns (o [B,H,Lq,64] view over token-major memory, lse2 [B,H,Lq])."""
+    B, H, Lq, _ = q.shape
+    Lk = k.shape[2]
+    o = torch.empty((B, Lq, H, 64), dtype=torch.bfloat16, device=q.device).permute(0, 2, 1, 3)
+    lse2 = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    tq, tk, tv, to = _at(q), _at(k), _at(v), _at(o)
+    _lib.call("vpt_attn_fwd", C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, _p(seqlens_k),
+              float(scale), _p(lse2), _stream())
+    return o, lse2
+
+
+def attn_bwd_raw(q, k, v, o, d_o, lse2, seqlens_k, scale: float):
+    """Returns (dq fp32, dk bf16, dv bf16), each a [B,H,L,64] view over token-major memory."""
+    B, H, Lq, _ = q.shape
+    Lk = k.shape[2]
+    dev = q.device
+    dq = torch.zeros((B, Lq, H, 64), dtype=torch.float32, device=dev).permute(0, 2, 1, 3)
+    dk = torch.empty((B, Lk, H, 64), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
+    dv = torch.empty((B, Lk, H, 64), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
+    delta = torch.empty((B, H, Lq), dtype=torch.float32, device=dev)
+    ts = [_at(t) for t in (q, k, v, o, d_o, dq, dk, dv)]
+    _lib.call("vpt_attn_bwd", *[C.byref(t) for t in ts], B, H, Lq, Lk, _p(seqlens_k), float(scale), _p(lse2), _p(delta),
+              _stream())
+    return dq, dk, dv
+
+
+class AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, seqlens_k, scale):
+        q, k, v = _attn_ok(q), _attn_ok(k), _attn_ok(v)
+        o, lse2 = attn_fwd_raw(q, k, v, seqlens_k, scale)
+        ctx.save_for_backward(q, k, v, o, lse2, seqlens_k)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse2, seqlens_k = ctx.saved_tensors
+        dq, dk, dv = attn_bwd_raw(q, k, v, o, _attn_ok(d_o), lse2, seqlens_k, ctx.scale)
+        return dq.to(torch.bfloat16), dk, dv, None, None
+
+
+def attention(q, k, v, seqlens_k=None, scale: float | None = None):
+    """softmax(q k^T * scale + key-padding mask) v for [B,H,L,64] bf16 tensors; seqlens_k int32 [B] or None."""
+    _need_cuda(q, k, v)
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    return AttentionFn.apply(q, k, v, seqlens_k, float(scale))
+
+
+# ------------------------------------------------------------------------------------------------------- norms
+def rmsnorm_fwd_raw(x2, w, eps: float, want_rstd: bool = True):
+    rows, D = x2.shape
+    y = torch.empty((rows, D), dtype=torch.bfloat16, device=x2.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device) if want_rstd else None
+    _lib.call("vpt_rmsnorm_fwd", _p(x2), _p(w), _p(y), _p(rstd), rows, D, x2.stride(0) if rows > 1 else D, D, float(eps),
+              _stream())
+    return y, rstd
+
+
+def rmsnorm_bwd_raw(dy2, x2, w, rstd, dres2, eps: float, dw=None):
+    rows, D = x2.shape
+    assert dy2.is_contiguous() and x2.is_contiguous() and (dres2 is None or dres2.is_contiguous())
+    dx = torch.empty((rows, D), dtype=torch.bfloat16, device=x2.device)
+    _lib.call("vpt_rmsnorm_bwd", _p(dy2), _p(x2), _p(w), _p(rstd), _p(dres2), _p(dx), _p(dw), rows, D, D, float(eps),
+              _stream())
+    return dx
+
+
+class RMSNormFn(torch.autograd.Function):
+    """FP32RMSNorm.forward: bf16(rms_norm(x.float()) * w)."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        if x.dtype != torch.bfloat16:
+            raise TypeError("fused RMSNorm runs on bfloat16 activations")
+        D = x.shape[-1]
+        if D == 64 and x.dim() == 4:
+            x2 = x.contiguous().reshape(-1, D)
+        else:
+            x2 = _rows(x)
+        wb = None if w is None else w.to(torch.bfloat16)
+        y, rstd = rmsnorm_fwd_raw(x2, wb, eps)
+        ctx.save_for_backward(x2.contiguous(), wb, rstd)
+        ctx.eps = eps
+        ctx.w_grad = w is not None and w.requires_grad
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, rstd = ctx.saved_tensors
+        dy2 = dy.to(torch.bfloat16).reshape(x2.shape).contiguous()
+        dw = torch.zeros(x2.shape[1], dtype=torch.float32, device=x2.device) if ctx.w_grad else None
+        dx = rmsnorm_bwd_raw(dy2, x2, wb, rstd, None, ctx.eps, dw)
+        return dx.reshape(dy.shape), (dw.to(wb.dtype) if dw is not None else None), None
+
+
+def rms_norm(x, weight, eps: float = 1e-6):
+    _need_cuda(x)
+    return RMSNormFn.apply(x, weight, eps)
+
+
+def qknorm_rope_fwd_raw(x2, w, cos_sin, H: int, L: int, eps: float):
+    tokens = x2.shape[0]
+    y = torch.empty((tokens, H * 64), dtype=torch.bfloat16, device=x2.device)
+    _lib.call("vpt_qknorm_rope_fwd", _p(x2), _p(w), _p(cos_sin), _p(y), tokens, H, L,
+              x2.stride(0) if tokens > 1 else H * 64, H * 64, float(eps), _stream())
+    return y
+
+
+def qknorm_rope_bwd_raw(dy2, x2, w, cos_sin, H: int, L: int, eps: float, dw=None):
+    tokens = x2.shape[0]
+    dx = torch.empty((tokens, H * 64), dtype=torch.bfloat16, device=x2.device)
+    _lib.call("vpt_qknorm_rope_bwd", _p(dy2), int(dy2.dtype == torch.float32), _p(x2), _p(w), _p(cos_sin), _p(dx), _p(dw),
+              tokens, H, L, dy2.stride(0) if tokens > 1 else H * 64, x2.stride(0) if tokens > 1 else H * 64, H * 64,
+              float(eps), _stream())
+    return dx
+
+
+class QKNormRopeFn(torch.autograd.Function):
+    """q_norm (RMS over head_dim) followed by apply_rope, on token-major [B, L, H, 64]."""
+
+    @staticmethod
+    def forward(ctx, x, w, cos_sin, eps):
+        B, L, H, hd = x.shape
+        x2 = _rows(x.reshape(B * L, H * hd))
+        wb = w.to(torch.bfloat16)
+        y = qknorm_rope_fwd_raw(x2, wb, cos_sin, H, L, eps)
+        ctx.save_for_backward(x2, wb, cos_sin)
+        ctx.dims = (B, L, H, hd, eps, w.requires_grad)
+        return y.reshape(B, L, H, hd)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, cos_sin = ctx.saved_tensors
+        B, L, H, hd, eps, wg = ctx.dims
+        dy2 = dy.reshape(B * L, H * hd)
+        if dy2.dtype not in (torch.float32, torch.bfloat16):
+            dy2 = dy2.to(torch.bfloat16)
+        dy2 = dy2.contiguous()
+        dw = torch.zeros(64, dtype=torch.float32, device=x2.device) if wg else None
+        dx = qknorm_rope_bwd_raw(dy2, x2, wb, cos_sin, H, L, eps, dw)
+        return dx.reshape(B, L, H, hd), (dw.to(wb.dtype) if dw is not None else None), None, None
+
+
+def qknorm_rope(x, weight, cos_sin, eps: float = 1e-6):
+    return QKNormRopeFn.apply(x, weight, cos_sin, eps)
+
+
+# ------------------------------------------------------------------------------------------------------- SwiGLU
+def swiglu_fwd_raw(g2, u2):
+    rows, F = g2.shape
+    ld = (F + 7) // 8 * 8
+    a_full = torch.zeros((rows, ld), dtype=torch.bfloat16, device=g2.device) if ld != F else \
+        torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
+    Fv = F // 8 * 8
+    _lib.call("vpt_swiglu_fwd", _p(g2), _p(u2), _p(a_full), rows, Fv, g2.stride(0), u2.stride(0), ld, _stream())
+    a = a_full[:, :F]
+    if Fv != F:  # ragged tail (F = 2730, 3413): a handful of columns
+        a[:, Fv:] = torch.nn.functional.silu(g2[:, Fv:F]) * u2[:, Fv:F]
+    return a
+
+
+def swiglu_bwd_raw(da2, g2, u2):
+    rows, F = g2.shape
+    ld = (F + 7) // 8 * 8
+    dg_full = torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
+    du_full = torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
+    Fv = F // 8 * 8
+    _lib.call("vpt_swiglu_bwd", _p(da2), _p(g2), _p(u2), _p(dg_full), _p(du_full), rows, Fv, da2.stride(0), g2.stride(0),
+              u2.stride(0), ld, ld, _stream())
+    dg, du = dg_full[:, :F], du_full[:, :F]
+    if Fv != F:
+        gt = g2[:, Fv:F].float()
+        sg = torch.sigmoid(gt)
+        dat = da2[:, Fv:F].float()
+        du[:, Fv:] = (dat * gt * sg).to(torch.bfloat16)
+        dg[:, Fv:] = (dat * u2[:, Fv:F].float() * (sg * (1 + gt * (1 - sg)))).to(torch.bfloat16)
+    return dg, du
+
+
+class SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, u):
+        g2, u2 = _rows(g), _rows(u)
+        a = swiglu_fwd_raw(g2, u2)
+        ctx.save_for_backward(g2, u2)
+        return a.reshape(g.shape)
+
+    @staticmethod
+    def backward(ctx, da):
+        g2, u2 = ctx.saved_tensors
+        dg, du = swiglu_bwd_raw(_rows(da), g2, u2)
+        return dg.reshape(da.shape), du.reshape(da.shape)
+
+
+def swiglu(g, u):
+    return SwiGLUFn.apply(g, u)
+
+
+# ------------------------------------------------------------------------------------------------------- adaLN
+class LNModulateFn(torch.autograd.Function):
+    """FP32LayerNorm(no affine)(x) * (1 + scale[:, None]) + shift[:, None]   x [B,L,D], scale/shift [B,D]."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, eps):
+        B, L, D = x.shape
+        xc, sc, sh = x.contiguous(), scale.contiguous(), shift.contiguous()
+        y = torch.empty_like(xc)
+        mean = torch.empty(B * L, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(B * L, dtype=torch.float32, device=x.device)
+        _lib.call("vpt_ln_modulate_fwd", _p(xc), _p(sc), _p(sh), _p(y), _p(mean), _p(rstd), B * L, L, D, float(eps), _stream())
+        ctx.save_for_backward(xc, sc, mean, rstd)
+        ctx.mod_grad = scale.requires_grad or shift.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, sc, mean, rstd = ctx.saved_tensors
+        B, L, D = xc.shape
+        dyc = dy.contiguous()
+        dx = torch.empty_like(xc)
+        dsc = dsh = None
+        if ctx.mod_grad:
+            dsc = torch.zeros((B, D), dtype=torch.float32, device=xc.device)
+            dsh = torch.zeros((B, D), dtype=torch.float32, device=xc.device)
+        _lib.call("vpt_ln_modulate_bwd", _p(dyc), _p(xc), _p(sc), _p(mean), _p(rstd), _p(dx), _p(dsc), _p(dsh), B * L, L, D,
+                  _stream())
+        return dx, (dsc.to(sc.dtype) if dsc is not None else None), (dsh.to(sc.dtype) if dsh is not None else None), None
+
+
+def ln_modulate(x, scale, shift, eps: float = 1e-5):
+    _need_cuda(x)
+    return LNModulateFn.apply(x, scale, shift, eps)
+
+
+class GateResidualFn(torch.autograd.Function):
+    """x + h * gate[:, None]   x,h [B,L,D], gate [B,D]."""
+
+    @staticmethod
+    def forward(ctx, x, h, gate):
+        B, L, D = x.shape
+        xc, hc, gc = x.contiguous(), h.contiguous(), gate.contiguous()
+        y = torch.empty_like(xc)
+        _lib.call("vpt_gate_residual_fwd", _p(xc), _p(hc), _p(gc), _p(y), B * L, L, D, _stream())
+        ctx.save_for_backward(hc, gc)
+        ctx.gate_grad = gate.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        hc, gc = ctx.saved_tensors
+        B, L, D = hc.shape
+        dyc = dy.contiguous()
+        dh = torch.empty_like(hc)
+        dg = torch.zeros((B, D), dtype=torch.float32, device=hc.device) if ctx.gate_grad else None
+        _lib.call("vpt_gate_residual_bwd", _p(dyc), _p(hc), _p(gc), _p(dh), _p(dg), B * L, L, D, _stream())
+        return dy, dh, (dg.to(gc.dtype) if dg is not None else None)
+
+
+def gate_residual(x, h, gate):
+    _need_cuda(x)
+    return GateResidualFn.apply(x, h, gate)
+
+
+# ------------------------------------------------------------------------------------------------------- patchify
+def _patch_call(name, src, dst, B, Cc, H, W, p, order):
+    if src.element_size() != 2:
+        raise TypeError("patchify kernels move 2-byte elements (bf16 / fp16)")
+    _lib.call(name, _p(src), _p(dst), B, Cc, H, W, p, order, _stream())
+
+
+class PatchifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, p, order):
+        B, Cc, H, W = image.shape
+        img = image.contiguous()
+        out = torch.empty((B, (H // p) * (W // p), Cc * p * p), dtype=image.dtype, device=image.device)
+        _patch_call("vpt_patchify", img, out, B, Cc, H, W, p, order)
+        ctx.meta = (B, Cc, H, W, p, order)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        B, Cc, H, W, p, order = ctx.meta
+        dc = d.contiguous()
+        out = torch.empty((B, Cc, H, W), dtype=d.dtype, device=d.device)
+        _patch_call("vpt_unpatchify", dc, out, B, Cc, H, W, p, order)
+        return out, None, None
+
+
+class UnpatchifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, patches, Cc, H, W, p, order):
+        B = patches.shape[0]
+        pc = patches.contiguous()
+        out = torch.empty((B, Cc, H, W), dtype=patches.dtype, device=patches.device)
+        _patch_call("vpt_unpatchify", pc, out, B, Cc, H, W, p, order)
+        ctx.meta = (B, Cc, H, W, p, order)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        B, Cc, H, W, p, order = ctx.meta
+        dc = d.contiguous()
+        out = torch.empty((B, (H // p) * (W // p), Cc * p * p), dtype=d.dtype, device=d.device)
+        _patch_call("vpt_patchify", dc, out, B, Cc, H, W, p, order)
+        return out, None, None, None, None, None
+
+
+def patchify_op(image, p: int, order: int = 0):
+    _need_cuda(image)
+    return PatchifyFn.apply(image, p, order)
+
+
+def unpatchify_op(patches, channels: int, height: int, width: int, p: int, order: int = 0):
+    _need_cuda(patches)
+    return UnpatchifyFn.apply(patches, channels, height, width, p, order)
