@@ -36,11 +36,20 @@ typedef struct {
   const float* code;            /* [16] */
   float offset;
   int32_t N, K;                 /* out_features, in_features */
+  /* ragged in_features (K % 64 != 0): row-aligned copy made once by vpt_nf4_repack; NULL / 0 otherwise */
+  const uint8_t* packed_rows;   /* [N, K_pad/2] */
+  const float* absmax_f32;      /* [ceil(N*K/64)] decoded statistics */
+  int32_t K_pad;                /* K rounded up to a multiple of 64 */
 } vpt_nf4_weight;
 
 /* bitsandbytes.functional.dequantize_4bit (called from bnb.nn.Linear4bit.forward -> MatMul4Bit, inherited by
  * BnbLinear4bit, src/modules/quant/bnb.py:37).  out: n elements of out_dtype.  Bit-exact. */
 int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream);
+
+/* Load-time repack of a weight whose in_features is not a multiple of 64 (the 2730 / 3413 wide SwiGLU hidden of JiT-L / -H):
+ * bitsandbytes packs the flattened tensor, so rows are not byte- or block-aligned.  Produces row-aligned codes and the
+ * decoded per-block statistics; dequantised values stay bit-identical.  No reference counterpart (layout only). */
+int vpt_nf4_repack(const vpt_nf4_weight* w, uint8_t* packed_rows, float* absmax_f32, int32_t K_pad, vpt_stream_t stream);
 
 /* bitsandbytes.functional.quantize_4bit(A, quant_type="nf4") with compress_statistics=True, as called by
  * quantize_state_dict (src/modules/quant/functional.py:362-368) and Params4bit._quantize on .cuda()
@@ -53,13 +62,14 @@ int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const float* nested_
  *   y = x W^T + bias + Ts lora_up^T (+ residual),   Ts = bf16(scale * x lora_down^T),   scale = alpha / rank
  * and the activation gradient of the same (MatMul4Bit.backward + autograd of the LoRA branch):
  *   dx = dy W + dTs lora_down (+ residual),         dTs = bf16(scale * dy lora_up)
- * rank is 16 (pad smaller ranks with zero rows/columns).  K % 64 == 0.  x/dy/y/dx are row-major with the given
+ * rank is 16 (pad smaller ranks with zero rows/columns).  K % 64 == 0 or a repacked weight.  x/dy/y/dx are row-major with the given
  * leading dimensions (multiples of 8 elements).  `side` receives Ts / dTs ([M,16] bf16) for the parameter gradients. */
 typedef struct {
   vpt_nf4_weight w;
   const void* w_bf16;          /* optional: [N,K] bf16 weight used instead of the NF4 tensors (unquantised Linear) */
   const void* bias;            /* [N] bf16 or NULL (forward only) */
-  const void* lora_down;       /* [16,K] bf16 or NULL (LoRA disabled) */
+  const void* lora_down;       /* [16,K] bf16 (row pitch ld_lora_down) or NULL (LoRA disabled) */
+  int64_t ld_lora_down;        /* multiple of 8 elements; columns >= K zero */
   const void* lora_up;         /* [N,16] bf16 */
   float scale;
   const void* in;              /* fwd: x [M,K];  bwd: dy [M,N] */

@@ -161,7 +161,8 @@ static bool run_case(const Problem& P, const Dev& d, bool bwd, bool nf4, bool lo
   g.p.M = M; g.p.NO = NO; g.p.R = R;
   g.p.D = d.out; g.p.ldd = NO;
   g.p.bias = bwd ? nullptr : d.bias;
-  g.p.w = Nf4Weight{d.packed, d.qabs, d.nested, d.ncode, d.code, P.offset, N, K};
+  g.p.w = Nf4Weight{d.packed, d.qabs, d.nested, d.ncode, d.code, P.offset, N, K, nullptr, nullptr, 0};
+  g.p.ld_down = K;
   g.p.lora_down = d.down; g.p.lora_up = d.up; g.p.scale = P.scale; g.p.side = d.side;
   if (dbg) {
     g.p.dbg_b_lbo = dbg[0]; g.p.dbg_b_sbo = dbg[1]; g.p.dbg_q_lbo = dbg[2];
@@ -270,7 +271,8 @@ static int bench_main(int only_k, int only_n, int only_bwd, int only_nf4, int on
             g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = bn;
             g.act = bwd ? dY : X; g.lda = R; g.w_bf16 = W;
             g.p.M = M; g.p.NO = NO; g.p.R = R; g.p.D = out; g.p.ldd = NO; g.p.bias = bwd ? nullptr : bias;
-            g.p.w = Nf4Weight{packed, qabs, nested, ncode, code, 0.02f, N, K};
+            g.p.w = Nf4Weight{packed, qabs, nested, ncode, code, 0.02f, N, K, nullptr, nullptr, 0};
+            g.p.ld_down = K;
             g.p.lora_down = down; g.p.lora_up = up; g.p.scale = 0.0625f; g.p.side = side;
             for (int i = 0; i < 3; ++i) if (launch_gemm(g, 0)) { printf("launch failed %s\n", last_error().c_str()); return 1; }
             CK(cudaDeviceSynchronize());

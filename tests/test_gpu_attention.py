@@ -1,0 +1,53 @@
+"""sm_100a attention forward / backward vs the oracle (explicit fp32 softmax) and the reference golden vector."""
+import pytest
+import torch
+
+from oracle import jit as oj
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,lens", [(2, 3, 330, 330, [330, 285]), (1, 2, 128, 128, None), (2, 2, 266, 266, None),
+                                           (2, 1, 200, 77, [77, 40]), (1, 2, 1100, 1100, [1093])])
+@pytest.mark.parametrize("layout", ["bhld", "blhd"])
+def test_attention_fwd_bwd(B, H, Lq, Lk, lens, layout):
+    from vision_pt_b200 import ops
+    torch.manual_seed(B * 100 + Lq)
+    mk = lambda L: torch.randn(B, H, L, 64).to(torch.bfloat16)
+    q, k, v, d_o = mk(Lq) * 1.5, mk(Lk) * 1.5, mk(Lk), mk(Lq)
+    seq = None if lens is None else torch.tensor(lens, dtype=torch.int32)
+
+    def dev(t):
+        if layout == "bhld":
+            return t.cuda().requires_grad_(True)
+        return t.permute(0, 2, 1, 3).contiguous().cuda().permute(0, 2, 1, 3).requires_grad_(True)
+
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    o = ops.attention(qg, kg, vg, None if seq is None else seq.cuda())
+    o.backward(d_o.cuda())
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    orf = oj.attention_explicit(qr, kr, vr, None if seq is None else seq.long())
+    orf.backward(d_o.float())
+    assert rel_err(o, orf) <= 2e-2
+    assert rel_err(qg.grad, qr.grad) <= 2e-2
+    assert rel_err(kg.grad, kr.grad) <= 2e-2
+    assert rel_err(vg.grad, vr.grad) <= 2e-2
+    if seq is not None:   # padded keys receive exactly zero gradient
+        for b, n in enumerate(lens):
+            if n < Lk:
+                assert kg.grad[b, :, n:].abs().max() == 0 and vg.grad[b, :, n:].abs().max() == 0
+
+
+def test_reference_sdpa_vector(golden):
+    """scaled_dot_product_attention(q, k, v, mask=[B,H,L,L] expanded key padding) of the reference, same call."""
+    from vision_pt_b200.modules.attention import scaled_dot_product_attention
+    g = golden["attention"]
+    B, H, L, _ = g["q"].shape
+    mask = g["key_mask"].bool().cuda().view(B, 1, 1, L).expand(-1, H, L, -1)   # what JiT's Attention builds
+    y = scaled_dot_product_attention(g["q"].cuda(), g["k"].cuda(), g["v"].cuda(), mask=mask)
+    assert y.shape == g["y"].shape and rel_err(y, g["y"]) <= 2e-2
+    with pytest.raises(NotImplementedError):
+        scaled_dot_product_attention(g["q"].cuda(), g["k"].cuda(), g["v"].cuda(), mask=torch.ones(B, H, L, L, dtype=torch.bool, device="cuda"))
+    with pytest.raises(ValueError):
+        scaled_dot_product_attention(g["q"].cuda(), g["k"].cuda(), g["v"].cuda(), backend="nope")

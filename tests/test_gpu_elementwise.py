@@ -1,0 +1,134 @@
+"""HBM-bound kernels vs the oracle (forward and backward), plus the reference golden vectors."""
+import pytest
+import torch
+
+from oracle import jit as oj
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,D", [(37, 128), (300, 768), (129, 1024), (65, 1280), (33, 2048), (10, 64)])
+def test_rmsnorm(rows, D):
+    from vision_pt_b200 import ops
+    torch.manual_seed(D)
+    x = (torch.randn(rows, D) * 2).to(torch.bfloat16)
+    w = (torch.randn(D) * 0.2 + 1).to(torch.bfloat16)
+    dy = torch.randn(rows, D).to(torch.bfloat16)
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    y = ops.rms_norm(xg, wg, 1e-6)
+    y.backward(dy.cuda())
+    assert rel_err(y, oj.rms_norm_fp32(x, w)) <= 1e-2
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    oj.rms_norm_fp32(xr, wr).backward(dy.float())
+    assert rel_err(xg.grad, xr.grad) <= 2e-2 and rel_err(wg.grad, wr.grad) <= 2e-2
+
+
+def test_rmsnorm_reference_vector(golden):
+    from vision_pt_b200.modules.norm import get_norm_layer
+    g = golden["rmsnorm"]
+    m = get_norm_layer("rms", 128, eps=1e-6).to(torch.bfloat16).cuda()
+    m.weight.data.copy_(g["w"])
+    got = m(g["x"].cuda()).cpu()
+    # one bf16 ulp at most: the kernel and ATen may round the fp32 rsqrt differently
+    assert (got.float() - g["y"].float()).abs().max() <= 2 ** -7 * g["y"].float().abs().max()
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 50, 2), (3, 330, 12), (1, 77, 16)])
+def test_qknorm_rope(B, L, H, golden):
+    from vision_pt_b200 import ops
+    cfg = golden["rope"]["cfg"]
+    torch.manual_seed(L)
+    ctx = 8
+    hp = 4
+    # any (height, width) whose token count is >= L works: take the table and cut it to L rows
+    f = oj.rope_freqs_cis(cfg, 16 * hp, 16 * ((L + hp - 1) // hp), ctx)[:L]
+    cs = torch.stack([f.real, f.imag], dim=-1).contiguous().float()
+    x = torch.randn(B, L, H, 64).to(torch.bfloat16)
+    w = (torch.randn(64) * 0.2 + 1).to(torch.bfloat16)
+    dy = torch.randn(B, L, H, 64).to(torch.bfloat16)
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    y = ops.qknorm_rope(xg, wg, cs.cuda(), 1e-6)
+    y.backward(dy.cuda())
+    ref = oj.apply_rope(oj.rms_norm_fp32(x.permute(0, 2, 1, 3), w), f).permute(0, 2, 1, 3)
+    assert rel_err(y, ref) <= 1e-2
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    oj.apply_rope(oj.rms_norm_fp32(xr.permute(0, 2, 1, 3), wr), f).permute(0, 2, 1, 3).backward(dy.float())
+    assert rel_err(xg.grad, xr.grad) <= 2e-2 and rel_err(wg.grad, wr.grad) <= 2e-2
+
+
+def test_rope_table_matches_reference(golden):
+    from vision_pt_b200.jit.config import DenoiserConfig
+    from vision_pt_b200.jit.denoiser import rope_table
+    g = golden["rope"]
+    t = rope_table(DenoiserConfig(**g["cfg"]), g["height"], g["width"], g["ctx"])
+    assert torch.equal(t[..., 0], g["freqs_cis"].real) and torch.equal(t[..., 1], g["freqs_cis"].imag)
+
+
+@pytest.mark.parametrize("rows,F", [(100, 2048), (33, 2730), (7, 341)])
+def test_swiglu(rows, F):
+    from vision_pt_b200 import ops
+    torch.manual_seed(F)
+    g, u, da = (torch.randn(rows, F).to(torch.bfloat16) for _ in range(3))
+    gg, ug = g.cuda().requires_grad_(True), u.cuda().requires_grad_(True)
+    a = ops.swiglu(gg, ug)
+    a.backward(da.cuda())
+    assert rel_err(a, oj.swiglu_gate(g, u)) <= 1e-2
+    gr, ur = g.float().requires_grad_(True), u.float().requires_grad_(True)
+    oj.swiglu_gate(gr, ur).backward(da.float())
+    assert rel_err(gg.grad, gr.grad) <= 2e-2 and rel_err(ug.grad, ur.grad) <= 2e-2
+
+
+@pytest.mark.parametrize("B,L,D", [(2, 37, 128), (3, 100, 768), (2, 65, 1280)])
+def test_adaln_modulate_and_gate(B, L, D):
+    from vision_pt_b200 import ops
+    torch.manual_seed(D + L)
+    x, h, dy = (torch.randn(B, L, D).to(torch.bfloat16) for _ in range(3))
+    sc, sh, gt = (torch.randn(B, D).to(torch.bfloat16) * 0.5 for _ in range(3))
+    leaves = [t.cuda().requires_grad_(True) for t in (x, sc, sh)]
+    y = ops.ln_modulate(*leaves, 1e-5)
+    y.backward(dy.cuda())
+    assert rel_err(y, oj.adaln_modulate(x, sc, sh)) <= 1e-2
+    refs = [t.float().requires_grad_(True) for t in (x, sc, sh)]
+    oj.adaln_modulate(*refs).backward(dy.float())
+    for a, b in zip(leaves, refs):
+        assert rel_err(a.grad, b.grad) <= 2e-2
+    leaves = [t.cuda().requires_grad_(True) for t in (x, h, gt)]
+    y = ops.gate_residual(*leaves)
+    y.backward(dy.cuda())
+    assert rel_err(y, oj.gate_residual(x, h, gt)) <= 1e-2
+    refs = [t.float().requires_grad_(True) for t in (x, h, gt)]
+    oj.gate_residual(*refs).backward(dy.float())
+    for a, b in zip(leaves, refs):
+        assert rel_err(a.grad, b.grad) <= 2e-2
+
+
+def test_adaln_reference_vector(golden):
+    from vision_pt_b200.modules.norm import adaln_gate_residual, adaln_modulate
+    g = golden["adaln"]
+    y = adaln_modulate(g["x"].cuda(), g["scale"].cuda(), g["shift"].cuda(), eps=1e-6)
+    assert rel_err(y, g["y"]) <= 1e-2
+    assert rel_err(adaln_gate_residual(g["x"].cuda(), g["y"].cuda(), g["gate"].cuda()), g["gated"]) <= 1e-2
+
+
+@pytest.mark.parametrize("B,C,H,W,p", [(1, 3, 256, 256, 4), (4, 16, 832, 1152, 2), (2, 3, 256, 256, 16), (2, 3, 512, 448, 16)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_patchify_bit_exact(B, C, H, W, p, order):
+    """reference tests/test_patch.py shapes: permutation kernels are bit-exact and inverse to each other."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(0)
+    img = torch.randn(B, C, H, W).to(torch.bfloat16)
+    pt = ops.patchify_op(img.cuda(), p, order)
+    assert torch.equal(pt.cpu(), oj.patchify(img, p, order))
+    back = ops.unpatchify_op(pt, C, H, W, p, order)
+    assert torch.equal(back.cpu(), img)
+
+
+def test_patch_module_api(golden):
+    from vision_pt_b200.modules.patch import patchify, unpatchify
+    g = golden["patchify"]
+    out = patchify(g["image"].cuda(), 16)
+    assert out.latent_height == 2 and out.latent_width == 3 and torch.equal(out.patches.cpu(), g["patches"])
+    assert torch.equal(unpatchify(out.patches, 2, 3, 16, 3).image.cpu(), g["image"])
+    with pytest.raises(ValueError):
+        patchify(torch.zeros(4, device="cuda"), 2)

@@ -1,0 +1,129 @@
+"""Host-side mirror of the reference API that needs no GPU: key selection, module swapping, key names, errors."""
+import pytest
+import torch
+import torch.nn as nn
+
+
+def test_get_target_keys_reference_lists():
+    """reference tests/test_utils.py:12-50 semantics: substring include, regex include, exclude wins."""
+    from vision_pt_b200.modules.state_dict import RegexMatch, get_target_keys
+    keys = ["model.layer1.attn.to_q", "model.layer1.attn.to_k", "model.layer1.mlp.fc", "model.layer2.attn.to_q", "head"]
+    assert sorted(get_target_keys(["attn"], [], keys)) == ["model.layer1.attn.to_k", "model.layer1.attn.to_q", "model.layer2.attn.to_q"]
+    assert sorted(get_target_keys(["attn"], ["to_k"], keys)) == ["model.layer1.attn.to_q", "model.layer2.attn.to_q"]
+    assert sorted(get_target_keys([RegexMatch(regex=r"model\.layer1\..*")], [RegexMatch(regex=r".*\.mlp\..*")], keys)) == \
+        ["model.layer1.attn.to_k", "model.layer1.attn.to_q"]
+    assert get_target_keys([], [], keys) == []
+
+
+class _Toy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.layer1 = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 64))
+        self.head = nn.Linear(64, 8)
+
+
+def test_peft_replacement_and_key_names():
+    """reference tests/test_peft.py:67-127: which layers are wrapped, what trains, adapter key names."""
+    from vision_pt_b200.modules.peft import LoRAConfig, LoRALinear, PeftTargetConfig, get_adapter_parameters
+    m = _Toy()
+    m.requires_grad_(False)
+    PeftTargetConfig(include_keys=["layer1"], exclude_keys=["layer1.2"], config=LoRAConfig(rank=4, alpha=2.0)).replace_to_peft_layer(m)
+    assert isinstance(m.layer1[0], LoRALinear) and isinstance(m.layer1[2], nn.Linear) and isinstance(m.head, nn.Linear)
+    lay = m.layer1[0]
+    assert lay.lora_down.weight.shape == (4, 64) and lay.lora_up.weight.shape == (128, 4)
+    assert torch.count_nonzero(lay.lora_up.weight) == 0 and torch.count_nonzero(lay.lora_down.weight) > 0
+    lay.requires_grad_(True)
+    trainable = sorted(n for n, p in m.named_parameters() if p.requires_grad)
+    assert trainable == ["layer1.0.lora_down.weight", "layer1.0.lora_up.weight"]
+    assert sorted(get_adapter_parameters(m)) == ["layer1.0.alpha", "layer1.0.lora_down.weight", "layer1.0.lora_up.weight"]
+    m.train()
+    assert not lay.linear.training
+    assert abs(lay.scale - 0.5) < 1e-12
+    with pytest.raises(ValueError):
+        PeftTargetConfig(include_keys=[], config=LoRAConfig(rank=4))
+
+
+def test_peft_weight_round_trip():
+    from vision_pt_b200.modules.peft import LoRAConfig, PeftTargetConfig, get_adapter_parameters, load_peft_weight
+    a, b = _Toy(), _Toy()
+    PeftTargetConfig(include_keys=["head"], config=LoRAConfig(rank=8, alpha=3.0)).replace_to_peft_layer(a)
+    nn.init.normal_(a.head.lora_up.weight)
+    sd = {k: v.clone() for k, v in get_adapter_parameters(a).items()}
+    load_peft_weight(b, sd)
+    assert torch.equal(b.head.lora_up.weight, a.head.lora_up.weight) and b.head.rank == 8 and abs(b.head.scale - 3.0 / 8) < 1e-6
+    with pytest.raises(ValueError):
+        load_peft_weight(_Toy(), {"x": torch.zeros(1)})
+
+
+def test_quant_registry_swaps_and_errors():
+    """reference tests/test_modules_quant.py:21-126 for the bnb_nf4 type; the other types are declared out of scope."""
+    from vision_pt_b200.modules.quant import (NF4Linear, get_quant_type_from_children_dict, replace_by_prequantized_weights,
+                                              replace_to_quant_linear, validate_quant_type)
+    m = _Toy()
+    replace_to_quant_linear(m, "bnb_nf4", ["layer1"])
+    assert isinstance(m.layer1[0], NF4Linear) and isinstance(m.layer1[2], NF4Linear) and not isinstance(m.head, NF4Linear)
+    assert isinstance(m.layer1[0], nn.Linear) and m.layer1[0].quant_type == "nf4"
+    assert m.layer1[0].weight.is_meta and not m.layer1[0].weight.requires_grad
+    with pytest.raises(ValueError):
+        validate_quant_type("int3")
+    with pytest.raises(NotImplementedError):
+        replace_to_quant_linear(_Toy(), "bnb_int8", ["head"])
+    sd = {"head.weight": torch.zeros(256, 1, dtype=torch.uint8), "head.weight.absmax": torch.zeros(8, dtype=torch.uint8),
+          "head.weight.quant_state.bitsandbytes__nf4": torch.zeros(4, dtype=torch.uint8), "layer1.0.weight": torch.zeros(128, 64)}
+    m2 = _Toy()
+    replace_by_prequantized_weights(m2, sd)
+    assert isinstance(m2.head, NF4Linear) and not isinstance(m2.layer1[0], NF4Linear)
+    assert get_quant_type_from_children_dict({"quant_state.bitsandbytes__nf4": torch.zeros(1)}) == "bnb_nf4"
+    with pytest.raises(ValueError):
+        get_quant_type_from_children_dict({"foo": torch.zeros(1)})
+    with pytest.raises(RuntimeError):
+        m.layer1[0](torch.zeros(2, 64))          # no quantised weight yet -> loud failure, never a silent fallback
+
+
+def test_prequantized_state_dict_loads_on_cpu():
+    from oracle import nf4 as on
+    from vision_pt_b200.modules.quant import NF4Linear
+    w = (torch.randn(64, 128) * 0.05).to(torch.bfloat16)
+    st = on.quantize_nf4(w)
+    sd = {"weight": st.packed, "bias": torch.zeros(64, dtype=torch.bfloat16)}
+    sd.update({f"weight.{k}": v for k, v in st.as_dict().items()})
+    lin = NF4Linear(128, 64)
+    lin.load_state_dict(sd, assign=True)
+    assert lin.is_quantized and lin.quant_state.shape == (64, 128) and lin.quant_state.dtype == torch.bfloat16
+    out = lin.state_dict()
+    assert set(out) == set(sd)
+    for k in sd:
+        assert torch.equal(out[k], sd[k]), k
+
+
+def test_cpu_tensors_are_rejected():
+    from vision_pt_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.rms_norm(torch.zeros(4, 64, dtype=torch.bfloat16), torch.ones(64, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        ops.attention(*(torch.zeros(1, 1, 8, 64, dtype=torch.bfloat16) for _ in range(3)))
+
+
+def test_key_lengths_from_mask():
+    from vision_pt_b200.modules.attention import key_lengths_from_mask
+    km = torch.tensor([[1, 1, 1, 0], [1, 1, 0, 0]], dtype=torch.bool)
+    assert key_lengths_from_mask(km, 2, 4).tolist() == [3, 2]
+    assert key_lengths_from_mask(km.view(2, 1, 1, 4).expand(-1, 3, 5, -1), 2, 4).tolist() == [3, 2]
+    assert key_lengths_from_mask(None, 2, 4) is None
+    with pytest.raises(NotImplementedError):
+        key_lengths_from_mask(torch.ones(2, 3, 5, 4, dtype=torch.bool), 2, 4)
+
+
+def test_jit_config_and_model_structure():
+    """Parameter names are the reference's (checkpoint / PEFT key compatibility): compare with the golden state dict."""
+    import os
+    from vision_pt_b200.jit import Denoiser, DenoiserConfig, JiT_B_16_Config
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.pt"), weights_only=False)["denoiser_f32"]
+    m = Denoiser(DenoiserConfig(**g["cfg"]))
+    assert set(m.state_dict()) == set(g["state"])
+    for k, v in m.state_dict().items():
+        assert v.shape == g["state"][k].shape, k
+    b = JiT_B_16_Config()
+    assert (b.hidden_size, b.depth, b.num_heads, b.context_start_block) == (768, 12, 12, 4)
+    with pytest.raises(AssertionError):
+        Denoiser(DenoiserConfig(hidden_size=128, num_heads=4, depth=1))   # rope dims must sum to head_dim

@@ -14,13 +14,14 @@ class Nf4WeightC(C.Structure):
     _fields_ = [
         ("packed", C.c_void_p), ("qabsmax", C.c_void_p), ("nested_absmax", C.c_void_p), ("nested_code", C.c_void_p),
         ("code", C.c_void_p), ("offset", C.c_float), ("N", C.c_int32), ("K", C.c_int32),
+        ("packed_rows", C.c_void_p), ("absmax_f32", C.c_void_p), ("K_pad", C.c_int32),
     ]
 
 
 class LinearArgsC(C.Structure):
     _fields_ = [
         ("w", Nf4WeightC), ("w_bf16", C.c_void_p), ("bias", C.c_void_p), ("lora_down", C.c_void_p),
-        ("lora_up", C.c_void_p), ("scale", C.c_float), ("inp", C.c_void_p), ("ld_in", C.c_int64), ("out", C.c_void_p),
+        ("ld_lora_down", C.c_int64), ("lora_up", C.c_void_p), ("scale", C.c_float), ("inp", C.c_void_p), ("ld_in", C.c_int64), ("out", C.c_void_p),
         ("ld_out", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64), ("side", C.c_void_p), ("M", C.c_int32),
         ("tile_n", C.c_int32),
     ]
@@ -36,6 +37,7 @@ _AT = C.POINTER(AttnTensorC)
 # name -> argtypes (the stream is always last); every function returns int
 SIGNATURES: dict[str, list] = {
     "vpt_nf4_dequant": [C.POINTER(Nf4WeightC), _I64, C.c_int, _P, _P],
+    "vpt_nf4_repack": [C.POINTER(Nf4WeightC), _P, _P, _I32, _P],
     "vpt_nf4_quantize": [_P, C.c_int, _I64, _P, _P, _P, _P, _P, _P, _P],
     "vpt_nf4lora_linear_fwd": [C.POINTER(LinearArgsC), _P],
     "vpt_nf4lora_linear_bwd_dx": [C.POINTER(LinearArgsC), _P],

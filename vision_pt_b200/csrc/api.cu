@@ -41,6 +41,18 @@ extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype
   return 0;
 }
 
+extern "C" int vpt_nf4_repack(const vpt_nf4_weight* w, uint8_t* packed_rows, float* absmax_f32, int32_t K_pad,
+                              vpt_stream_t stream) {
+  VPT_REQUIRE(w && packed_rows && absmax_f32 && w->packed && w->qabsmax, "vpt_nf4_repack: null pointer");
+  VPT_REQUIRE(K_pad % 64 == 0 && K_pad >= w->K && K_pad - w->K < 64, "vpt_nf4_repack: K_pad must be K rounded up to 64");
+  const long nb = (static_cast<long>(w->N) * w->K + 63) / 64;
+  nf4_absmax_kernel<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(w->qabsmax, w->nested_absmax, w->nested_code, w->offset, absmax_f32, nb);
+  nf4_repack_rows_kernel<<<blocks_for(static_cast<long>(w->N) * (K_pad / 2), 256, 148 * 32), 256, 0, S(stream)>>>(w->packed, packed_rows, w->N, w->K,
+                                                                                                                    K_pad);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const float* nested_code, uint8_t* packed,
                                 uint8_t* qabsmax, float* nested_absmax, float* offset_out, float* absmax_ws,
                                 vpt_stream_t stream) {
@@ -66,13 +78,22 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
   VPT_REQUIRE(a && a->in && a->out, "vpt_nf4lora_linear: null pointer");
   const int N = a->w.N, K = a->w.K;
   VPT_REQUIRE(N > 0 && K > 0 && a->M > 0, "vpt_nf4lora_linear: bad shape");
-  VPT_REQUIRE(K % 64 == 0, "vpt_nf4lora_linear: in_features must be a multiple of 64 (repack ragged weights first)");
   VPT_REQUIRE(a->ld_in % 8 == 0 && a->ld_out % 8 == 0, "vpt_nf4lora_linear: leading dimensions must be multiples of 8");
   const bool nf4 = a->w_bf16 == nullptr;
-  if (nf4) VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
+  const bool ragged = nf4 && a->w.packed_rows != nullptr;
+  if (nf4) {
+    VPT_REQUIRE(a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 code tables missing");
+    if (ragged) {
+      VPT_REQUIRE(a->w.absmax_f32 && a->w.K_pad % 64 == 0 && a->w.K_pad >= K, "vpt_nf4lora_linear: bad repacked weight");
+    } else {
+      VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax, "vpt_nf4lora_linear: NF4 tensors missing");
+      VPT_REQUIRE(K % 64 == 0, "vpt_nf4lora_linear: in_features must be a multiple of 64 (repack ragged weights with vpt_nf4_repack)");
+    }
+  } else {
+    VPT_REQUIRE(K % 8 == 0, "vpt_nf4lora_linear: a bf16 weight needs in_features % 8 == 0");
+  }
   const bool lora = a->lora_down != nullptr;
-  if (lora) VPT_REQUIRE(a->lora_up != nullptr, "vpt_nf4lora_linear: lora_up missing");
-  if (bwd) VPT_REQUIRE(N % 8 == 0, "vpt_nf4lora_linear_bwd_dx: out_features must be a multiple of 8");
+  if (lora) VPT_REQUIRE(a->lora_up != nullptr && a->ld_lora_down % 8 == 0 && a->ld_lora_down >= K, "vpt_nf4lora_linear: bad LoRA arguments");
   GemmLaunch g{};
   g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = a->tile_n;
   g.act = a->in; g.lda = static_cast<int>(a->ld_in); g.w_bf16 = a->w_bf16;
@@ -80,8 +101,10 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
   g.p.D = static_cast<__nv_bfloat16*>(a->out); g.p.ldd = static_cast<int>(a->ld_out);
   g.p.bias = bwd ? nullptr : static_cast<const __nv_bfloat16*>(a->bias);
   g.p.residual = static_cast<const __nv_bfloat16*>(a->residual); g.p.ldr = static_cast<int>(a->ld_res);
-  g.p.w = Nf4Weight{a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, N, K};
+  g.p.w = Nf4Weight{a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, N, K,
+                    a->w.packed_rows, a->w.absmax_f32, a->w.K_pad};
   g.p.lora_down = static_cast<const __nv_bfloat16*>(a->lora_down);
+  g.p.ld_down = static_cast<int>(a->ld_lora_down);
   g.p.lora_up = static_cast<const __nv_bfloat16*>(a->lora_up);
   g.p.scale = a->scale;
   g.p.side = static_cast<__nv_bfloat16*>(a->side);
@@ -153,15 +176,20 @@ extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void
 }
 extern "C" int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t rows, int32_t F, int64_t ldg, int64_t ldu,
                               int64_t lda, vpt_stream_t stream) {
-  VPT_REQUIRE(g && u && a && rows > 0 && F % 8 == 0 && ldg % 8 == 0 && ldu % 8 == 0 && lda % 8 == 0, "vpt_swiglu_fwd: bad arguments");
-  swiglu_fwd_kernel<<<blocks_for(rows * (F / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(g), BF(u), BFM(a), rows, F, ldg, ldu, lda);
+  const int64_t f8 = (F + 7) / 8 * 8;
+  VPT_REQUIRE(g && u && a && rows > 0 && F > 0 && ldg % 8 == 0 && ldu % 8 == 0 && lda % 8 == 0 && ldg >= f8 && ldu >= f8 && lda >= f8,
+              "vpt_swiglu_fwd: bad arguments (row pitches must be multiples of 8 and cover F rounded up to 8)");
+  swiglu_fwd_kernel<<<blocks_for(rows * (f8 / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(g), BF(u), BFM(a), rows, F, ldg, ldu, lda);
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }
 extern "C" int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void* dg, void* du, int64_t rows, int32_t F,
                               int64_t ldda, int64_t ldg, int64_t ldu, int64_t lddg, int64_t lddu, vpt_stream_t stream) {
-  VPT_REQUIRE(da && g && u && dg && du && rows > 0 && F % 8 == 0, "vpt_swiglu_bwd: bad arguments");
-  swiglu_bwd_kernel<<<blocks_for(rows * (F / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(da), BF(g), BF(u), BFM(dg), BFM(du), rows, F, ldda, ldg, ldu, lddg, lddu);
+  const int64_t f8 = (F + 7) / 8 * 8;
+  VPT_REQUIRE(da && g && u && dg && du && rows > 0 && F > 0 && ldda >= f8 && ldg >= f8 && ldu >= f8 && lddg >= f8 && lddu >= f8 &&
+                  (ldda | ldg | ldu | lddg | lddu) % 8 == 0,
+              "vpt_swiglu_bwd: bad arguments");
+  swiglu_bwd_kernel<<<blocks_for(rows * (f8 / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(da), BF(g), BF(u), BFM(dg), BFM(du), rows, F, ldda, ldg, ldu, lddg, lddu);
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }

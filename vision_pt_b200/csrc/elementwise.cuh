@@ -242,11 +242,12 @@ qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------- SwiGLU gate
-// a = bf16( bf16(silu(g)) * u )     [rows, F] with row pitches; F % 8 == 0
+// a = bf16( bf16(silu(g)) * u )     [rows, F]; every row pitch >= F rounded up to 8 (the ragged tail chunk is computed
+// on the padding too and lands in padding)
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ a,
                   long rows, int F, long ldg, long ldu, long lda) {
-  const int nch = F >> 3;
+  const int nch = (F + 7) >> 3;
   const long total = rows * nch;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long r = i / nch;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ u,
                   __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ du, long rows, int F, long ldda, long ldg,
                   long ldu, long lddg, long lddu) {
-  const int nch = F >> 3;
+  const int nch = (F + 7) >> 3;
   const long total = rows * nch;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long r = i / nch;

@@ -16,7 +16,7 @@ struct GemmLaunch {
   int max_ctas;                  // 0 = all SMs
 };
 
-template <int BN, bool kBwd, bool kNF4, bool kLoRA>
+template <int BN, bool kBwd, bool kNF4, bool kLoRA, bool kRagged>
 int launch_gemm_t(const GemmLaunch& g, cudaStream_t stream) {
   using S = GemmSmem<BN, kBwd, kLoRA>;
   GemmParams p = g.p;
@@ -33,11 +33,11 @@ int launch_gemm_t(const GemmLaunch& g, cudaStream_t stream) {
       return 1;
   }
   if (!kBwd && kLoRA) {
-    if (make_tmap_bf16_2d(&tmP, p.lora_down, p.w.K, kRank, static_cast<uint64_t>(p.w.K) * 2, 64, kRank,
+    if (make_tmap_bf16_2d(&tmP, p.lora_down, p.w.K, kRank, static_cast<uint64_t>(p.ld_down) * 2, 64, kRank,
                           CU_TENSOR_MAP_SWIZZLE_128B))
       return 1;
   }
-  auto kern = gemm_nf4lora_kernel<BN, kBwd, kNF4, kLoRA>;
+  auto kern = gemm_nf4lora_kernel<BN, kBwd, kNF4, kLoRA, kRagged>;
   static bool attr_set = false;
   if (!attr_set) {
     VPT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -73,8 +73,14 @@ inline int choose_bn(int M, int NO, bool lora) {
 template <bool kBwd, bool kNF4, bool kLoRA>
 int launch_gemm_bn(const GemmLaunch& g, cudaStream_t stream) {
   const int bn = g.bn > 0 ? g.bn : choose_bn(g.p.M, g.p.NO, kLoRA);
-  if (bn == 192) return launch_gemm_t<192, kBwd, kNF4, kLoRA>(g, stream);
-  if (bn == 128) return launch_gemm_t<128, kBwd, kNF4, kLoRA>(g, stream);
+  const bool ragged = kNF4 && g.p.w.packed_rows != nullptr;
+  if (kNF4 && ragged) {
+    if (bn == 192) return launch_gemm_t<192, kBwd, kNF4, kLoRA, kNF4>(g, stream);
+    if (bn == 128) return launch_gemm_t<128, kBwd, kNF4, kLoRA, kNF4>(g, stream);
+  } else {
+    if (bn == 192) return launch_gemm_t<192, kBwd, kNF4, kLoRA, false>(g, stream);
+    if (bn == 128) return launch_gemm_t<128, kBwd, kNF4, kLoRA, false>(g, stream);
+  }
   return fail("unsupported tile width");
 }
 

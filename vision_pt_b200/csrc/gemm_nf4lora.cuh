@@ -40,6 +40,10 @@ struct Nf4Weight {
   const float* code;            // [16]
   float offset;
   int N, K;                     // out_features, in_features
+  // ragged layout (K % 64 != 0), produced once by vpt_nf4_repack: row-aligned codes + decoded statistics
+  const uint8_t* packed_rows;   // [N, K_pad / 2]
+  const float* absmax_f32;      // [ceil(N*K/64)] fl32(fl32(code2[q]*nested) + offset)
+  int K_pad;
 };
 
 struct GemmParams {
@@ -50,7 +54,8 @@ struct GemmParams {
   const __nv_bfloat16* residual;  // [M, NO] (pitch ldr) added in the epilogue, or nullptr
   int ldr;
   Nf4Weight w;
-  const __nv_bfloat16* lora_down;  // [16, K]
+  const __nv_bfloat16* lora_down;  // [16, K] with row pitch ld_down (multiple of 8 elements, zero padded)
+  int ld_down;
   const __nv_bfloat16* lora_up;    // [N, 16]
   float scale;                  // alpha / rank
   __nv_bfloat16* side;          // [M,16]: fwd Ts = bf16(scale * X A_down^T); bwd dTs = bf16(scale * dY B_up)
@@ -111,6 +116,32 @@ __device__ __forceinline__ void nf4_dequant32_to_swizzled(const uint4& pk, float
   }
 }
 
+// Ragged rows: the 32 elements may straddle one 64-block boundary of the flattened weight; element e uses am_a when
+// e < split, am_b otherwise (same products, hence the same bits, as the flat layout).
+__device__ __forceinline__ void nf4_dequant32_split_to_swizzled(const uint4& pk, float am_a, float am_b, int split,
+                                                                uint32_t code_saddr, uint32_t row_saddr, int half,
+                                                                int row_in_atom) {
+  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x = w[i];
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int e = i * 8 + b * 2;
+      const uint32_t a_hi = ((x >> (8 * b + 2)) & 0x3cu) | code_saddr;
+      const uint32_t a_lo = (b == 0 ? ((x << 2) & 0x3cu) : ((x >> (8 * b - 2)) & 0x3cu)) | code_saddr;
+      const float hi = __fmul_rn(lds_f32(a_hi), e < split ? am_a : am_b);
+      const float lo = __fmul_rn(lds_f32(a_lo), e + 1 < split ? am_a : am_b);
+      o[b] = pack_bf16x2(hi, lo);
+    }
+    const uint32_t chunk = static_cast<uint32_t>((half * 4 + i) ^ row_in_atom);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_saddr + chunk * 16u), "r"(o[0]), "r"(o[1]),
+                 "r"(o[2]), "r"(o[3])
+                 : "memory");
+  }
+}
+
 __device__ __forceinline__ void st_shared_zero16(uint32_t saddr) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(saddr), "r"(0u) : "memory");
 }
@@ -122,7 +153,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, const uint4& v) {
 // tmA : activations [M, R] row-major, box {64, 128}, SWIZZLE_128B
 // tmB : (kNF4 == false) bf16 weight [N, K] row-major; fwd box {64, BN}, bwd box {64, 64}; SWIZZLE_128B
 // tmP : (fwd, kLoRA) lora_down [16, K], box {64, 16}, SWIZZLE_128B
-template <int BN, bool kBwd, bool kNF4, bool kLoRA>
+template <int BN, bool kBwd, bool kNF4, bool kLoRA, bool kRagged = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
@@ -281,7 +312,7 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = et; i < (BN / 8) * kRank; i += 128) {
             const int j = i / (BN / 8), oc = i % (BN / 8);
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (o0 + oc * 8 < p.NO) v = *reinterpret_cast<const uint4*>(p.lora_down + static_cast<size_t>(j) * p.w.K + o0 + oc * 8);
+            if (o0 + oc * 8 < p.NO) v = *reinterpret_cast<const uint4*>(p.lora_down + static_cast<size_t>(j) * p.ld_down + o0 + oc * 8);
             st_shared_v4(q_s + oc * 256 + (j >> 3) * 128 + (j & 7) * 16, v);
           }
         }
@@ -365,9 +396,11 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kPerThread = (kTasks + kDeqThreads - 1) / kDeqThreads;
     const int K = p.w.K;
     uint4 pk[kPerThread];
-    uint32_t qa[kPerThread];
-    float nest[kPerThread];
+    uint32_t qa[kPerThread];      // flat layout: absmax code;        ragged: elements before the block boundary
+    float nest[kPerThread];       // flat layout: nested absmax;      ragged: absmax of the first block
+    float amb[kPerThread];        //                                   ragged: absmax of the second block
     bool valid[kPerThread];
+    const long nblocks = (static_cast<long>(p.w.N) * K + 63) >> 6;
 
     // (tile, kstep) -> global coordinates of this thread's tasks
     auto prefetch = [&](int tile, int ks) {
@@ -379,6 +412,7 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         pk[u] = make_uint4(0, 0, 0, 0);
         qa[u] = 0;
         nest[u] = 0.f;
+        amb[u] = 0.f;
         if (!kNF4 || t >= kTasks) continue;
         int wrow, wcol;                                  // weight row (n) and first column (k) of the 32 elements
         if (!kBwd) {
@@ -388,7 +422,17 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           wrow = ks * kBK + ((t & 127) >> 1);
           wcol = o0 + (t >> 7) * 64 + (t & 1) * 32;
         }
-        if (wrow < p.w.N && wcol < K) {
+        if (kRagged) {
+          if (wrow < p.w.N && wcol < p.w.K_pad) {
+            const long flat = static_cast<long>(wrow) * K + wcol;
+            const long blk = flat >> 6;
+            valid[u] = true;
+            pk[u] = __ldg(reinterpret_cast<const uint4*>(p.w.packed_rows + (static_cast<size_t>(wrow) * p.w.K_pad + wcol) / 2));
+            qa[u] = 64u - static_cast<uint32_t>(flat & 63);
+            nest[u] = __ldg(p.w.absmax_f32 + (blk < nblocks ? blk : nblocks - 1));
+            amb[u] = __ldg(p.w.absmax_f32 + (blk + 1 < nblocks ? blk + 1 : nblocks - 1));
+          }
+        } else if (wrow < p.w.N && wcol < K) {
           const size_t flat = static_cast<size_t>(wrow) * K + wcol;
           valid[u] = true;
           pk[u] = __ldg(reinterpret_cast<const uint4*>(p.w.packed + (flat >> 1)));
@@ -408,14 +452,23 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int s = it % kStages;
       // current task data -> locals, then start the loads of the next (tile, kstep)
       uint4 cpk[kPerThread];
-      float cam[kPerThread];
+      float cam[kPerThread], camb[kPerThread];
+      int csplit[kPerThread];
       bool cvalid[kPerThread];
 #pragma unroll
       for (int u = 0; u < kPerThread; ++u) {
         cpk[u] = pk[u];
         cvalid[u] = valid[u];
-        // double-quant decode, two separately rounded fp32 ops exactly like dequantize_blockwise followed by "+= offset"
-        cam[u] = valid[u] ? __fadd_rn(__fmul_rn(lds_f32(code_s + 64 + qa[u] * 4), nest[u]), p.w.offset) : 0.f;
+        if (kRagged) {
+          cam[u] = nest[u];
+          camb[u] = amb[u];
+          csplit[u] = static_cast<int>(qa[u]);
+        } else {
+          // double-quant decode, two separately rounded fp32 ops exactly like dequantize_blockwise followed by "+= offset"
+          cam[u] = valid[u] ? __fadd_rn(__fmul_rn(lds_f32(code_s + 64 + qa[u] * 4), nest[u]), p.w.offset) : 0.f;
+          camb[u] = 0.f;
+          csplit[u] = 64;
+        }
       }
       const int cur_tile = tile, cur_ks = ks;
       if (++ks == ksteps) {
@@ -444,7 +497,8 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             rin = r & 7;
           }
           if (cvalid[u]) {
-            nf4_dequant32_to_swizzled(cpk[u], cam[u], code_s, row_s, half, rin);
+            if (kRagged) nf4_dequant32_split_to_swizzled(cpk[u], cam[u], camb[u], csplit[u], code_s, row_s, half, rin);
+            else nf4_dequant32_to_swizzled(cpk[u], cam[u], code_s, row_s, half, rin);
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) st_shared_zero16(row_s + (((half * 4 + i) ^ rin) * 16));

@@ -71,6 +71,31 @@ nf4_dequant_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict
   }
 }
 
+// Load-time repack for ragged in_features (K % 64 != 0, e.g. the SwiGLU hidden 2730 / 3413 of JiT-L / -H): bitsandbytes
+// packs the FLATTENED [N,K] weight, so rows start at arbitrary nibbles and 64-blocks straddle rows.  The GEMM producers
+// want 16-byte aligned rows: codes are re-packed row by row with pitch K_pad/2 bytes (K_pad = K rounded up to 64, padding
+// = code 7 = 0.0).  The statistics stay indexed by the original flat position, so dequantised values are bit-identical.
+__global__ void __launch_bounds__(256)
+nf4_repack_rows_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ rows, int N, int K, int K_pad) {
+  const long total = static_cast<long>(N) * (K_pad / 2);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = i / (K_pad / 2);
+    const int k = static_cast<int>(i % (K_pad / 2)) * 2;
+    uint32_t c[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (k + e < K) {
+        const long f = n * K + k + e;
+        const uint8_t b = packed[f >> 1];
+        c[e] = (f & 1) ? (b & 15u) : (b >> 4);
+      } else {
+        c[e] = 7u;
+      }
+    }
+    rows[i] = static_cast<uint8_t>((c[0] << 4) | c[1]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- quantise
 template <int kDt>
 __device__ __forceinline__ float nf4_load(const void* w, long i) {

@@ -80,7 +80,8 @@ def rope_table(cfg: DenoiserConfig, height: int, width: int, context_len: int, n
         freqs = 1.0 / (cfg.rope_theta ** (torch.arange(0, dim, 2, dtype=torch.float64) / dim))
         angles.append(torch.outer(pos[:, a], freqs).float())
     ang = torch.cat(angles, dim=1)                               # [L, head_dim/2] fp32
-    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+    cis = torch.polar(torch.ones_like(ang), ang)                 # the reference builds the table with torch.polar
+    return torch.stack([cis.real, cis.imag], dim=-1).contiguous()
 
 
 class Attention(nn.Module):
@@ -171,9 +172,9 @@ def _linear_ok(layer: nn.Module) -> bool:
     if isinstance(base, NF4Linear):
         ok = base.is_quantized
     else:
-        ok = type(base) is nn.Linear and base.weight.dtype == torch.bfloat16 and not base.weight.requires_grad
-    return ok and base.in_features % 64 == 0 and base.out_features % 8 == 0 and \
-        (base.bias is None or not base.bias.requires_grad)
+        ok = (type(base) is nn.Linear and base.weight.dtype == torch.bfloat16 and not base.weight.requires_grad
+              and base.in_features % 8 == 0)
+    return ok and (base.bias is None or not base.bias.requires_grad)
 
 
 class JiTBlockFn(torch.autograd.Function):

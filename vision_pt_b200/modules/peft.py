@@ -108,9 +108,10 @@ class LoRALinear(PeftLayer):
     def fusable(self) -> bool:
         """True when base GEMM + LoRA branch can run as the single fused kernel (CUDA bf16, rank <= 16, no dropout)."""
         base = self.linear
-        plain = type(base) is nn.Linear and base.weight.dtype == torch.bfloat16 and base.weight.is_cuda
+        plain = (type(base) is nn.Linear and base.weight.dtype == torch.bfloat16 and base.weight.is_cuda
+                 and base.in_features % 8 == 0)
         quant = isinstance(base, NF4Linear) and base.is_quantized and base.weight.is_cuda
-        return ((plain or quant) and base.in_features % 64 == 0 and isinstance(self.dropout, nn.Identity)
+        return ((plain or quant) and isinstance(self.dropout, nn.Identity)
                 and self.lora_up.bias is None and self.rank <= ops.RANK
                 and self.lora_down.weight.dtype == torch.bfloat16 and self.lora_down.weight.is_cuda)
 

@@ -32,11 +32,18 @@ def _need_cuda(*ts: torch.Tensor | None) -> None:
 
 
 def _rows(t: torch.Tensor) -> torch.Tensor:
-    """[..., D] -> 2-D [rows, D] view with unit inner stride and a row pitch that is a multiple of 8 elements."""
+    """[..., D] -> 2-D [rows, D] view with unit inner stride, 16-byte aligned rows (pitch a multiple of 8 elements).
+    Ragged widths (D % 8 != 0, e.g. the 2730-wide SwiGLU hidden of JiT-L) are copied into a padded buffer."""
     t2 = t.reshape(-1, t.shape[-1])
-    if t2.stride(1) != 1 or (t2.shape[0] > 1 and t2.stride(0) % 8 != 0) or t2.data_ptr() % 16 != 0:
-        t2 = t2.contiguous()
-    return t2
+    ok = t2.stride(1) == 1 and (t2.shape[0] == 1 or t2.stride(0) % 8 == 0) and t2.data_ptr() % 16 == 0
+    if ok:
+        return t2
+    rows, d = t2.shape
+    if d % 8 == 0:
+        return t2.contiguous()
+    buf = torch.zeros((rows, (d + 7) // 8 * 8), dtype=t2.dtype, device=t2.device)
+    buf[:, :d] = t2
+    return buf[:, :d]
 
 
 # ------------------------------------------------------------------------------------------------------- NF4
@@ -51,10 +58,33 @@ class Nf4Tensors:
     offset: float
     shape: tuple[int, int]
     dtype: torch.dtype
+    # row-aligned copy for ragged in_features (K % 64 != 0), built lazily on the GPU by vpt_nf4_repack
+    packed_rows: torch.Tensor | None = None
+    absmax_f32: torch.Tensor | None = None
 
-    def c_struct(self) -> Nf4WeightC:
+    @property
+    def k_pad(self) -> int:
+        return (self.shape[1] + 63) // 64 * 64
+
+    def c_struct(self, for_gemm: bool = False) -> Nf4WeightC:
+        rows = stats = None
+        kp = 0
+        if for_gemm and self.shape[1] % 64 != 0:
+            self.ensure_repacked()
+            rows, stats, kp = self.packed_rows, self.absmax_f32, self.k_pad
         return Nf4WeightC(_p(self.packed), _p(self.absmax), _p(self.nested_absmax), _p(self.nested_code), _p(self.code),
-                          float(self.offset), int(self.shape[0]), int(self.shape[1]))
+                          float(self.offset), int(self.shape[0]), int(self.shape[1]), _p(rows), _p(stats), kp)
+
+    def ensure_repacked(self) -> None:
+        if self.packed_rows is not None:
+            return
+        n, k = self.shape
+        dev = self.packed.device
+        rows = torch.empty((n, self.k_pad // 2), dtype=torch.uint8, device=dev)
+        stats = torch.empty((n * k + 63) // 64, dtype=torch.float32, device=dev)
+        ws = self.c_struct()
+        _lib.call("vpt_nf4_repack", C.byref(ws), _p(rows), _p(stats), self.k_pad, _stream())
+        self.packed_rows, self.absmax_f32 = rows, stats
 
     def to(self, device) -> "Nf4Tensors":
         return Nf4Tensors(self.packed.to(device), self.absmax.to(device), self.nested_absmax.to(device),
@@ -94,18 +124,22 @@ def nf4_quantize(weight: torch.Tensor, nested_code: torch.Tensor, code: torch.Te
 
 # ------------------------------------------------------------------------------------------------------- linear
 def _pad_rank(down: torch.Tensor | None, up: torch.Tensor | None):
+    """LoRA matrices in the kernel's shape: rank padded to 16 with zeros, lora_down rows padded to a 16-byte pitch."""
     if down is None:
         return None, None
-    r = down.shape[0]
-    if r == RANK:
-        return down.contiguous(), up.contiguous()
+    r, k = down.shape
     if r > RANK:
         raise NotImplementedError(f"the fused NF4-LoRA kernel handles rank <= {RANK}, got {r}")
-    d = down.new_zeros(RANK, down.shape[1])
-    d[:r] = down
+    if r == RANK and k % 8 == 0:
+        return down.contiguous(), up.contiguous()
+    k8 = (k + 7) // 8 * 8
+    d = down.new_zeros(RANK, k8)
+    d[:r, :k] = down
+    if r == RANK:
+        return d[:, :k], up.contiguous()
     u = up.new_zeros(up.shape[0], RANK)
     u[:, :r] = up
-    return d, u
+    return d[:, :k], u
 
 
 def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, scale: float, residual=None,
@@ -117,12 +151,12 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
         raise TypeError("fused linear runs in bfloat16")
     args = LinearArgsC()
     if isinstance(w, Nf4Tensors):
-        args.w = w.c_struct()
+        args.w = w.c_struct(for_gemm=True)
         N, K = w.shape
         args.w_bf16 = None
     else:
         N, K = w.shape
-        args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K))
+        args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K), None, None, 0)
         args.w_bf16 = _p(w)
     M = x2.shape[0]
     n_out = K if backward else N
@@ -132,6 +166,7 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     side = torch.empty((M, RANK), dtype=torch.bfloat16, device=x2.device) if (want_side and down is not None) else None
     args.bias = _p(bias)
     args.lora_down = _p(down)
+    args.ld_lora_down = down.stride(0) if down is not None else 0
     args.lora_up = _p(up)
     args.scale = float(scale)
     args.inp = _p(x2)
@@ -378,16 +413,12 @@ def qknorm_rope(x, weight, cos_sin, eps: float = 1e-6):
 
 # ------------------------------------------------------------------------------------------------------- SwiGLU
 def swiglu_fwd_raw(g2, u2):
+    """g2, u2: [rows, F] views whose row pitch covers F rounded up to 8 (see _rows / linear_raw)."""
     rows, F = g2.shape
     ld = (F + 7) // 8 * 8
-    a_full = torch.zeros((rows, ld), dtype=torch.bfloat16, device=g2.device) if ld != F else \
-        torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
-    Fv = F // 8 * 8
-    _lib.call("vpt_swiglu_fwd", _p(g2), _p(u2), _p(a_full), rows, Fv, g2.stride(0), u2.stride(0), ld, _stream())
-    a = a_full[:, :F]
-    if Fv != F:  # ragged tail (F = 2730, 3413): a handful of columns
-        a[:, Fv:] = torch.nn.functional.silu(g2[:, Fv:F]) * u2[:, Fv:F]
-    return a
+    a_full = torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
+    _lib.call("vpt_swiglu_fwd", _p(g2), _p(u2), _p(a_full), rows, F, g2.stride(0), u2.stride(0), ld, _stream())
+    return a_full[:, :F] if ld != F else a_full
 
 
 def swiglu_bwd_raw(da2, g2, u2):
@@ -395,17 +426,11 @@ def swiglu_bwd_raw(da2, g2, u2):
     ld = (F + 7) // 8 * 8
     dg_full = torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
     du_full = torch.empty((rows, ld), dtype=torch.bfloat16, device=g2.device)
-    Fv = F // 8 * 8
-    _lib.call("vpt_swiglu_bwd", _p(da2), _p(g2), _p(u2), _p(dg_full), _p(du_full), rows, Fv, da2.stride(0), g2.stride(0),
+    _lib.call("vpt_swiglu_bwd", _p(da2), _p(g2), _p(u2), _p(dg_full), _p(du_full), rows, F, da2.stride(0), g2.stride(0),
               u2.stride(0), ld, ld, _stream())
-    dg, du = dg_full[:, :F], du_full[:, :F]
-    if Fv != F:
-        gt = g2[:, Fv:F].float()
-        sg = torch.sigmoid(gt)
-        dat = da2[:, Fv:F].float()
-        du[:, Fv:] = (dat * gt * sg).to(torch.bfloat16)
-        dg[:, Fv:] = (dat * u2[:, Fv:F].float() * (sg * (1 + gt * (1 - sg)))).to(torch.bfloat16)
-    return dg, du
+    if ld != F:
+        return dg_full[:, :F], du_full[:, :F]
+    return dg_full, du_full
 
 
 class SwiGLUFn(torch.autograd.Function):
