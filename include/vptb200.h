@@ -147,6 +147,24 @@ int vpt_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H
 int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
                    int32_t order, vpt_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------ optimiser / loss
+ * accelerator.clip_grad_norm_ + optimizer.step + zero_grad (src/models/for_training.py:98-109,
+ * src/trainer/common.py:382-388) over the flat LoRA buffers: param bf16 [n], grad / exp_avg / exp_avg_sq fp32 [n].
+ * vpt_grad_sumsq: out[0] += sum((g*scale)^2), out zero on entry.  vpt_adamw_step: torch.optim.AdamW update with
+ * g <- g * grad_scale * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (sumsq NULL = no clipping); *step is the 1-based
+ * step number (device scalar, so that a captured graph replays); zero_grad != 0 clears grad afterwards. */
+int vpt_grad_sumsq(const float* g, int64_t n, float scale, float* out, vpt_stream_t stream);
+int vpt_adamw_step(void* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, const float* sumsq, float max_norm,
+                   const float* step, int32_t zero_grad, vpt_stream_t stream);
+/* treat_loss, model_pred "image" (train/jit/class_to_image.py:106-139): mode 0 = MSE(pred, clean), mode 1 = MSE of
+ * the velocities (image_to_velocity, src/models/jit/pipeline.py:253-260) with timestep [batch] fp32.  pred bf16,
+ * clean/noisy of in_dtype (VPT_BF16/F16/F32); loss_out[0] += mean (zero on entry); dpred (bf16, may be NULL) = dloss/dpred. */
+int vpt_flow_loss(const void* pred, const void* clean, const void* noisy, int in_dtype, const float* timestep,
+                  int64_t batch, int64_t per_sample, int32_t mode, float clamp_eps, float* loss_out, void* dpred,
+                  vpt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,9 @@ SIGNATURES: dict[str, list] = {
     "vpt_gate_residual_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
     "vpt_patchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     "vpt_unpatchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "vpt_grad_sumsq": [_P, _I64, _F, _P, _P],
+    "vpt_adamw_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _F, _P, _I32, _P],
+    "vpt_flow_loss": [_P, _P, _P, C.c_int, _P, _I64, _I64, _I32, _F, _P, _P, _P],
 }
 
 _lib = None
@@ -82,8 +85,22 @@ def load() -> C.CDLL:
     return lib
 
 
+# kernels launched per C-ABI call (vpt_attn_bwd = delta pre-pass + main kernel); used for the bench's gpu_launches
+_KERNELS_PER_CALL = {"vpt_attn_bwd": 2, "vpt_nf4_quantize": 3}
+CALLS: dict[str, int] = {}
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of libvptb200 kernels launched by this process so far."""
+    return _launches
+
+
 def call(name: str, *args) -> None:
+    global _launches
     lib = load()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed: {lib.vpt_last_error().decode()}")
+    _launches += _KERNELS_PER_CALL.get(name, 1)
+    CALLS[name] = CALLS.get(name, 0) + 1

@@ -6,6 +6,7 @@
 #include "gemm_launch.cuh"
 #include "lora_grad.cuh"
 #include "nf4.cuh"
+#include "optim.cuh"
 
 using namespace vpt;
 
@@ -241,4 +242,33 @@ extern "C" int vpt_patchify(const void* img, void* patches, int32_t B, int32_t C
 extern "C" int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
                               int32_t order, vpt_stream_t stream) {
   return patch_common(patches, img, B, C, H, W, p, order, false, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ optimiser / loss
+extern "C" int vpt_grad_sumsq(const float* g, int64_t n, float scale, float* out, vpt_stream_t stream) {
+  VPT_REQUIRE(g && out && n > 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "vpt_grad_sumsq: bad arguments");
+  grad_sumsq_kernel<<<blocks_for(n / 4 + 1, 256, 148 * 8), 256, 0, S(stream)>>>(g, n, scale, out);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_adamw_step(void* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, float grad_scale, const float* sumsq,
+                              float max_norm, const float* step, int32_t zero_grad, vpt_stream_t stream) {
+  VPT_REQUIRE(param && grad && exp_avg && exp_avg_sq && step && n > 0, "vpt_adamw_step: bad arguments");
+  AdamWParams a{BFM(param), grad, exp_avg, exp_avg_sq, static_cast<long>(n), lr, beta1, beta2, eps, weight_decay,
+                grad_scale, sumsq, max_norm, step, zero_grad};
+  adamw_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(a);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_flow_loss(const void* pred, const void* clean, const void* noisy, int in_dtype, const float* timestep,
+                             int64_t batch, int64_t per_sample, int32_t mode, float clamp_eps, float* loss_out, void* dpred,
+                             vpt_stream_t stream) {
+  VPT_REQUIRE(pred && clean && loss_out && batch > 0 && per_sample > 0 && (mode == 0 || (mode == 1 && noisy && timestep)) &&
+                  in_dtype >= 0 && in_dtype <= 2, "vpt_flow_loss: bad arguments");
+  const long total = static_cast<long>(batch) * per_sample;
+  flow_loss_kernel<<<blocks_for(total, 256 * 8, 148 * 16), 256, 0, S(stream)>>>(BF(pred), clean, noisy, in_dtype, timestep, per_sample, total, mode,
+                                                                       clamp_eps, loss_out, BFM(dpred));
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
 }

@@ -1,0 +1,134 @@
+// Optimiser step over the flat LoRA parameter buffer: gradient-norm clipping + AdamW in one pass.
+//
+// Reference semantics (file:line under /root/reference):
+//   clip_grad_norm_ after backward         src/models/for_training.py:98-109 (accelerator.clip_grad_norm_ -> torch
+//                                          clip_grad_norm_: coef = min(1, max_norm / (total_norm + 1e-6)))
+//   optimizer.step / zero_grad             src/trainer/common.py:382-388 (torch.optim.AdamW semantics, decoupled decay)
+// Only the LoRA matrices train, so all parameters live in ONE contiguous bf16 buffer with an fp32 gradient buffer of
+// the same length (the lora_grad kernels accumulate into it; with data parallelism it is the all-reduce payload).
+// Both kernels are HBM-bound streaming passes; nothing here synchronises the host: the step number and the squared
+// gradient norm are read from device memory so that a captured CUDA graph replays correctly.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpt {
+
+// out[0] += sum((g * scale)^2)   (out must be zero on entry)
+__global__ void __launch_bounds__(256)
+grad_sumsq_kernel(const float* __restrict__ g, long n, float scale, float* __restrict__ out) {
+  float acc = 0.f;
+  const long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(g4 + i);
+    acc += (v.x * scale) * (v.x * scale) + (v.y * scale) * (v.y * scale) + (v.z * scale) * (v.z * scale) + (v.w * scale) * (v.w * scale);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x] * scale;
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    atomicAdd(out, t);
+  }
+}
+
+struct AdamWParams {
+  __nv_bfloat16* p;        // [n] parameters (updated in place)
+  float* g;                // [n] gradients; zeroed after use when zero_grad != 0
+  float* m;                // [n] first moment
+  float* v;                // [n] second moment
+  long n;
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;        // 1 / world_size for a SUM all-reduce, 1 otherwise
+  const float* sumsq;      // device scalar: squared norm of (g * grad_scale); nullptr = no clipping
+  float max_norm;
+  const float* step;       // device scalar: 1-based step number of THIS update
+  int zero_grad;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(const AdamWParams a) {
+  float coef = a.grad_scale;
+  if (a.sumsq != nullptr) {
+    const float norm = sqrtf(__ldg(a.sumsq));
+    coef *= fminf(1.f, a.max_norm / (norm + 1e-6f));
+  }
+  const float t = __ldg(a.step);
+  const float bc1 = 1.f - powf(a.beta1, t);
+  const float bc2 = 1.f - powf(a.beta2, t);
+  const float step_size = a.lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float decay = 1.f - a.lr * a.weight_decay;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float g = a.g[i] * coef;
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.m[i] = m;
+    a.v[i] = v;
+    float p = __bfloat162float(a.p[i]) * decay;
+    p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+    a.p[i] = __float2bfloat16_rn(p);
+    if (a.zero_grad) a.g[i] = 0.f;
+  }
+}
+
+}  // namespace vpt
+
+// ------------------------------------------------------------------------------------------- flow-matching loss
+// treat_loss (train/jit/class_to_image.py:106-164) for model_pred == "image", forward and gradient in one pass:
+//   mode 0 (loss_target "image")    : loss = mean((pred - clean)^2)
+//   mode 1 (loss_target "velocity") : loss = mean(((pred - noisy)/d - (clean - noisy)/d)^2),  d = max(1 - t[b], clamp_eps)
+//                                     (JiT pipeline image_to_velocity, src/models/jit/pipeline.py:253-260)
+// loss_out[0] += partial sums (zero on entry); dpred = d loss / d pred (bf16), to be scaled by the upstream gradient.
+namespace vpt {
+
+__device__ __forceinline__ float loss_load(const void* p, int dtype, long i) {
+  if (dtype == 0) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+  if (dtype == 1) return __half2float(static_cast<const __half*>(p)[i]);
+  return static_cast<const float*>(p)[i];
+}
+
+__global__ void __launch_bounds__(256)
+flow_loss_kernel(const __nv_bfloat16* __restrict__ pred, const void* __restrict__ clean, const void* __restrict__ noisy,
+                 int in_dtype, const float* __restrict__ timestep, long per_sample, long total, int mode, float clamp_eps,
+                 float* __restrict__ loss_out, __nv_bfloat16* __restrict__ dpred) {
+  const float inv_n = 1.f / static_cast<float>(total);
+  float acc = 0.f;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float p = __bfloat162float(pred[i]);
+    const float c = loss_load(clean, in_dtype, i);
+    float diff, w = 1.f;
+    if (mode == 1) {
+      const float d = fmaxf(1.f - __ldg(timestep + i / per_sample), clamp_eps);
+      const float z = loss_load(noisy, in_dtype, i);
+      diff = (p - z) / d - (c - z) / d;
+      w = 1.f / d;
+    } else {
+      diff = p - c;
+    }
+    acc += diff * diff;
+    if (dpred != nullptr) dpred[i] = __float2bfloat16_rn(2.f * diff * w * inv_n);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    atomicAdd(loss_out, t * inv_n);
+  }
+}
+
+}  // namespace vpt

@@ -37,6 +37,15 @@ def get_timestep_embedding(timesteps: torch.Tensor, embedding_dim: int, flip_sin
     return emb
 
 
+def _kernel_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor | None:
+    """x W^T + b through the tcgen05 kernel for a FROZEN bf16 weight (patch embed, final layer, context embedder);
+    None when the layer does not qualify (trainable, other dtype, CPU) and the caller falls back to torch."""
+    if (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and not weight.requires_grad
+            and weight.shape[-1] % 8 == 0 and (bias is None or not bias.requires_grad)):
+        return ops.nf4_lora_linear(x, weight, bias)
+    return None
+
+
 class BottleneckPatchEmbed(nn.Module):
     def __init__(self, patch_size=16, in_channels=3, bottleneck_dim=128, hidden_dim=768, bias=True):
         super().__init__()
@@ -45,6 +54,15 @@ class BottleneckPatchEmbed(nn.Module):
         self.proj_2 = nn.Conv2d(bottleneck_dim, hidden_dim, kernel_size=1, stride=1, bias=bias)
 
     def forward(self, image: torch.Tensor) -> torch.Tensor:
+        w1, w2 = self.proj_1.weight, self.proj_2.weight
+        if image.is_cuda and image.dtype == torch.bfloat16 and not image.requires_grad:
+            # a stride-p conv over non-overlapping patches = patchify in (c, py, px) order + GEMM (reference :51-67)
+            patches = ops.patchify_op(image, self.patch_size, order=0)
+            h = _kernel_linear(patches, w1.view(w1.shape[0], -1), None)
+            if h is not None:
+                y = _kernel_linear(h, w2.view(w2.shape[0], -1), self.proj_2.bias)
+                if y is not None:
+                    return y
         return self.proj_2(self.proj_1(image)).flatten(2).transpose(1, 2)
 
 
@@ -122,9 +140,17 @@ class SwiGLU(nn.Module):
         self.w_3 = nn.Linear(hidden_dim, dim, bias=bias)
         self.ffn_dropout = nn.Dropout(dropout)
 
+    @staticmethod
+    def _lin(layer, x):
+        if type(layer) is nn.Linear:
+            y = _kernel_linear(x, layer.weight, layer.bias)
+            if y is not None:
+                return y
+        return layer(x)
+
     def forward(self, hidden_states):
-        a = ops.swiglu(self.w_1(hidden_states), self.w_2(hidden_states))
-        return self.w_3(self.ffn_dropout(a))
+        a = ops.swiglu(self._lin(self.w_1, hidden_states), self._lin(self.w_2, hidden_states))
+        return self._lin(self.w_3, self.ffn_dropout(a))
 
 
 class FinalLayer(nn.Module):
@@ -135,7 +161,7 @@ class FinalLayer(nn.Module):
         self.linear = nn.Linear(hidden_dim, patch_size * patch_size * out_channels, bias=True)
 
     def forward(self, hidden_states):
-        return self.linear(self.mlp(self.norm_final(hidden_states)))
+        return SwiGLU._lin(self.linear, self.mlp(self.norm_final(hidden_states)))
 
 
 class BottleneckFinalLayer(nn.Module):
@@ -242,13 +268,7 @@ class JiTBlockFn(torch.autograd.Function):
             l = lins[i]
             if l.down is None or not (ctx.needs_input_grad[4 + 2 * i] or ctx.needs_input_grad[5 + 2 * i]):
                 return
-            n, kk = l.up.shape[0], l.down.shape[1]
-            gup = torch.zeros((n, ops.RANK), dtype=torch.float32, device=dev)
-            gdown = torch.zeros((ops.RANK, kk), dtype=torch.float32, device=dev)
-            ops.lora_grad_raw(dout, t_side, gup, transposed=False)
-            ops.lora_grad_raw(inp, dt_side, gdown, transposed=True)
-            grads[2 * i] = gdown[:l.rank].to(l.down.dtype)
-            grads[2 * i + 1] = gup[:, :l.rank].to(l.up.dtype)
+            grads[2 * i], grads[2 * i + 1] = ops.lora_param_grads(dout, t_side, inp, dt_side, l.down, l.up, l.rank)
 
         # MLP branch
         da, dt_3 = back(6, dy2)
@@ -404,7 +424,7 @@ class JiT(nn.Module):
         time_embed = self.time_embedder(timestep * cfg.timestep_scale)
         time_tokens = time_embed.unsqueeze(1) + self.time_position_embeds.unsqueeze(0)
         n_time = time_tokens.shape[1]
-        context_embed = self.context_embedder(context)
+        context_embed = SwiGLU._lin(self.context_embedder, context)
         ctx_len = context_embed.shape[1]
         size_embed = self.get_imagesize_embed(original_size, target_size, crop_coords)
         n_size = size_embed.shape[1]

@@ -14,6 +14,10 @@ from ._lib import AttnTensorC, LinearArgsC, Nf4WeightC
 
 RANK = 16  # LoRA rank of the fused kernels; smaller ranks are zero-padded
 
+# bench.py sets this to a list to bracket every fused-linear launch with CUDA events on the launching stream
+# (roofline of the dominant kernel, measured inside real training steps); None = no instrumentation.
+GEMM_TIMER: list | None = None
+
 _DT = {torch.bfloat16: _lib.VPT_BF16, torch.float16: _lib.VPT_F16, torch.float32: _lib.VPT_F32}
 
 
@@ -178,7 +182,17 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     args.side = _p(side)
     args.M = M
     args.tile_n = tile_n
+    timer = GEMM_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("vpt_nf4lora_linear_bwd_dx" if backward else "vpt_nf4lora_linear_fwd", C.byref(args), _stream())
+    if timer is not None:
+        e1.record()
+        lora = down is not None
+        flops = 2.0 * M * K * N + (2.0 * M * RANK * (K + N) if lora else 0.0)
+        timer.append({"e0": e0, "e1": e1, "flops": flops, "M": M, "K": K, "N": N, "bwd": backward, "lora": lora,
+                      "nf4": isinstance(w, Nf4Tensors)})
     return out, side
 
 
@@ -188,6 +202,28 @@ def lora_grad_raw(src2: torch.Tensor, small: torch.Tensor, out_f32: torch.Tensor
     ld_out = out_f32.shape[1] if transposed else RANK
     _lib.call("vpt_lora_grad", _p(src2), src2.stride(0) if M > 1 else P, _p(small), _p(out_f32), M, P, int(transposed),
               ld_out, _stream())
+
+
+def grad_sink(param: torch.Tensor | None) -> torch.Tensor | None:
+    """fp32 slice of the trainer's flat LoRA-gradient buffer for this parameter (vision_pt_b200.train.FlatLoRA), or None.
+    When present, the lora_grad kernels accumulate straight into it and autograd receives no gradient for the matrix."""
+    return getattr(param, "_vpt_grad32", None) if param is not None else None
+
+
+def lora_param_grads(dy2, side, x2, dside, down, up, rank: int):
+    """lora_down / lora_up gradients of one linear.  Returns (ddown, dup) for autograd, or (None, None) when they were
+    accumulated into the flat fp32 buffer."""
+    sink_d, sink_u = grad_sink(down), grad_sink(up)
+    if sink_d is not None and sink_u is not None and rank == RANK:
+        lora_grad_raw(dy2, side, sink_u, transposed=False)
+        lora_grad_raw(x2, dside, sink_d, transposed=True)
+        return None, None
+    N, K = dy2.shape[1], x2.shape[1]
+    gup = torch.zeros((N, RANK), dtype=torch.float32, device=dy2.device)
+    gdown = torch.zeros((RANK, K), dtype=torch.float32, device=dy2.device)
+    lora_grad_raw(dy2, side, gup, transposed=False)
+    lora_grad_raw(x2, dside, gdown, transposed=True)
+    return gdown[:rank].to(down.dtype), gup[:, :rank].to(up.dtype)
 
 
 class NF4LoRALinearFn(torch.autograd.Function):
@@ -205,6 +241,7 @@ class NF4LoRALinearFn(torch.autograd.Function):
         bias_b = None if bias is None else bias.to(torch.bfloat16)
         y, side = linear_raw(x2, w, bias_b, dpad, upad, scale, res2, want_side=down is not None)
         ctx.w, ctx.scale, ctx.rank, ctx.in_dtype = w, scale, rank, in_dtype
+        ctx.lora_params = (down, up)
         ctx.has_res = residual is not None
         ctx.bias_grad = bias is not None and bias.requires_grad
         ctx.save_for_backward(x2, side, dpad, upad)
@@ -228,13 +265,7 @@ class NF4LoRALinearFn(torch.autograd.Function):
                 if ctx.in_dtype != torch.bfloat16:
                     dx = dx.to(ctx.in_dtype)
         if need_lora_grad:
-            K = x2.shape[1]
-            gup = torch.zeros((N, RANK), dtype=torch.float32, device=dy2.device)
-            gdown = torch.zeros((RANK, K), dtype=torch.float32, device=dy2.device)
-            lora_grad_raw(dy2, side, gup, transposed=False)
-            lora_grad_raw(x2, dside, gdown, transposed=True)
-            dup = gup[:, :ctx.rank].to(upad.dtype)
-            ddown = gdown[:ctx.rank].to(dpad.dtype)
+            ddown, dup = lora_param_grads(dy2, side, x2, dside, ctx.lora_params[0], ctx.lora_params[1], ctx.rank)
         if ctx.bias_grad:
             dbias = dy2.float().sum(0).to(dy.dtype)
         dres = dy if ctx.has_res else None
@@ -570,3 +601,49 @@ def patchify_op(image, p: int, order: int = 0):
 def unpatchify_op(patches, channels: int, height: int, width: int, p: int, order: int = 0):
     _need_cuda(patches)
     return UnpatchifyFn.apply(patches, channels, height, width, p, order)
+
+
+# ------------------------------------------------------------------------------------------------------- loss / optimiser
+class FlowLossFn(torch.autograd.Function):
+    """treat_loss for model_pred == "image": MSE on images (mode 0) or on velocities (mode 1); one kernel computes the
+    loss and d loss / d pred."""
+
+    @staticmethod
+    def forward(ctx, pred, clean, noisy, timestep, mode, clamp_eps):
+        if pred.dtype != torch.bfloat16:
+            raise TypeError("flow_loss takes the bf16 model prediction")
+        pc = pred.contiguous()
+        cc = clean.contiguous()
+        nc = noisy.contiguous().to(cc.dtype) if noisy is not None else None
+        B = pc.shape[0]
+        per = pc.numel() // B
+        loss = torch.zeros(1, dtype=torch.float32, device=pc.device)
+        dpred = torch.empty_like(pc) if pred.requires_grad else None
+        t32 = timestep.float().contiguous() if timestep is not None else None
+        _lib.call("vpt_flow_loss", _p(pc), _p(cc), _p(nc), _DT[cc.dtype], _p(t32), B, per, int(mode), float(clamp_eps),
+                  _p(loss), _p(dpred), _stream())
+        ctx.save_for_backward(dpred)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dpred,) = ctx.saved_tensors
+        return dpred * dloss.to(dpred.dtype), None, None, None, None, None
+
+
+def flow_loss(pred, clean, noisy=None, timestep=None, loss_target: str = "image", clamp_eps: float = 0.05):
+    _need_cuda(pred, clean)
+    return FlowLossFn.apply(pred, clean, noisy, timestep, 1 if loss_target == "velocity" else 0, clamp_eps)
+
+
+def grad_sumsq(grad32: torch.Tensor, scale: float, out: torch.Tensor) -> None:
+    _lib.call("vpt_grad_sumsq", _p(grad32), grad32.numel(), float(scale), _p(out), _stream())
+
+
+def adamw_step(param, grad32, exp_avg, exp_avg_sq, step_t, lr, betas, eps, weight_decay, grad_scale=1.0, sumsq=None,
+               max_norm=0.0, zero_grad=True) -> None:
+    if param.dtype != torch.bfloat16 or grad32.dtype != torch.float32:
+        raise TypeError("adamw_step: bf16 parameters with fp32 gradients")
+    _lib.call("vpt_adamw_step", _p(param), _p(grad32), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr), float(betas[0]),
+              float(betas[1]), float(eps), float(weight_decay), float(grad_scale), _p(sumsq), float(max_norm), _p(step_t),
+              int(zero_grad), _stream())

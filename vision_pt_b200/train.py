@@ -1,0 +1,259 @@
+"""JiT NF4-QLoRA training step on the sm_100a kernels, one process per GPU.
+
+Mirrors the reference's step for this path -- train/jit/class_to_image.py:166-243 (`train_step`: class-label context,
+timestep sampling, noising, denoiser call, `treat_loss`), src/trainer/common.py:326-388 (backward, gradient sync,
+optimizer step, zero_grad) and src/models/for_training.py:98-109 (gradient-norm clipping) -- with the B200-first
+differences stated in DESIGN.md:
+
+* every LoRA matrix lives in ONE bf16 buffer and its gradient in ONE fp32 buffer (`FlatLoRA`); the lora_grad kernels
+  accumulate straight into that buffer, data parallelism is a single NCCL all-reduce of it (the frozen NF4 base is
+  replicated and never communicated), and clipping + AdamW + zero_grad are two kernels over it;
+* the whole step (noise, forward, loss, backward, all-reduce, update) is captured once per (H, W) bucket in a CUDA graph
+  and replayed: no host synchronisation, no `.item()`, no per-step tensor-map encoding.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .jit import Denoiser, DenoiserConfig, JiT_B_16_Config, JiT_H_16_Config, JiT_L_16_Config
+from .modules.peft import LoRAConfig, LoRALinear, PeftTargetConfig
+from .modules.quant import quantize_inplace
+from .modules.state_dict import RegexMatch
+
+MODEL_CONFIGS = {"JiT-B/16": JiT_B_16_Config, "JiT-L/16": JiT_L_16_Config, "JiT-H/16": JiT_H_16_Config}
+BLOCK_LINEARS = ("to_q", "to_k", "to_v", "to_o", "w_1", "w_2", "w_3")
+LORA_TARGET = RegexMatch(regex=r"blocks\.\d+\.(attn|mlp)\.")   # see SURVEY 8b: ".mlp." alone also hits time_embedder.mlp
+
+
+class ClassEncoder(nn.Module):
+    """Label-id context encoder, src/models/jit/class_encoder.py:94-140: an embedding with a padding slot; the mask marks
+    the leading valid labels of each sample."""
+
+    def __init__(self, num_classes: int, embedding_dim: int):
+        super().__init__()
+        self.num_classes = num_classes
+        self.pad_token_id = num_classes
+        self.embedding = nn.Embedding(num_classes + 1, embedding_dim, padding_idx=num_classes)
+
+    def forward(self, class_ids: torch.Tensor) -> torch.Tensor:
+        return self.embedding(class_ids)
+
+
+def build_jit_qlora(model: str | DenoiserConfig = "JiT-B/16", rank: int = 16, alpha: float = 16.0, device="cuda",
+                    seed: int = 42, quantize: bool = True, lora_up_std: float = 0.0) -> Denoiser:
+    """Random-init JiT (JiT.initialize_weights, reference denoiser.py:764-798) in bf16, block linears NF4-quantised
+    (quantize_inplace -> bnb_nf4) and wrapped with LoRA (PeftTargetConfig.replace_to_peft_layer); only LoRA trains."""
+    cfg = MODEL_CONFIGS[model]() if isinstance(model, str) else model
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    net = Denoiser(cfg)
+    net.initialize_weights()
+    net.to(torch.bfloat16)
+    net.requires_grad_(False)
+    if quantize:
+        names = [n for n, _ in net.named_modules()]
+        keys = [n for n in names if n.startswith("blocks.") and n.rsplit(".", 1)[-1] in BLOCK_LINEARS]
+        quantize_inplace(net, "bnb_nf4", keys)
+    PeftTargetConfig(include_keys=[LORA_TARGET], config=LoRAConfig(rank=rank, alpha=alpha)).replace_to_peft_layer(net)
+    net.to(device)
+    for name, p in net.named_parameters():
+        if "lora_up" in name and lora_up_std > 0:
+            nn.init.normal_(p, std=lora_up_std)
+        p.requires_grad_(("lora_down" in name or "lora_up" in name) and "alpha" not in name)
+    torch.random.set_rng_state(gen_state)
+    return net
+
+
+class FlatLoRA:
+    """All trainable LoRA matrices of a model as views of one bf16 buffer, gradients as views of one fp32 buffer.
+
+    `param._vpt_grad32` is the hook the kernels look for (ops.grad_sink): gradients are accumulated there by the
+    lora_grad kernels and never pass through autograd's AccumulateGrad."""
+
+    def __init__(self, model: nn.Module):
+        self.params: list[nn.Parameter] = []
+        for mod in model.modules():
+            if isinstance(mod, LoRALinear):
+                for p in (mod.lora_down.weight, mod.lora_up.weight):
+                    if p.requires_grad:
+                        self.params.append(p)
+        if not self.params:
+            raise ValueError("no trainable LoRA parameters")
+        dev = self.params[0].device
+        # every slice starts on a 16-byte boundary of the fp32 buffer (float4 loads) -> sizes rounded up to 8 elements
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 7) // 8 * 8
+        self.numel = n
+        self.param = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.direct = True
+        for p, off in zip(self.params, self.offsets):
+            view = self.param[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            if p.dtype != torch.bfloat16:
+                raise TypeError("LoRA matrices are bf16 on this path (PeftConfigMixin.dtype)")
+            p._vpt_grad32 = self.grad[off:off + p.numel()].view_as(p)
+            rank = min(p.shape)
+            self.direct = self.direct and rank == ops.RANK
+
+    def gather_autograd_grads(self) -> None:
+        """Ranks other than 16 take the generic autograd route (`p.grad`); fold those into the flat buffer."""
+        for p in self.params:
+            if p.grad is not None:
+                p._vpt_grad32.add_(p.grad.float())
+                p.grad = None
+
+
+@dataclass
+class TrainHParams:
+    lr: float = 1e-4
+    betas: tuple[float, float] = (0.9, 0.999)
+    eps: float = 1e-8
+    weight_decay: float = 0.01
+    clip_grad_norm: float | None = 1.0
+    loss_target: str = "image"        # configs/jit/x-loss/config.yml:21 ("image" | "velocity")
+    timestep_eps: float = 0.05
+    noise_scale: float = 1.0
+    ts_std: float = 0.8               # scale_shift_sigmoid timestep sampling (src/modules/timestep/sampling.py:259-272)
+    ts_mean: float = -0.8
+
+
+class JiTQLoRATrainStep:
+    """One optimisation step of JiT NF4-QLoRA class-to-image training; `run()` replays a captured CUDA graph.
+
+    Inputs of a step (static device buffers the caller fills, e.g. by an async copy from pinned host memory):
+      image [B,3,H,W] fp16 (the dataset emits fp16, src/dataset/text_to_image.py:152), class_ids [B,T] int64,
+      attention_mask [B,T] int64 (leading ones).  Output: `loss` (fp32 device scalar of the last step)."""
+
+    def __init__(self, model: Denoiser, batch: int, height: int, width: int, num_classes: int = 1000,
+                 max_token_length: int = 64, hp: TrainHParams | None = None, process_group=None, use_graph: bool = True,
+                 seed: int = 0):
+        self.model = model
+        self.hp = hp or TrainHParams()
+        self.group = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        dev = next(model.parameters()).device
+        self.device = dev
+        cfg = model.config
+        gen = torch.Generator(device="cpu").manual_seed(1234)   # same class table on every rank (replicated, frozen)
+        self.class_encoder = ClassEncoder(num_classes, cfg.context_dim)
+        with torch.no_grad():
+            self.class_encoder.embedding.weight.copy_(torch.randn(num_classes + 1, cfg.context_dim, generator=gen) * 0.02)
+            self.class_encoder.embedding.weight[num_classes].zero_()
+        self.class_encoder.to(dev, torch.bfloat16).requires_grad_(False)
+        self.flat = FlatLoRA(model)
+        n = self.flat.numel
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.image = torch.zeros((batch, cfg.in_channels, height, width), dtype=torch.float16, device=dev)
+        self.class_ids = torch.full((batch, max_token_length), num_classes, dtype=torch.int64, device=dev)
+        self.attention_mask = torch.zeros((batch, max_token_length), dtype=torch.int64, device=dev)
+        self.size_info = torch.tensor([[height, width]], device=dev).repeat(batch, 1)
+        self.crop = torch.zeros_like(self.size_info)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.graph: torch.cuda.CUDAGraph | None = None
+        self.kernel_launches = 0
+        torch.manual_seed(seed)
+        model.train()
+
+    # ------------------------------------------------------------------ the step itself (eager or under capture)
+    def _step(self) -> None:
+        hp = self.hp
+        images = self.image
+        B = images.shape[0]
+        with torch.no_grad():
+            context = self.class_encoder(self.class_ids)
+            t = (torch.randn(B, device=self.device) * hp.ts_std + hp.ts_mean).sigmoid()
+            noise = torch.randn_like(images) * hp.noise_scale
+            tv = t.view(B, 1, 1, 1).to(images.dtype)
+            noisy = tv * images + (1 - tv) * noise
+        pred = self.model(image=noisy.to(torch.bfloat16), timestep=t.to(torch.bfloat16), context=context,
+                          original_size=self.size_info, target_size=self.size_info, crop_coords=self.crop,
+                          context_mask=self.attention_mask)
+        loss = ops.flow_loss(pred, images, noisy, t, loss_target=hp.loss_target, clamp_eps=hp.timestep_eps)
+        loss.backward()
+        if not self.flat.direct:
+            self.flat.gather_autograd_grads()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat.grad, group=self.group)   # SUM; the mean is folded into grad_scale
+        scale = 1.0 / self.world
+        sumsq = None
+        if hp.clip_grad_norm is not None:
+            self.sumsq.zero_()
+            ops.grad_sumsq(self.flat.grad, scale, self.sumsq)
+            sumsq = self.sumsq
+        self.step_t += 1
+        ops.adamw_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.step_t, hp.lr, hp.betas, hp.eps,
+                       hp.weight_decay, grad_scale=scale, sumsq=sumsq, max_norm=hp.clip_grad_norm or 0.0, zero_grad=True)
+        self.loss.copy_(loss.detach())
+
+    def capture(self, warmup: int = 2) -> None:
+        """Eager warm-up on a side stream (one-time kernel attribute setup, allocator growth, NCCL init), then capture."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        before = ops._lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        self.kernel_launches = ops._lib.launch_count() - before
+
+    def run(self) -> torch.Tensor:
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            before = ops._lib.launch_count()
+            self._step()
+            self.kernel_launches = ops._lib.launch_count() - before
+        return self.loss
+
+
+def synthetic_batch(batch: int, height: int, width: int, num_classes: int = 1000, max_token_length: int = 64,
+                    seed: int = 0, pin: bool = True):
+    """Host-side synthetic batch of the named shape: image ~ N(0,1) fp16, 8..40 valid labels per sample."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn((batch, 3, height, width), generator=g).to(torch.float16)
+    n_labels = torch.randint(8, 41, (batch,), generator=g)
+    ids = torch.randint(0, num_classes, (batch, max_token_length), generator=g)
+    ar = torch.arange(max_token_length).unsqueeze(0)
+    mask = (ar < n_labels.unsqueeze(1)).to(torch.int64)
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, num_classes))
+    out = (image, ids, mask)
+    if pin and torch.cuda.is_available():
+        out = tuple(t.pin_memory() for t in out)
+    return out
+
+
+def step_flops(cfg: DenoiserConfig, batch: int, height: int, width: int, ctx_len: int = 64, rank: int = 16) -> dict:
+    """Algorithmic FLOPs of one training step (fwd + bwd, blocks only): per linear 4 M K N + 6 M r (K+N),
+    attention 4 B H L^2 hd forward and 2.5x that backward (full L x L counted)."""
+    D, H = cfg.hidden_size, cfg.num_heads
+    hd = D // H
+    F = int(int(D * cfg.mlp_ratio) * 2 / 3)
+    n_patch = (height // cfg.patch_size) * (width // cfg.patch_size)
+    pre = n_patch + 6 + cfg.num_time_tokens
+    lin = attn = 0.0
+    for i in range(cfg.depth):
+        L = pre + (ctx_len if i >= cfg.context_start_block else 0)
+        M = batch * L
+        for (K, N) in ((D, D),) * 4 + ((D, F),) * 2 + ((F, D),):
+            lin += 4.0 * M * K * N + 6.0 * M * rank * (K + N)
+        attn += 3.5 * 4.0 * batch * H * L * L * hd
+    return {"linear": lin, "attention": attn, "total": lin + attn}
