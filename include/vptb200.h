@@ -62,7 +62,7 @@ int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const float* nested_
  *   y = x W^T + bias + Ts lora_up^T (+ residual),   Ts = bf16(scale * x lora_down^T),   scale = alpha / rank
  * and the activation gradient of the same (MatMul4Bit.backward + autograd of the LoRA branch):
  *   dx = dy W + dTs lora_down (+ residual),         dTs = bf16(scale * dy lora_up)
- * rank is 16 (pad smaller ranks with zero rows/columns).  K % 64 == 0 or a repacked weight.  x/dy/y/dx are row-major with the given
+ * rank is 16 (pad smaller ranks with zero rows/columns).  K % 64 == 0, a repacked weight, or w_scratch given.  x/dy/y/dx are row-major with the given
  * leading dimensions (multiples of 8 elements).  `side` receives Ts / dTs ([M,16] bf16) for the parameter gradients. */
 typedef struct {
   vpt_nf4_weight w;
@@ -81,6 +81,12 @@ typedef struct {
   void* side;                  /* [M,16] bf16 or NULL */
   int32_t M;
   int32_t tile_n;              /* 0 = auto (128 or 192) */
+  /* Optional caller-owned workspace [N, ld_scratch] bf16 (ld_scratch >= K, multiple of 8).  When given with an NF4
+   * weight, the weight is dequantised ONCE per call into it (bit-identical values; it stays L2-resident) and the
+   * tcgen05 main loop reads it by TMA, instead of every CTA re-dequantising its weight tile per 128-row block of x.
+   * This is the large-M (training) path; NULL selects the per-stage prologue dequantiser (small M). */
+  void* w_scratch;
+  int64_t ld_scratch;
 } vpt_linear_args;
 
 int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream);

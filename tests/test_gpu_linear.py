@@ -35,10 +35,15 @@ def _make(M, K, N, rank, nf4, bias, seed=0):
 
 @pytest.mark.parametrize("M,K,N", [(300, 128, 192), (257, 768, 768), (130, 768, 2048), (129, 2048, 768), (64, 64, 200),
                                    (200, 341, 128), (150, 128, 341), (140, 2730, 1024), (131, 1024, 2730)])
-@pytest.mark.parametrize("nf4", [True, False])
+@pytest.mark.parametrize("nf4", ["prologue", "scratch", False])
 @pytest.mark.parametrize("rank", [16, 4])
-def test_lora_linear_forward_backward(M, K, N, nf4, rank):
-    layer, w_ref, x = _make(M, K, N, rank, nf4, bias=True)
+def test_lora_linear_forward_backward(M, K, N, nf4, rank, monkeypatch):
+    """nf4 = how the NF4 weight reaches the tensor cores: per-stage prologue dequant, or once per call into the bf16
+    workspace (include/vptb200.h: w_scratch); False = plain bf16 base weight."""
+    from vision_pt_b200 import ops
+    if nf4:
+        monkeypatch.setattr(ops, "NF4_GEMM_MODE", nf4)
+    layer, w_ref, x = _make(M, K, N, rank, bool(nf4), bias=True)
     if nf4:
         # the quantised module holds exactly the oracle's codes for this weight
         assert torch.equal(layer.linear.weight.cpu(), w_ref.packed)
@@ -99,9 +104,29 @@ def test_base_output_matches_dequant_matmul():
     assert rel_err(q(x), ref) <= 1e-2
 
 
-def test_residual_and_linearity():
+def test_scratch_and_prologue_paths_agree_bitwise():
+    """Both NF4 routes feed the tensor cores the same bf16 weight bits, so whole outputs agree exactly (same tile order)."""
+    from vision_pt_b200 import ops
+    for (K, N) in ((768, 768), (1024, 2730), (2730, 1024)):
+        layer, _, _ = _make(8, K, N, 16, True, bias=True, seed=11)
+        x = (torch.randn(1500, K, device="cuda") * 0.5).to(torch.bfloat16)
+        st = layer.linear.quant_state
+        args = (st, layer.linear.bias, layer.lora_down.weight, layer.lora_up.weight, layer.scale)
+        outs = []
+        for mode in ("prologue", "scratch"):
+            ops.NF4_GEMM_MODE = mode
+            try:
+                outs.append(ops.nf4_lora_linear(x, *args))
+            finally:
+                ops.NF4_GEMM_MODE = "auto"
+        assert torch.equal(outs[0], outs[1]), (K, N)
+
+
+@pytest.mark.parametrize("mode", ["prologue", "scratch"])
+def test_residual_and_linearity(mode, monkeypatch):
     """size-independent properties at the bench shape: f(x) + r == f(x; residual=r); f(2x) - b == 2 (f(x) - b)."""
     from vision_pt_b200 import ops
+    monkeypatch.setattr(ops, "NF4_GEMM_MODE", mode)
     layer, _, _ = _make(8, 768, 768, 16, True, bias=True, seed=9)
     M = 21120
     x = (torch.randn(M, 768, device="cuda") * 0.5).to(torch.bfloat16)

@@ -80,7 +80,23 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
   const int N = a->w.N, K = a->w.K;
   VPT_REQUIRE(N > 0 && K > 0 && a->M > 0, "vpt_nf4lora_linear: bad shape");
   VPT_REQUIRE(a->ld_in % 8 == 0 && a->ld_out % 8 == 0, "vpt_nf4lora_linear: leading dimensions must be multiples of 8");
-  const bool nf4 = a->w_bf16 == nullptr;
+  const bool via_scratch = a->w_bf16 == nullptr && a->w_scratch != nullptr;
+  const void* w_dense = a->w_bf16;
+  long ldw = 0;
+  if (via_scratch) {
+    // dequantise once per call into the caller's L2-resident workspace, then run the TMA-fed bf16 main loop on it
+    VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
+    VPT_REQUIRE(a->ld_scratch >= K && a->ld_scratch % 8 == 0 && (reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0,
+                "vpt_nf4lora_linear: w_scratch needs a 16-byte aligned base and a row pitch >= K that is a multiple of 8");
+    const long n = static_cast<long>(N) * K;
+    nf4_dequant_pitched_kernel<<<blocks_for((n + 7) / 8, 256, 148 * 16), 256, 0, stream>>>(
+        a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset,
+        static_cast<__nv_bfloat16*>(a->w_scratch), n, K, static_cast<long>(a->ld_scratch));
+    VPT_CUDA_OK(cudaGetLastError());
+    w_dense = a->w_scratch;
+    ldw = static_cast<long>(a->ld_scratch);
+  }
+  const bool nf4 = w_dense == nullptr;
   const bool ragged = nf4 && a->w.packed_rows != nullptr;
   if (nf4) {
     VPT_REQUIRE(a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 code tables missing");
@@ -90,14 +106,14 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
       VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax, "vpt_nf4lora_linear: NF4 tensors missing");
       VPT_REQUIRE(K % 64 == 0, "vpt_nf4lora_linear: in_features must be a multiple of 64 (repack ragged weights with vpt_nf4_repack)");
     }
-  } else {
+  } else if (!via_scratch) {
     VPT_REQUIRE(K % 8 == 0, "vpt_nf4lora_linear: a bf16 weight needs in_features % 8 == 0");
   }
   const bool lora = a->lora_down != nullptr;
   if (lora) VPT_REQUIRE(a->lora_up != nullptr && a->ld_lora_down % 8 == 0 && a->ld_lora_down >= K, "vpt_nf4lora_linear: bad LoRA arguments");
   GemmLaunch g{};
   g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = a->tile_n;
-  g.act = a->in; g.lda = static_cast<int>(a->ld_in); g.w_bf16 = a->w_bf16;
+  g.act = a->in; g.lda = static_cast<int>(a->ld_in); g.w_bf16 = w_dense; g.ldw = ldw;
   g.p.M = a->M; g.p.NO = bwd ? K : N; g.p.R = bwd ? N : K;
   g.p.D = static_cast<__nv_bfloat16*>(a->out); g.p.ldd = static_cast<int>(a->ld_out);
   g.p.bias = bwd ? nullptr : static_cast<const __nv_bfloat16*>(a->bias);

@@ -12,6 +12,7 @@ struct GemmLaunch {
   const void* act;               // A operand [M, R] bf16
   int lda;
   const void* w_bf16;            // [N, K] bf16 when !nf4
+  long ldw;                      // row pitch of w_bf16 in elements (0 = K)
   GemmParams p;                  // M, NO, R, D, ldd, bias, w, lora_*, scale, side filled by the caller
   int max_ctas;                  // 0 = all SMs
 };
@@ -28,7 +29,7 @@ int launch_gemm_t(const GemmLaunch& g, cudaStream_t stream) {
   tmB = tmA;
   tmP = tmA;
   if (!kNF4) {
-    if (make_tmap_bf16_2d(&tmB, g.w_bf16, p.w.K, p.w.N, static_cast<uint64_t>(p.w.K) * 2, 64, kBwd ? 64 : BN,
+    if (make_tmap_bf16_2d(&tmB, g.w_bf16, p.w.K, p.w.N, static_cast<uint64_t>(g.ldw > 0 ? g.ldw : p.w.K) * 2, 64, kBwd ? 64 : BN,
                           CU_TENSOR_MAP_SWIZZLE_128B))
       return 1;
   }

@@ -71,6 +71,62 @@ nf4_dequant_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict
   }
 }
 
+// Dequantise the FLATTENED bitsandbytes layout into a row-pitched bf16 matrix out[n * ld + k] (ld >= K, ld % 8 == 0):
+// the operand the TMA-fed GEMM reads.  Values are the same bits as nf4_dequant_kernel<bf16>; only the addressing
+// differs, so ragged in_features (2730, 3413: rows that start mid-byte / mid-block) need no repacked copy.
+// One thread = one 32-bit word of codes = 8 weights of one 64-block.
+__global__ void __launch_bounds__(256)
+nf4_dequant_pitched_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ qabsmax,
+                           const float* __restrict__ nested_absmax, const float* __restrict__ nested_code,
+                           const float* __restrict__ code, float offset, __nv_bfloat16* __restrict__ out, long n, int K,
+                           long ld) {
+  __shared__ float s_code[16];
+  __shared__ float s_ncode[256];
+  if (threadIdx.x < 16) s_code[threadIdx.x] = code[threadIdx.x];
+  s_ncode[threadIdx.x] = nested_code[threadIdx.x];
+  __syncthreads();
+  const long nbytes = (n + 1) >> 1;
+  for (long byte0 = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; byte0 < nbytes;
+       byte0 += static_cast<long>(gridDim.x) * blockDim.x * 4) {
+    const long e0 = byte0 * 2;
+    const long blk = e0 >> 6;
+    const float am = __fadd_rn(__fmul_rn(s_ncode[qabsmax[blk]], nested_absmax[blk >> 8]), offset);
+    uint32_t w;
+    if (byte0 + 4 <= nbytes) {
+      w = *reinterpret_cast<const uint32_t*>(packed + byte0);
+    } else {
+      w = 0;
+      for (int b = 0; byte0 + b < nbytes; ++b) w |= static_cast<uint32_t>(packed[byte0 + b]) << (8 * b);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t byte = (w >> (8 * b)) & 0xffu;
+      const __nv_bfloat162 h = __floats2bfloat162_rn(__fmul_rn(s_code[byte >> 4], am), __fmul_rn(s_code[byte & 15u], am));
+      o[b] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const long row = e0 / K;
+    const int col = static_cast<int>(e0 - row * K);
+    __nv_bfloat16* dst = out + row * ld + col;
+    if (col + 8 <= K && e0 + 8 <= n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      long r = row;
+      int c = col;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (e0 + e >= n) break;
+        const uint32_t v = o[e >> 1];
+        reinterpret_cast<unsigned short*>(out)[r * ld + c] = (e & 1) ? static_cast<unsigned short>(v >> 16) : static_cast<unsigned short>(v & 0xffffu);
+        if (++c == K) {
+          c = 0;
+          ++r;
+        }
+      }
+    }
+  }
+}
+
 // Load-time repack for ragged in_features (K % 64 != 0, e.g. the SwiGLU hidden 2730 / 3413 of JiT-L / -H): bitsandbytes
 // packs the FLATTENED [N,K] weight, so rows start at arbitrary nibbles and 64-blocks straddle rows.  The GEMM producers
 // want 16-byte aligned rows: codes are re-packed row by row with pitch K_pad/2 bytes (K_pad = K rounded up to 64, padding

@@ -14,6 +14,26 @@ from ._lib import AttnTensorC, LinearArgsC, Nf4WeightC
 
 RANK = 16  # LoRA rank of the fused kernels; smaller ranks are zero-padded
 
+# How an NF4 weight reaches the tensor cores (include/vptb200.h: vpt_linear_args.w_scratch):
+#   "scratch"  : dequantised once per call into an L2-resident bf16 workspace, main loop fed by TMA  (large M)
+#   "prologue" : dequantised per pipeline stage by the producer warps of every CTA                    (small M)
+#   "auto"     : scratch when M >= NF4_SCRATCH_MIN_M
+NF4_GEMM_MODE = "auto"
+NF4_SCRATCH_MIN_M = 1024
+_SCRATCH: dict[tuple, torch.Tensor] = {}
+
+
+def _weight_scratch(device: torch.device, numel: int) -> torch.Tensor:
+    """Per (device, stream) bf16 workspace for the dequantised weight; kernels on one stream run in order, so one
+    buffer per stream is enough.  Grown geometrically, never freed."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(numel, 8 << 20), dtype=torch.bfloat16, device=device)
+        _SCRATCH[key] = buf
+    return buf
+
+
 # bench.py sets this to a list to bracket every fused-linear launch with CUDA events on the launching stream
 # (roofline of the dominant kernel, measured inside real training steps); None = no instrumentation.
 GEMM_TIMER: list | None = None
@@ -154,15 +174,22 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     if x2.dtype != torch.bfloat16:
         raise TypeError("fused linear runs in bfloat16")
     args = LinearArgsC()
+    M = x2.shape[0]
+    scratch = None
     if isinstance(w, Nf4Tensors):
-        args.w = w.c_struct(for_gemm=True)
         N, K = w.shape
+        use_scratch = NF4_GEMM_MODE == "scratch" or (NF4_GEMM_MODE == "auto" and M >= NF4_SCRATCH_MIN_M)
+        args.w = w.c_struct(for_gemm=not use_scratch)
         args.w_bf16 = None
+        if use_scratch:
+            ld_s = (K + 7) // 8 * 8
+            scratch = _weight_scratch(x2.device, N * ld_s)
+            args.w_scratch = _p(scratch)
+            args.ld_scratch = ld_s
     else:
         N, K = w.shape
         args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K), None, None, 0)
         args.w_bf16 = _p(w)
-    M = x2.shape[0]
     n_out = K if backward else N
     ld_out = (n_out + 7) // 8 * 8
     out_full = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x2.device)
