@@ -104,6 +104,17 @@ class FlatLoRA:
             rank = min(p.shape)
             self.direct = self.direct and rank == ops.RANK
 
+    def all_reduce(self, group=None) -> float:
+        """The one exchange step of data parallelism (reference: DDP's bucketed all-reduce of the trainable = LoRA
+        gradients, src/trainer/common.py:62-65,376-380): SUM all-reduce of the flat fp32 gradient buffer.  Returns the
+        factor that turns the sum into the mean; the optimiser kernel folds it in (grad_scale)."""
+        if group is None and not torch.distributed.is_initialized():
+            return 1.0
+        world = torch.distributed.get_world_size(group)
+        if world > 1:
+            torch.distributed.all_reduce(self.grad, group=group)
+        return 1.0 / world
+
     def gather_autograd_grads(self) -> None:
         """Ranks other than 16 take the generic autograd route (`p.grad`); fold those into the flat buffer."""
         for p in self.params:
@@ -185,9 +196,7 @@ class JiTQLoRATrainStep:
         loss.backward()
         if not self.flat.direct:
             self.flat.gather_autograd_grads()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat.grad, group=self.group)   # SUM; the mean is folded into grad_scale
-        scale = 1.0 / self.world
+        scale = self.flat.all_reduce(self.group) if self.world > 1 else 1.0   # SUM; the mean is folded into grad_scale
         sumsq = None
         if hp.clip_grad_norm is not None:
             self.sumsq.zero_()
