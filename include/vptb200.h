@@ -81,14 +81,17 @@ typedef struct {
   void* side;                  /* [M,16] bf16 or NULL */
   int32_t M;
   int32_t tile_n;              /* 0 = auto (128 or 192) */
-  /* Optional caller-owned workspace [N, ld_scratch] bf16 (ld_scratch >= K, multiple of 8).  When given with an NF4
-   * weight, the weight is dequantised ONCE per call into it (bit-identical values; it stays L2-resident) and the
-   * tcgen05 main loop reads it by TMA, instead of every CTA re-dequantising its weight tile per 128-row block of x.
-   * This is the large-M (training) path; NULL selects the per-stage prologue dequantiser (small M). */
+  /* Optional caller-owned workspace of vpt_linear_scratch_bytes(N, K) bytes, 16-byte aligned.  When given with an NF4
+   * weight, the weight is dequantised ONCE per call into it (bit-identical values; it stays L2-resident) -- [N, K] for the
+   * forward, transposed [K, N] for the backward -- and the CTA-pair tcgen05 main loop reads it by TMA, instead of every
+   * CTA re-dequantising its weight tile per 128-row block of x.  This is the large-M (training) path; NULL selects
+   * the per-stage prologue dequantiser (small M). */
   void* w_scratch;
-  int64_t ld_scratch;
+  int64_t ld_scratch;          /* unused since ABI 2 (kept for layout compatibility) */
+  int64_t scratch_bytes;       /* capacity of w_scratch */
 } vpt_linear_args;
 
+int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K);
 int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream);
 int vpt_nf4lora_linear_bwd_dx(const vpt_linear_args* a, vpt_stream_t stream);
 

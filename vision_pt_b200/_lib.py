@@ -23,7 +23,7 @@ class LinearArgsC(C.Structure):
         ("w", Nf4WeightC), ("w_bf16", C.c_void_p), ("bias", C.c_void_p), ("lora_down", C.c_void_p),
         ("ld_lora_down", C.c_int64), ("lora_up", C.c_void_p), ("scale", C.c_float), ("inp", C.c_void_p), ("ld_in", C.c_int64), ("out", C.c_void_p),
         ("ld_out", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64), ("side", C.c_void_p), ("M", C.c_int32),
-        ("tile_n", C.c_int32), ("w_scratch", C.c_void_p), ("ld_scratch", C.c_int64),
+        ("tile_n", C.c_int32), ("w_scratch", C.c_void_p), ("ld_scratch", C.c_int64), ("scratch_bytes", C.c_int64),
     ]
 
 
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.vpt_last_error.restype = C.c_char_p
     lib.vpt_last_error.argtypes = []
     lib.vpt_abi_version.restype = C.c_int
+    lib.vpt_linear_scratch_bytes.restype = C.c_int64
+    lib.vpt_linear_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -94,6 +96,12 @@ _launches = 0
 def launch_count() -> int:
     """Number of libvptb200 kernels launched by this process so far."""
     return _launches
+
+
+def add_launches(n: int) -> None:
+    """Extra kernels a call launched beyond the first (e.g. the per-call NF4 dequantisation in front of a GEMM)."""
+    global _launches
+    _launches += n
 
 
 def call(name: str, *args) -> None:

@@ -1,9 +1,12 @@
 // extern "C" entry points declared in include/vptb200.h.  Thin argument checking + kernel launches.
 #include "../../include/vptb200.h"
 
+#include <stdlib.h>
+
 #include "attn_launch.cuh"
 #include "elementwise.cuh"
 #include "gemm_launch.cuh"
+#include "gemm_pair_launch.cuh"
 #include "lora_grad.cuh"
 #include "nf4.cuh"
 #include "optim.cuh"
@@ -19,7 +22,7 @@ static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
 }
 
 extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
-extern "C" int vpt_abi_version(void) { return 1; }
+extern "C" int vpt_abi_version(void) { return 2; }
 
 // ---------------------------------------------------------------------------------------------------- NF4
 extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
@@ -75,26 +78,78 @@ extern "C" int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------- linear
+extern "C" int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K) {
+  const int64_t ldk = (K + 7) / 8 * 8, ldn = (N + 7) / 8 * 8;
+  const int64_t fwd = static_cast<int64_t>(N) * ldk;
+  const int64_t bwd = static_cast<int64_t>(K) * ldn + 16 * ldn + static_cast<int64_t>(K) * 16;
+  return 2 * (fwd > bwd ? fwd : bwd) + 256;
+}
 static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream) {
   VPT_REQUIRE(a && a->in && a->out, "vpt_nf4lora_linear: null pointer");
   const int N = a->w.N, K = a->w.K;
   VPT_REQUIRE(N > 0 && K > 0 && a->M > 0, "vpt_nf4lora_linear: bad shape");
   VPT_REQUIRE(a->ld_in % 8 == 0 && a->ld_out % 8 == 0, "vpt_nf4lora_linear: leading dimensions must be multiples of 8");
   const bool via_scratch = a->w_bf16 == nullptr && a->w_scratch != nullptr;
+  const bool lora = a->lora_down != nullptr;
+  if (lora) VPT_REQUIRE(a->lora_up != nullptr && a->ld_lora_down % 8 == 0 && a->ld_lora_down >= K, "vpt_nf4lora_linear: bad LoRA arguments");
+  static const bool use_pairs = getenv("VPT_NO_PAIR") == nullptr;   // A/B switch for profiling the 1-CTA kernel
+  if (use_pairs && (via_scratch || (a->w_bf16 != nullptr && !bwd && K % 8 == 0))) {
+    // Large-M route: CTA-pair kernel over a K-major bf16 weight.  An NF4 weight is dequantised once per call into the
+    // caller's L2-resident workspace -- as [N, K] for the forward, TRANSPOSED [K, N] (plus the two transposed LoRA
+    // matrices) for the backward, so that both directions run the same kernel.
+    PairLaunch g{};
+    g.act = a->in; g.lda = static_cast<int>(a->ld_in);
+    g.out = a->out; g.ldd = static_cast<int>(a->ld_out);
+    g.bn = a->tile_n;
+    g.p.M = a->M; g.p.NO = bwd ? K : N; g.p.R = bwd ? N : K;
+    g.p.bias = bwd ? nullptr : static_cast<const __nv_bfloat16*>(a->bias);
+    g.p.residual = static_cast<const __nv_bfloat16*>(a->residual); g.p.ldr = static_cast<int>(a->ld_res);
+    g.p.scale = a->scale;
+    g.p.side = static_cast<__nv_bfloat16*>(a->side);
+    if (via_scratch) {
+      VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
+      VPT_REQUIRE((reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0 && a->scratch_bytes >= vpt_linear_scratch_bytes(N, K),
+                  "vpt_nf4lora_linear: w_scratch must be 16-byte aligned and hold vpt_linear_scratch_bytes(N, K) bytes");
+      __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(a->w_scratch);
+      const long n = static_cast<long>(N) * K;
+      if (!bwd) {
+        const long ldk = (K + 7) / 8 * 8;
+        nf4_dequant_pitched_kernel<<<blocks_for((n + 7) / 8, 256, 148 * 16), 256, 0, stream>>>(
+            a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, ws, n, K, ldk);
+        g.w = ws; g.ldw = ldk;
+        g.p_rows = a->lora_down; g.ldp = a->ld_lora_down;
+        g.p.q_rows = static_cast<const __nv_bfloat16*>(a->lora_up);
+      } else {
+        const long ldn = (N + 7) / 8 * 8;
+        __nv_bfloat16* upT = ws + static_cast<long>(K) * ldn;       // [16, ldn]
+        __nv_bfloat16* downT = upT + 16 * ldn;                      // [K, 16]
+        const int tiles_k = (K + 63) / 64, tiles = ((N + 63) / 64) * tiles_k;
+        nf4_dequant_transposed_kernel<<<tiles + (lora ? 4 : 0), 256, 0, stream>>>(
+            a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, ws, N, K, ldn, tiles_k,
+            tiles, static_cast<const __nv_bfloat16*>(a->lora_up), upT, ldn, static_cast<const __nv_bfloat16*>(a->lora_down),
+            static_cast<long>(a->ld_lora_down), downT);
+        g.w = ws; g.ldw = ldn;
+        g.p_rows = lora ? upT : nullptr; g.ldp = ldn;
+        g.p.q_rows = downT;
+      }
+      VPT_CUDA_OK(cudaGetLastError());
+    } else {
+      g.w = a->w_bf16; g.ldw = K;
+      g.p_rows = a->lora_down; g.ldp = a->ld_lora_down;
+      g.p.q_rows = static_cast<const __nv_bfloat16*>(a->lora_up);
+    }
+    return launch_pair(g, stream);
+  }
   const void* w_dense = a->w_bf16;
   long ldw = 0;
   if (via_scratch) {
-    // dequantise once per call into the caller's L2-resident workspace, then run the TMA-fed bf16 main loop on it
-    VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
-    VPT_REQUIRE(a->ld_scratch >= K && a->ld_scratch % 8 == 0 && (reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0,
-                "vpt_nf4lora_linear: w_scratch needs a 16-byte aligned base and a row pitch >= K that is a multiple of 8");
     const long n = static_cast<long>(N) * K;
+    ldw = (K + 7) / 8 * 8;
     nf4_dequant_pitched_kernel<<<blocks_for((n + 7) / 8, 256, 148 * 16), 256, 0, stream>>>(
         a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset,
-        static_cast<__nv_bfloat16*>(a->w_scratch), n, K, static_cast<long>(a->ld_scratch));
+        static_cast<__nv_bfloat16*>(a->w_scratch), n, K, ldw);
     VPT_CUDA_OK(cudaGetLastError());
     w_dense = a->w_scratch;
-    ldw = static_cast<long>(a->ld_scratch);
   }
   const bool nf4 = w_dense == nullptr;
   const bool ragged = nf4 && a->w.packed_rows != nullptr;
@@ -106,11 +161,9 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
       VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax, "vpt_nf4lora_linear: NF4 tensors missing");
       VPT_REQUIRE(K % 64 == 0, "vpt_nf4lora_linear: in_features must be a multiple of 64 (repack ragged weights with vpt_nf4_repack)");
     }
-  } else if (!via_scratch) {
+  } else {
     VPT_REQUIRE(K % 8 == 0, "vpt_nf4lora_linear: a bf16 weight needs in_features % 8 == 0");
   }
-  const bool lora = a->lora_down != nullptr;
-  if (lora) VPT_REQUIRE(a->lora_up != nullptr && a->ld_lora_down % 8 == 0 && a->ld_lora_down >= K, "vpt_nf4lora_linear: bad LoRA arguments");
   GemmLaunch g{};
   g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = a->tile_n;
   g.act = a->in; g.lda = static_cast<int>(a->ld_in); g.w_bf16 = w_dense; g.ldw = ldw;

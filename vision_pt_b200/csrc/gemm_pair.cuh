@@ -1,0 +1,326 @@
+// LoRA GEMM on CTA pairs (tcgen05 cta_group::2): the large-M (training) route of the fused NF4-LoRA linear.
+//
+//   D[M, NO] = A[M, R] * Bw[NO, R]^T + bias + Ts * Q[NO, 16]^T (+ residual),   Ts = bf16(scale * A * P[16, R]^T)
+//
+// forward :  A = x,  Bw = dequantised weight [N, K],            P = lora_down [16, K],   Q = lora_up [N, 16]
+// backward:  A = dy, Bw = dequantised weight transposed [K, N], P = lora_up^T [16, N],   Q = lora_down^T [K, 16]
+// (src/modules/quant/bnb.py:37-129 + src/modules/peft/lora.py:92-104 of the reference and their autograd).  The weight
+// arrives as the bf16 workspace the NF4 dequantiser filled for this call (nf4.cuh), so every operand is K-major and the
+// two directions are the same kernel.
+//
+// Why pairs: with one CTA per 128x192 tile the main loop pulls 104 B per SM-cycle out of L2 and measured 49 % tensor-pipe
+// activity at 48 % L2 throughput (profiles/r1b_gemm_1cta.txt).  A pair computes a 256 x BN tile: each CTA loads its own 128
+// rows of A and HALF of the B rows; the tensor cores of both SMs read both halves.  L2 bytes per FLOP drop by 1.45x.
+//
+// Per CTA, 8 warps: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) + TMEM allocator, warps 4-7 epilogue
+// (TMEM -> registers -> 128B-swizzled smem slabs -> TMA store).  Accumulators are double buffered in TMEM (2 x 256 columns);
+// the 16 LoRA columns ride in the same UMMA (N = BN + 16), the rank-16 update is one more K=16 UMMA issued while the next
+// tile's main loop is already running.
+#pragma once
+#include "sm100.cuh"
+
+namespace vpt {
+
+constexpr int kPairThreads = 256;
+constexpr int kPairEpiWarp0 = 4;
+constexpr int kPairRank = 16;
+
+struct PairParams {
+  int M, NO, R;
+  const __nv_bfloat16* bias;       // [NO] or nullptr
+  const __nv_bfloat16* residual;   // [M, NO] pitch ldr, or nullptr
+  int ldr;
+  const __nv_bfloat16* q_rows;     // [NO, 16] second-phase LoRA operand
+  float scale;
+  __nv_bfloat16* side;             // [M, 16] or nullptr
+  int num_m_pairs, num_n_tiles;
+};
+
+template <int BN, bool kLoRA>
+struct PairSmem {
+  static constexpr int kNT = BN + (kLoRA ? kPairRank : 0);   // UMMA N
+  static constexpr int kNH = kNT / 2;                         // B rows held by each CTA
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = (kNH * 128 + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSlabBytes = 32 * 128;                 // one warp's [32 rows x 64 cols] bf16 output slab
+  static constexpr int kOutBytes = 4 * 2 * kSlabBytes;
+  static constexpr int kTsBytes = 128 * 32;
+  static constexpr int kQBytes = (BN / 2) * 32;
+  static constexpr int kBiasBytes = BN * 4;
+  static constexpr int kFixed = kOutBytes + kTsBytes + kQBytes + kBiasBytes + 256 + 1024;
+  static constexpr int kStagesRaw = (227 * 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kOffOut = kStages * kStageBytes;
+  static constexpr int kOffTs = kOffOut + kOutBytes;
+  static constexpr int kOffQ = kOffTs + kTsBytes;
+  static constexpr int kOffBias = kOffQ + kQBytes;
+  static constexpr int kOffBars = kOffBias + kBiasBytes;
+  static constexpr int kNumBars = 2 * kStages + 7;
+  static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+// tmA : A [M, R],           box {64, 128}
+// tmB0: Bw [NO, R],         box {64, kNH}            rows o0 .. o0 + kNH            (CTA 0)
+// tmB1: Bw [NO, R],         box {64, kNH - 16 | kNH} rows o0 + kNH .. o0 + BN       (CTA 1)
+// tmP : P [16, R],          box {64, 16}             appended below CTA 1's weight rows
+// tmD : D [M, NO],          box {64, 32}             (store)                         all SWIZZLE_128B
+template <int BN, bool kLoRA>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmP,
+                 const __grid_constant__ CUtensorMap tmD, const PairParams p) {
+  using S = PairSmem<BN, kLoRA>;
+  static_assert(BN % 64 == 0 && BN >= 64 && S::kNT <= 256, "unsupported BN");
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kIdescMain = umma_idesc_bf16(256, S::kNT, 0, 0);
+  constexpr uint32_t kIdescLora = umma_idesc_bf16(256, BN, 0, 0);
+  constexpr uint32_t kStageTx = S::kABytes + S::kNH * 128;     // bytes each CTA's loads credit per stage
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBars);
+  uint64_t* full = bars;                       // [kStages] leader's copy is the live one (count 2 + both CTAs' bytes)
+  uint64_t* empty = bars + kStages;            // [kStages] per CTA, arrived by the multicast commit
+  uint64_t* tmem_full = bars + 2 * kStages;    // [2] per CTA: main loop of a tile finished
+  uint64_t* tmem_full2 = tmem_full + 2;        // [2] per CTA: rank-16 update finished
+  uint64_t* tmem_empty = tmem_full2 + 2;       // [2] leader's: 8 epilogue warps (both CTAs) drained the buffer
+  uint64_t* ts_full = tmem_empty + 2;          // [1] leader's: 8 epilogue warps staged Ts / Q
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kOffTmemSlot);
+  float* s_bias = reinterpret_cast<float*>(smem + S::kOffBias);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.num_m_pairs * p.num_n_tiles;
+  const int ksteps = (p.R + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_full2[b], 1);
+      mbar_init(&tmem_empty[b], 8);
+    }
+    mbar_init(ts_full, 8);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(leader ? &tmB0 : &tmB1);
+    if (kLoRA && !leader) tma_prefetch_desc(&tmP);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                           // the peer's barriers exist before anything remote touches them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128;
+        const int o0 = (tile % p.num_n_tiles) * BN;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          const uint32_t bar = mapa_shared(smem_u32(&full[s]), 0);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (leader) {
+            mbar_arrive_expect_tx(&full[s], 2 * kStageTx);
+            tma_load_2d_pair(&tmA, bar, sa, ks * 64, m0);
+            tma_load_2d_pair(&tmB0, bar, sb, ks * 64, o0);
+          } else {
+            mbar_arrive_cluster(bar);
+            tma_load_2d_pair(&tmA, bar, sa, ks * 64, m0);
+            tma_load_2d_pair(&tmB1, bar, sb, ks * 64, o0 + S::kNH);
+            if (kLoRA) tma_load_2d_pair(&tmP, bar, sb + (S::kNH - kPairRank) * 128, ks * 64, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer (leader CTA, one lane)
+    if (leader && lane == 0) {
+      uint32_t it = 0, lt = 0;
+      bool lora_pending = false;
+      uint32_t pend_buf = 0, pend_parity = 0;
+      auto issue_lora = [&]() {
+        tc_fence_after_sync();
+        const uint64_t adesc = umma_smem_desc(smem_u32(smem + S::kOffTs), 128, 256, kLayoutNone);
+        const uint64_t bdesc = umma_smem_desc(smem_u32(smem + S::kOffQ), 128, 256, kLayoutNone);
+        umma_ss_pair(tmem_base + pend_buf * 256, adesc, bdesc, kIdescLora, 1);
+        umma_commit_pair(&tmem_full2[pend_buf]);
+        lora_pending = false;
+      };
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+        const uint32_t buf = lt & 1;
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          if (kLoRA && lora_pending && mbar_test_wait(ts_full, pend_parity)) issue_lora();
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = umma_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
+            const uint64_t bdesc = umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
+            umma_ss_pair(d_tmem, adesc, bdesc, kIdescMain, (ks | k) != 0);
+          }
+          umma_commit_pair(&empty[s]);
+        }
+        if (kLoRA && lora_pending) {             // the previous tile's update must precede this tile's hand-over
+          mbar_wait(ts_full, pend_parity);
+          issue_lora();
+        }
+        umma_commit_pair(&tmem_full[buf]);
+        if (kLoRA) {
+          lora_pending = true;
+          pend_buf = buf;
+          pend_parity = lt & 1;
+        }
+      }
+      if (kLoRA && lora_pending) {
+        mbar_wait(ts_full, pend_parity);
+        issue_lora();
+      }
+    }
+  } else if (warp >= kPairEpiWarp0) {
+    // ============================================================ epilogue (both CTAs)
+    const int q = warp - kPairEpiWarp0;          // TMEM lane quarter == warp % 4
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - kPairEpiWarp0 * 32;
+    const uint32_t ts_bar = mapa_shared(smem_u32(ts_full), 0);
+    uint8_t* slab0 = smem + S::kOffOut + q * 2 * S::kSlabBytes;
+    uint32_t lt = 0, chunk_no = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+      const int m0 = (tile / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int nt = tile % p.num_n_tiles;
+      const int o0 = nt * BN;
+      const uint32_t buf = lt & 1;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+      const int m = m0 + row;
+
+      for (int i = et; i < BN; i += 128)
+        s_bias[i] = (p.bias != nullptr && o0 + i < p.NO) ? __bfloat162float(p.bias[o0 + i]) : 0.f;
+      if (kLoRA) {
+        // this CTA's half of Q: rows o0 + rank*BN/2 + r  -> K-major no-swizzle: (r/8)*256 + c*128 + (r%8)*16
+        const uint32_t q_s = smem_u32(smem + S::kOffQ);
+        const int qrow0 = o0 + static_cast<int>(rank) * (BN / 2);
+        for (int i = et; i < BN; i += 128) {       // BN/2 rows x 2 chunks
+          const int r = i >> 1, c = i & 1;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (qrow0 + r < p.NO) v = *reinterpret_cast<const uint4*>(p.q_rows + static_cast<size_t>(qrow0 + r) * kPairRank + c * 8);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q_s + (r >> 3) * 256 + c * 128 + (r & 7) * 16),
+                       "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                       : "memory");
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      tc_fence_after_sync();
+      if (kLoRA) {
+        uint32_t t[16];
+        tmem_ld16(t_lane + BN, t);
+        tmem_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pk[i] = pack_bf16x2(__uint_as_float(t[2 * i]) * p.scale, __uint_as_float(t[2 * i + 1]) * p.scale);
+        const uint32_t ts_s = smem_u32(smem + S::kOffTs) + (row >> 3) * 256 + (row & 7) * 16;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ts_s), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ts_s + 128), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        if (nt == 0 && m < p.M && p.side != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(p.side + static_cast<size_t>(m) * kPairRank);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ts_bar);
+        mbar_wait(&tmem_full2[buf], (lt >> 1) & 1);
+        tc_fence_after_sync();
+      }
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g, ++chunk_no) {
+        uint8_t* slab = slab0 + (chunk_no & 1) * S::kSlabBytes;
+        if (lane == 0) tma_store_wait_read<1>();   // the store that last read this slab has finished reading
+        __syncwarp();
+        const uint32_t srow = smem_u32(slab) + lane * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = g * 2 + h;
+          uint32_t v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          tmem_wait_ld();
+          const __nv_bfloat16* rrow =
+              (p.residual != nullptr && m < p.M) ? p.residual + static_cast<size_t>(m) * p.ldr + o0 + c * 32 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = o0 + c * 32 + j * 8;
+            uint32_t rr[4] = {0, 0, 0, 0};
+            if (rrow != nullptr) {
+              if (col + 8 <= p.NO) {
+                const uint4 t4 = *reinterpret_cast<const uint4*>(rrow + j * 8);
+                rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
+              } else {
+                for (int e = 0; e < 8 && col + e < p.NO; ++e)
+                  rr[e >> 1] |= static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(rrow)[j * 8 + e]) << (16 * (e & 1));
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = __uint_as_float(v[j * 8 + 2 * e]) + s_bias[c * 32 + j * 8 + 2 * e] + bf16lo(rr[e]);
+              const float b = __uint_as_float(v[j * 8 + 2 * e + 1]) + s_bias[c * 32 + j * 8 + 2 * e + 1] + bf16hi(rr[e]);
+              o[e] = pack_bf16x2(a, b);
+            }
+            const uint32_t chunk = static_cast<uint32_t>((h * 4 + j) ^ (lane & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          }
+        }
+        if (g == BN / 64 - 1) {
+          // every TMEM read of this tile has retired: hand the accumulator buffer back before the last store goes out
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[buf]), 0));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmD, slab, o0 + g * 64, m0 + q * 32);
+          tma_store_commit();
+        }
+      }
+      // s_bias / Q / Ts are rewritten for the next tile only after every epilogue thread is done with this one
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+}  // namespace vpt

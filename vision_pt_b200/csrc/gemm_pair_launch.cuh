@@ -1,0 +1,93 @@
+// Host launcher of gemm_pair_kernel: tensor maps, tile width, one CTA pair per TPC.
+#pragma once
+#include "gemm_pair.cuh"
+#include <stdlib.h>
+
+#include "host.cuh"
+
+namespace vpt {
+
+struct PairLaunch {
+  const void* act;        // A [M, R] bf16, pitch lda
+  int lda;
+  const void* w;          // Bw [NO, R] bf16, pitch ldw
+  long ldw;
+  const void* p_rows;     // P [16, R] bf16, pitch ldp (nullptr = no LoRA)
+  long ldp;
+  void* out;              // D [M, NO], pitch ldd
+  int ldd;
+  int bn;                 // 0 = choose
+  PairParams p;           // M, NO, R, bias, residual, ldr, q_rows, scale, side
+};
+
+template <int BN, bool kLoRA>
+int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
+  using S = PairSmem<BN, kLoRA>;
+  PairParams p = g.p;
+  p.num_m_pairs = (p.M + 255) / 256;
+  p.num_n_tiles = (p.NO + BN - 1) / BN;
+  CUtensorMap tmA, tmB0, tmB1, tmP, tmD;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (make_tmap_bf16_2d(&tmA, g.act, p.R, p.M, static_cast<uint64_t>(g.lda) * 2, 64, 128, sw)) return 1;
+  if (make_tmap_bf16_2d(&tmB0, g.w, p.R, p.NO, static_cast<uint64_t>(g.ldw) * 2, 64, S::kNH, sw)) return 1;
+  if (make_tmap_bf16_2d(&tmB1, g.w, p.R, p.NO, static_cast<uint64_t>(g.ldw) * 2, 64, kLoRA ? S::kNH - kPairRank : S::kNH, sw)) return 1;
+  tmP = tmA;
+  if (kLoRA && make_tmap_bf16_2d(&tmP, g.p_rows, p.R, kPairRank, static_cast<uint64_t>(g.ldp) * 2, 64, kPairRank, sw)) return 1;
+  if (make_tmap_bf16_2d(&tmD, g.out, p.NO, p.M, static_cast<uint64_t>(g.ldd) * 2, 64, 32, sw)) return 1;
+  auto kern = gemm_pair_kernel<BN, kLoRA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+    if (getenv("VPT_DEBUG") != nullptr) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (sm_count() / 2));
+      cfg.blockDim = dim3(kPairThreads);
+      cfg.dynamicSmemBytes = S::kTotal;
+      int nclusters = -1;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+      fprintf(stderr, "[vpt] gemm_pair<%d,%d>: smem %d B, %d stages, max active clusters %d (%s)\n", BN, int(kLoRA), S::kTotal,
+              S::kStages, nclusters, cudaGetErrorString(e));
+    }
+  }
+  int pairs = p.num_m_pairs * p.num_n_tiles;
+  const int cap = sm_count() / 2;
+  if (pairs > cap) pairs = cap;
+  kern<<<2 * pairs, kPairThreads, S::kTotal, stream>>>(tmA, tmB0, tmB1, tmP, tmD, p);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Tile width: whole waves of the 74 pairs x UMMA N, with the narrower tile charged for its extra L2 traffic.
+inline int choose_pair_bn(int M, int NO, bool lora) {
+  const int pairs = (sm_count() > 0 ? sm_count() : 148) / 2;
+  const int cands[2] = {192, 128};
+  int best = 192;
+  double best_cost = 1e30;
+  for (int c = 0; c < 2; ++c) {
+    const int bn = cands[c];
+    const long tiles = static_cast<long>((M + 255) / 256) * ((NO + bn - 1) / bn);
+    const long rounds = (tiles + pairs - 1) / pairs;
+    const double cost = static_cast<double>(rounds) * (bn + (lora ? kPairRank : 0)) * (bn == 128 ? 1.12 : 1.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+inline int launch_pair(const PairLaunch& g, cudaStream_t stream) {
+  const bool lora = g.p_rows != nullptr;
+  const int bn = g.bn > 0 ? g.bn : choose_pair_bn(g.p.M, g.p.NO, lora);
+  if (lora) {
+    if (bn == 192) return launch_pair_t<192, true>(g, stream);
+    if (bn == 128) return launch_pair_t<128, true>(g, stream);
+  } else {
+    if (bn == 192) return launch_pair_t<192, false>(g, stream);
+    if (bn == 128) return launch_pair_t<128, false>(g, stream);
+  }
+  return fail("unsupported tile width");
+}
+
+}  // namespace vpt

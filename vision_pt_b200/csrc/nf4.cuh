@@ -127,6 +127,85 @@ nf4_dequant_pitched_kernel(const uint8_t* __restrict__ packed, const uint8_t* __
   }
 }
 
+// Dequantise into the TRANSPOSED bf16 matrix out[k * ld + n] (ld >= N rounded up to 8): the operand of the backward
+// GEMM dX = dY * W, which then reads the weight K-major exactly like the forward.  Same bits as nf4_dequant_kernel<bf16>.
+// One CTA = one 64 (n) x 64 (k) tile, transposed through shared memory.  The block after the last tile transposes the two
+// LoRA matrices the backward kernel wants row-major in the other direction:
+//   upT[r * ldu + n] = up[n * 16 + r]       downT[k * 16 + r] = down[r * ldd + k]
+__global__ void __launch_bounds__(256)
+nf4_dequant_transposed_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ qabsmax,
+                              const float* __restrict__ nested_absmax, const float* __restrict__ nested_code,
+                              const float* __restrict__ code, float offset, __nv_bfloat16* __restrict__ out, int N, int K,
+                              long ld, int tiles_k, int num_tiles, const __nv_bfloat16* __restrict__ up,
+                              __nv_bfloat16* __restrict__ upT, long ldu, const __nv_bfloat16* __restrict__ down, long ldd,
+                              __nv_bfloat16* __restrict__ downT) {
+  if (static_cast<int>(blockIdx.x) >= num_tiles) {
+    if (up == nullptr) return;
+    const int t0 = (blockIdx.x - num_tiles) * blockDim.x + threadIdx.x;
+    const int stride = (gridDim.x - num_tiles) * blockDim.x;
+    for (int i = t0; i < 16 * static_cast<int>(ldu); i += stride) {
+      const int r = i / static_cast<int>(ldu), n = i % static_cast<int>(ldu);
+      upT[i] = n < N ? up[static_cast<long>(n) * 16 + r] : __float2bfloat16_rn(0.f);
+    }
+    for (int i = t0; i < K * 16; i += stride) {
+      const int k = i >> 4, r = i & 15;
+      downT[i] = down[static_cast<long>(r) * ldd + k];
+    }
+    return;
+  }
+  __shared__ float s_code[16];
+  __shared__ float s_ncode[256];
+  __shared__ unsigned short tile[64][66];
+  if (threadIdx.x < 16) s_code[threadIdx.x] = code[threadIdx.x];
+  s_ncode[threadIdx.x] = nested_code[threadIdx.x];
+  __syncthreads();
+  const int n0 = (blockIdx.x / tiles_k) * 64, k0 = (blockIdx.x % tiles_k) * 64;
+  const bool aligned = (K & 7) == 0;
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int r = i >> 3, g = i & 7;
+    const int n = n0 + r, k = k0 + g * 8;
+    unsigned short v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0;
+    if (n < N && k < K) {
+      const long flat = static_cast<long>(n) * K + k;
+      if (aligned) {                               // 8 codes = one 32-bit word inside one 64-block
+        const long blk = flat >> 6;
+        const float am = __fadd_rn(__fmul_rn(s_ncode[qabsmax[blk]], nested_absmax[blk >> 8]), offset);
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(packed + (flat >> 1));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t byte = (w >> (8 * b)) & 0xffu;
+          v[2 * b] = __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s_code[byte >> 4], am)));
+          v[2 * b + 1] = __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s_code[byte & 15u], am)));
+        }
+      } else {
+        for (int e = 0; e < 8 && k + e < K; ++e) {
+          const long f = flat + e;
+          const long blk = f >> 6;
+          const float am = __fadd_rn(__fmul_rn(s_ncode[qabsmax[blk]], nested_absmax[blk >> 8]), offset);
+          const uint32_t byte = packed[f >> 1];
+          const uint32_t nib = (f & 1) ? (byte & 15u) : (byte >> 4);
+          v[e] = __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s_code[nib], am)));
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tile[r][g * 8 + e] = v[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int kk = i >> 3, g = i & 7;
+    const int k = k0 + kk, n = n0 + g * 8;
+    if (k >= K || n >= ld) continue;
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = static_cast<uint32_t>(tile[g * 8 + 2 * e][kk]) | (static_cast<uint32_t>(tile[g * 8 + 2 * e + 1][kk]) << 16);
+    *reinterpret_cast<uint4*>(out + static_cast<long>(k) * ld + n) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Load-time repack for ragged in_features (K % 64 != 0, e.g. the SwiGLU hidden 2730 / 3413 of JiT-L / -H): bitsandbytes
 // packs the FLATTENED [N,K] weight, so rows start at arbitrary nibbles and 64-blocks straddle rows.  The GEMM producers
 // want 16-byte aligned rows: codes are re-packed row by row with pitch K_pad/2 bytes (K_pad = K rounded up to 64, padding

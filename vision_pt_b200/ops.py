@@ -23,13 +23,13 @@ NF4_SCRATCH_MIN_M = 1024
 _SCRATCH: dict[tuple, torch.Tensor] = {}
 
 
-def _weight_scratch(device: torch.device, numel: int) -> torch.Tensor:
-    """Per (device, stream) bf16 workspace for the dequantised weight; kernels on one stream run in order, so one
-    buffer per stream is enough.  Grown geometrically, never freed."""
+def _weight_scratch(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) workspace for the dequantised weight (vpt_linear_scratch_bytes); kernels on one stream run
+    in order, so one buffer per stream is enough.  Grown geometrically, never freed."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _SCRATCH.get(key)
-    if buf is None or buf.numel() < numel:
-        buf = torch.empty(max(numel, 8 << 20), dtype=torch.bfloat16, device=device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return buf
 
@@ -182,10 +182,11 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
         args.w = w.c_struct(for_gemm=not use_scratch)
         args.w_bf16 = None
         if use_scratch:
-            ld_s = (K + 7) // 8 * 8
-            scratch = _weight_scratch(x2.device, N * ld_s)
+            need = int(_lib.load().vpt_linear_scratch_bytes(N, K))
+            scratch = _weight_scratch(x2.device, need)
             args.w_scratch = _p(scratch)
-            args.ld_scratch = ld_s
+            args.ld_scratch = (K + 7) // 8 * 8
+            args.scratch_bytes = scratch.numel()
     else:
         N, K = w.shape
         args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K), None, None, 0)
@@ -214,6 +215,8 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.call("vpt_nf4lora_linear_bwd_dx" if backward else "vpt_nf4lora_linear_fwd", C.byref(args), _stream())
+    if scratch is not None:
+        _lib.add_launches(1)          # the per-call dequantisation kernel in front of the GEMM
     if timer is not None:
         e1.record()
         lora = down is not None
