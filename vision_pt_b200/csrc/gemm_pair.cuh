@@ -44,7 +44,8 @@ struct PairSmem {
   static constexpr int kBBytes = (kNH * 128 + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabBytes = 32 * 128;                 // one warp's [32 rows x 64 cols] bf16 output slab
-  static constexpr int kOutBytes = 4 * 2 * kSlabBytes;
+  static constexpr int kSlabs = 4;                            // per epilogue warp (residual prefetch distance 2)
+  static constexpr int kOutBytes = 4 * kSlabs * kSlabBytes;
   static constexpr int kTsBytes = 128 * 32;
   static constexpr int kQBytes = (BN / 2) * 32;
   static constexpr int kBiasBytes = BN * 4;
@@ -56,7 +57,7 @@ struct PairSmem {
   static constexpr int kOffQ = kOffTs + kTsBytes;
   static constexpr int kOffBias = kOffQ + kQBytes;
   static constexpr int kOffBars = kOffBias + kBiasBytes;
-  static constexpr int kNumBars = 2 * kStages + 7;
+  static constexpr int kNumBars = 2 * kStages + 7 + 4 * kSlabs;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -66,12 +67,14 @@ struct PairSmem {
 // tmB0: Bw [NO, R],         box {64, kNH}            rows o0 .. o0 + kNH            (CTA 0)
 // tmB1: Bw [NO, R],         box {64, kNH - 16 | kNH} rows o0 + kNH .. o0 + BN       (CTA 1)
 // tmP : P [16, R],          box {64, 16}             appended below CTA 1's weight rows
-// tmD : D [M, NO],          box {64, 32}             (store)                         all SWIZZLE_128B
+// tmD : D [M, NO],          box {64, 32}             (store)
+// tmR : residual [M, NO],   box {64, 32}             (prefetched into the output slabs)   all SWIZZLE_128B
 template <int BN, bool kLoRA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmP,
-                 const __grid_constant__ CUtensorMap tmD, const PairParams p) {
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                 const PairParams p) {
   using S = PairSmem<BN, kLoRA>;
   static_assert(BN % 64 == 0 && BN >= 64 && S::kNT <= 256, "unsupported BN");
   constexpr int kStages = S::kStages;
@@ -88,6 +91,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full2 = tmem_full + 2;        // [2] per CTA: rank-16 update finished
   uint64_t* tmem_empty = tmem_full2 + 2;       // [2] leader's: 8 epilogue warps (both CTAs) drained the buffer
   uint64_t* ts_full = tmem_empty + 2;          // [1] leader's: 8 epilogue warps staged Ts / Q
+  uint64_t* res_full = ts_full + 1;            // [4 warps][kSlabs] residual slab landed (per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kOffTmemSlot);
   float* s_bias = reinterpret_cast<float*>(smem + S::kOffBias);
 
@@ -111,6 +115,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_empty[b], 8);
     }
     mbar_init(ts_full, 8);
+    for (int i = 0; i < 4 * S::kSlabs; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -118,6 +123,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(leader ? &tmB0 : &tmB1);
     if (kLoRA && !leader) tma_prefetch_desc(&tmP);
     tma_prefetch_desc(&tmD);
+    if (p.residual != nullptr) tma_prefetch_desc(&tmR);
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before_sync();
@@ -208,8 +214,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     const int et = threadIdx.x - kPairEpiWarp0 * 32;
     const uint32_t ts_bar = mapa_shared(smem_u32(ts_full), 0);
-    uint8_t* slab0 = smem + S::kOffOut + q * 2 * S::kSlabBytes;
+    uint8_t* slab0 = smem + S::kOffOut + q * S::kSlabs * S::kSlabBytes;
+    uint64_t* my_res = res_full + q * S::kSlabs;
+    constexpr int kChunks = BN / 64;             // 64-column output chunks per tile
+    const bool has_res = p.residual != nullptr;
     uint32_t lt = 0, chunk_no = 0;
+    // Residual: chunk c of this warp's chunk sequence is fetched by TMA into slab c % kSlabs two chunks ahead of its use;
+    // the epilogue adds the accumulators in place and stores the slab.  (A per-thread row read of the residual stalled the
+    // epilogue on global-load latency: +55 us on a 768 -> 2048 call, profiles/r1c_pair_v1.txt.)
+    auto prefetch_res = [&](uint32_t c) {
+      const int t = cluster_id + static_cast<int>(c / kChunks) * num_clusters;
+      if (t >= num_tiles) return;
+      const int g = static_cast<int>(c % kChunks);
+      const int rm0 = (t / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128 + q * 32;
+      const int ro0 = (t % p.num_n_tiles) * BN + g * 64;
+      const uint32_t sl = c % S::kSlabs;
+      mbar_arrive_expect_tx(&my_res[sl], S::kSlabBytes);
+      tma_load_2d(&tmR, &my_res[sl], slab0 + sl * S::kSlabBytes, ro0, rm0);
+    };
+    if (has_res && lane == 0) {
+      prefetch_res(0);
+      prefetch_res(1);
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
       const int m0 = (tile / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128;
       const int nt = tile % p.num_n_tiles;
@@ -261,10 +287,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after_sync();
       }
 #pragma unroll 1
-      for (int g = 0; g < BN / 64; ++g, ++chunk_no) {
-        uint8_t* slab = slab0 + (chunk_no & 1) * S::kSlabBytes;
-        if (lane == 0) tma_store_wait_read<1>();   // the store that last read this slab has finished reading
+      for (int g = 0; g < kChunks; ++g, ++chunk_no) {
+        const uint32_t sl = chunk_no % S::kSlabs;
+        uint8_t* slab = slab0 + sl * S::kSlabBytes;
+        if (lane == 0) {
+          tma_store_wait_read<1>();                // the slab of chunk_no - 2 (= chunk_no + 2 mod 4) is free again
+          if (has_res) prefetch_res(chunk_no + 2);
+        }
         __syncwarp();
+        if (has_res) mbar_wait(&my_res[sl], (chunk_no / S::kSlabs) & 1);
         const uint32_t srow = smem_u32(slab) + lane * 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -272,21 +303,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(t_lane + c * 32, v);
           tmem_wait_ld();
-          const __nv_bfloat16* rrow =
-              (p.residual != nullptr && m < p.M) ? p.residual + static_cast<size_t>(m) * p.ldr + o0 + c * 32 : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int col = o0 + c * 32 + j * 8;
+            const uint32_t chunk = static_cast<uint32_t>((h * 4 + j) ^ (lane & 7));
             uint32_t rr[4] = {0, 0, 0, 0};
-            if (rrow != nullptr) {
-              if (col + 8 <= p.NO) {
-                const uint4 t4 = *reinterpret_cast<const uint4*>(rrow + j * 8);
-                rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
-              } else {
-                for (int e = 0; e < 8 && col + e < p.NO; ++e)
-                  rr[e >> 1] |= static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(rrow)[j * 8 + e]) << (16 * (e & 1));
-              }
-            }
+            if (has_res)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(srow + chunk * 16));
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -294,11 +316,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float b = __uint_as_float(v[j * 8 + 2 * e + 1]) + s_bias[c * 32 + j * 8 + 2 * e + 1] + bf16hi(rr[e]);
               o[e] = pack_bf16x2(a, b);
             }
-            const uint32_t chunk = static_cast<uint32_t>((h * 4 + j) ^ (lane & 7));
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
         }
-        if (g == BN / 64 - 1) {
+        if (g == kChunks - 1) {
           // every TMEM read of this tile has retired: hand the accumulator buffer back before the last store goes out
           tc_fence_before_sync();
           __syncwarp();

@@ -26,7 +26,7 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
   PairParams p = g.p;
   p.num_m_pairs = (p.M + 255) / 256;
   p.num_n_tiles = (p.NO + BN - 1) / BN;
-  CUtensorMap tmA, tmB0, tmB1, tmP, tmD;
+  CUtensorMap tmA, tmB0, tmB1, tmP, tmD, tmR;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   if (make_tmap_bf16_2d(&tmA, g.act, p.R, p.M, static_cast<uint64_t>(g.lda) * 2, 64, 128, sw)) return 1;
   if (make_tmap_bf16_2d(&tmB0, g.w, p.R, p.NO, static_cast<uint64_t>(g.ldw) * 2, 64, S::kNH, sw)) return 1;
@@ -34,6 +34,8 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
   tmP = tmA;
   if (kLoRA && make_tmap_bf16_2d(&tmP, g.p_rows, p.R, kPairRank, static_cast<uint64_t>(g.ldp) * 2, 64, kPairRank, sw)) return 1;
   if (make_tmap_bf16_2d(&tmD, g.out, p.NO, p.M, static_cast<uint64_t>(g.ldd) * 2, 64, 32, sw)) return 1;
+  tmR = tmD;
+  if (p.residual != nullptr && make_tmap_bf16_2d(&tmR, p.residual, p.NO, p.M, static_cast<uint64_t>(p.ldr) * 2, 64, 32, sw)) return 1;
   auto kern = gemm_pair_kernel<BN, kLoRA>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -53,7 +55,7 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
   int pairs = p.num_m_pairs * p.num_n_tiles;
   const int cap = sm_count() / 2;
   if (pairs > cap) pairs = cap;
-  kern<<<2 * pairs, kPairThreads, S::kTotal, stream>>>(tmA, tmB0, tmB1, tmP, tmD, p);
+  kern<<<2 * pairs, kPairThreads, S::kTotal, stream>>>(tmA, tmB0, tmB1, tmP, tmD, tmR, p);
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }
