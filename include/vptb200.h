@@ -63,7 +63,8 @@ int vpt_nf4_quantize(const void* w, int w_dtype, int64_t n, const float* nested_
  * and the activation gradient of the same (MatMul4Bit.backward + autograd of the LoRA branch):
  *   dx = dy W + dTs lora_down (+ residual),         dTs = bf16(scale * dy lora_up)
  * rank is 16 (pad smaller ranks with zero rows/columns).  K % 64 == 0, a repacked weight, or w_scratch given.  x/dy/y/dx are row-major with the given
- * leading dimensions (multiples of 8 elements).  `side` receives Ts / dTs ([M,16] bf16) for the parameter gradients. */
+ * leading dimensions (multiples of 8 elements).  `side` receives Ts^T / dTs^T ([16, ld_side] bf16, ld_side >= M and a
+ * multiple of 8: the layout vpt_lora_grad_batch reads by TMA) for the parameter gradients. */
 typedef struct {
   vpt_nf4_weight w;
   const void* w_bf16;          /* optional: [N,K] bf16 weight used instead of the NF4 tensors (unquantised Linear) */
@@ -78,7 +79,7 @@ typedef struct {
   int64_t ld_out;
   const void* residual;        /* optional, same shape as out */
   int64_t ld_res;
-  void* side;                  /* [M,16] bf16 or NULL */
+  void* side;                  /* [16, ld_side] bf16 or NULL */
   int32_t M;
   int32_t tile_n;              /* 0 = auto (128 or 192) */
   /* Optional caller-owned workspace of vpt_linear_scratch_bytes(N, K) bytes, 16-byte aligned.  When given with an NF4
@@ -89,17 +90,30 @@ typedef struct {
   void* w_scratch;
   int64_t ld_scratch;          /* unused since ABI 2 (kept for layout compatibility) */
   int64_t scratch_bytes;       /* capacity of w_scratch */
+  int64_t ld_side;             /* row pitch of `side` in elements */
 } vpt_linear_args;
 
 int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K);
 int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream);
 int vpt_nf4lora_linear_bwd_dx(const vpt_linear_args* a, vpt_stream_t stream);
 
-/* autograd of lora_down / lora_up (src/modules/peft/lora.py:100-104):  out += src^T small, fp32.
- *   lora_up.weight.grad   [N,16]: src = dy [M,N], small = Ts,  transposed = 0
- *   lora_down.weight.grad [16,K]: src = x  [M,K], small = dTs, transposed = 1 (ld_out = K) */
-int vpt_lora_grad(const void* src, int64_t ld_src, const void* small, float* out, int32_t M, int32_t P,
-                  int32_t transposed, int64_t ld_out, vpt_stream_t stream);
+/* autograd of lora_down / lora_up (src/modules/peft/lora.py:100-104), batched:  out_i += src^T small_i, fp32, i < nsmall.
+ *   lora_up.weight.grad   [N,16]: src = dy [M,N], small = Ts  (side of the forward call),  transposed = 0
+ *   lora_down.weight.grad [16,K]: src = x  [M,K], small = dTs (side of the backward call), transposed = 1 (ld_out = K)
+ * small_t[i] are side tensors in their [16, ld_small] layout.  Linears sharing their input (q/k/v, w_1/w_2) are one item
+ * with nsmall = 3 / 2 so the shared activation is read once.  At most 16 items per call (one transformer block). */
+typedef struct {
+  const void* src;
+  int64_t ld_src;
+  int32_t M, P;
+  int32_t nsmall;              /* 1..3 */
+  const void* small_t[3];
+  int64_t ld_small;
+  float* out[3];
+  int32_t transposed;
+  int64_t ld_out;
+} vpt_lora_grad_item;
+int vpt_lora_grad_batch(const vpt_lora_grad_item* items, int32_t n_items, vpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ attention
  * scaled_dot_product_attention(q, k, v, mask=key padding) (src/modules/attention.py:98-129) as used by

@@ -65,7 +65,7 @@ for si, (K, N) in enumerate(shapes):
                 t = (xs @ up.float()).to(torch.bfloat16).float()
                 ref = xs @ wd.float() + t @ down.float() + res[:4096].float()
             err = float((y[:4096].float() - ref).abs().max() / ref.abs().max())
-            serr = float((side[:4096].float() - t).abs().max() / t.abs().max().clamp_min(1e-9))
+            serr = float((side[:, :4096].t().float() - t).abs().max() / t.abs().max().clamp_min(1e-9))
             tail = float((y[-1].float() - (
                 (x[-1:].float() @ (wd.float().t() if not bwd else wd.float())) + (0 if bwd else bias.float())
                 + ((x[-1:].float() @ (down.float().t() if not bwd else up.float())).to(torch.bfloat16).float()

@@ -23,8 +23,14 @@ class LinearArgsC(C.Structure):
         ("w", Nf4WeightC), ("w_bf16", C.c_void_p), ("bias", C.c_void_p), ("lora_down", C.c_void_p),
         ("ld_lora_down", C.c_int64), ("lora_up", C.c_void_p), ("scale", C.c_float), ("inp", C.c_void_p), ("ld_in", C.c_int64), ("out", C.c_void_p),
         ("ld_out", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64), ("side", C.c_void_p), ("M", C.c_int32),
-        ("tile_n", C.c_int32), ("w_scratch", C.c_void_p), ("ld_scratch", C.c_int64), ("scratch_bytes", C.c_int64),
+        ("tile_n", C.c_int32), ("w_scratch", C.c_void_p), ("ld_scratch", C.c_int64), ("scratch_bytes", C.c_int64), ("ld_side", C.c_int64),
     ]
+
+
+class LoraGradItemC(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("ld_src", C.c_int64), ("M", C.c_int32), ("P", C.c_int32), ("nsmall", C.c_int32),
+                ("small_t", C.c_void_p * 3), ("ld_small", C.c_int64), ("out", C.c_void_p * 3), ("transposed", C.c_int32),
+                ("ld_out", C.c_int64)]
 
 
 class AttnTensorC(C.Structure):
@@ -41,7 +47,7 @@ SIGNATURES: dict[str, list] = {
     "vpt_nf4_quantize": [_P, C.c_int, _I64, _P, _P, _P, _P, _P, _P, _P],
     "vpt_nf4lora_linear_fwd": [C.POINTER(LinearArgsC), _P],
     "vpt_nf4lora_linear_bwd_dx": [C.POINTER(LinearArgsC), _P],
-    "vpt_lora_grad": [_P, _I64, _P, _P, _I32, _I32, _I32, _I64, _P],
+    "vpt_lora_grad_batch": [C.POINTER(LoraGradItemC), _I32, _P],
     "vpt_attn_fwd": [_AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P],
     "vpt_attn_bwd": [_AT, _AT, _AT, _AT, _AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P],
     "vpt_rmsnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _F, _P],

@@ -89,6 +89,7 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
   const int N = a->w.N, K = a->w.K;
   VPT_REQUIRE(N > 0 && K > 0 && a->M > 0, "vpt_nf4lora_linear: bad shape");
   VPT_REQUIRE(a->ld_in % 8 == 0 && a->ld_out % 8 == 0, "vpt_nf4lora_linear: leading dimensions must be multiples of 8");
+  VPT_REQUIRE(a->side == nullptr || (a->ld_side >= a->M && a->ld_side % 8 == 0), "vpt_nf4lora_linear: side needs ld_side >= M, a multiple of 8");
   const bool via_scratch = a->w_bf16 == nullptr && a->w_scratch != nullptr;
   const bool lora = a->lora_down != nullptr;
   if (lora) VPT_REQUIRE(a->lora_up != nullptr && a->ld_lora_down % 8 == 0 && a->ld_lora_down >= K, "vpt_nf4lora_linear: bad LoRA arguments");
@@ -106,6 +107,7 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     g.p.residual = static_cast<const __nv_bfloat16*>(a->residual); g.p.ldr = static_cast<int>(a->ld_res);
     g.p.scale = a->scale;
     g.p.side = static_cast<__nv_bfloat16*>(a->side);
+    g.p.ld_side = static_cast<long>(a->ld_side);
     if (via_scratch) {
       VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
       VPT_REQUIRE((reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0 && a->scratch_bytes >= vpt_linear_scratch_bytes(N, K),
@@ -178,16 +180,26 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
   g.p.lora_up = static_cast<const __nv_bfloat16*>(a->lora_up);
   g.p.scale = a->scale;
   g.p.side = static_cast<__nv_bfloat16*>(a->side);
+  g.p.ld_side = static_cast<long>(a->ld_side);
   return launch_gemm(g, stream);
 }
 extern "C" int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream) { return linear_common(a, false, S(stream)); }
 extern "C" int vpt_nf4lora_linear_bwd_dx(const vpt_linear_args* a, vpt_stream_t stream) { return linear_common(a, true, S(stream)); }
 
-extern "C" int vpt_lora_grad(const void* src, int64_t ld_src, const void* small, float* out, int32_t M, int32_t P,
-                             int32_t transposed, int64_t ld_out, vpt_stream_t stream) {
-  VPT_REQUIRE(src && small && out && M > 0 && P > 0, "vpt_lora_grad: bad arguments");
-  VPT_REQUIRE(ld_src % 8 == 0, "vpt_lora_grad: leading dimension must be a multiple of 8");
-  return launch_lora_grad(src, static_cast<int>(ld_src), small, out, M, P, transposed, static_cast<int>(ld_out), S(stream));
+extern "C" int vpt_lora_grad_batch(const vpt_lora_grad_item* items, int32_t n_items, vpt_stream_t stream) {
+  VPT_REQUIRE(items != nullptr && n_items > 0 && n_items <= kLgMaxItems, "vpt_lora_grad_batch: 1..16 items");
+  LoraGradDesc d[kLgMaxItems];
+  for (int i = 0; i < n_items; ++i) {
+    const vpt_lora_grad_item& s = items[i];
+    VPT_REQUIRE(s.src && s.M > 0 && s.P > 0 && s.nsmall >= 1 && s.nsmall <= 3, "vpt_lora_grad_batch: bad item");
+    d[i].src = s.src; d[i].ld_src = s.ld_src; d[i].M = s.M; d[i].P = s.P; d[i].nsmall = s.nsmall;
+    for (int j = 0; j < 3; ++j) {
+      d[i].small_t[j] = s.small_t[j];
+      d[i].out[j] = s.out[j];
+    }
+    d[i].ld_small = s.ld_small; d[i].transposed = s.transposed; d[i].ld_out = s.ld_out;
+  }
+  return launch_lora_grad_batch(d, n_items, S(stream));
 }
 
 // ---------------------------------------------------------------------------------------------------- attention

@@ -58,7 +58,8 @@ struct GemmParams {
   int ld_down;
   const __nv_bfloat16* lora_up;    // [N, 16]
   float scale;                  // alpha / rank
-  __nv_bfloat16* side;          // [M,16]: fwd Ts = bf16(scale * X A_down^T); bwd dTs = bf16(scale * dY B_up)
+  __nv_bfloat16* side;          // [16, ld_side] (transposed): fwd Ts = bf16(scale * X A_down^T); bwd dTs = bf16(scale * dY B_up)
+  long ld_side;
   int num_m_tiles, num_n_tiles;
   // descriptor stride overrides (bytes, 0 = default); only the bring-up probe sets them
   uint32_t dbg_b_lbo, dbg_b_sbo, dbg_q_lbo, dbg_q_sbo, dbg_ts_lbo, dbg_ts_sbo;
@@ -333,9 +334,12 @@ gemm_nf4lora_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         st_shared_v4(ts_s, make_uint4(pk[0], pk[1], pk[2], pk[3]));
         st_shared_v4(ts_s + 128, make_uint4(pk[4], pk[5], pk[6], pk[7]));
         if (nt == 0 && m < p.M && p.side != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(p.side + static_cast<size_t>(m) * kRank);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          unsigned short* dst = reinterpret_cast<unsigned short*>(p.side) + m;     // lanes = consecutive m: coalesced
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            dst[static_cast<size_t>(2 * i) * p.ld_side] = static_cast<unsigned short>(pk[i] & 0xffffu);
+            dst[static_cast<size_t>(2 * i + 1) * p.ld_side] = static_cast<unsigned short>(pk[i] >> 16);
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();

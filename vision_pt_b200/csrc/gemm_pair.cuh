@@ -32,7 +32,8 @@ struct PairParams {
   int ldr;
   const __nv_bfloat16* q_rows;     // [NO, 16] second-phase LoRA operand
   float scale;
-  __nv_bfloat16* side;             // [M, 16] or nullptr
+  __nv_bfloat16* side;             // Ts^T [16, ld_side] or nullptr (the layout lora_grad reads by TMA)
+  long ld_side;
   int num_m_pairs, num_n_tiles;
 };
 
@@ -275,9 +276,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ts_s), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ts_s + 128), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
         if (nt == 0 && m < p.M && p.side != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(p.side + static_cast<size_t>(m) * kPairRank);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          unsigned short* dst = reinterpret_cast<unsigned short*>(p.side) + m;     // lanes = consecutive m: coalesced
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            dst[static_cast<size_t>(2 * i) * p.ld_side] = static_cast<unsigned short>(pk[i] & 0xffffu);
+            dst[static_cast<size_t>(2 * i + 1) * p.ld_side] = static_cast<unsigned short>(pk[i] >> 16);
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();

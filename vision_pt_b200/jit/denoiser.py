@@ -264,11 +264,30 @@ class JiTBlockFn(torch.autograd.Function):
             l = lins[i]
             return ops.linear_raw(dout, l.w, None, pads[i][0], pads[i][1], l.scale, residual, want_side=True, backward=True)
 
+        # LoRA parameter gradients: collected over the block and reduced by ONE batched launch at the end; linears that
+        # share their input (q/k/v <- h1, w_1/w_2 <- h2) form one item so the activation is read once
+        want = [lins[i].down is not None and (ctx.needs_input_grad[4 + 2 * i] or ctx.needs_input_grad[5 + 2 * i])
+                for i in range(7)]
+        direct = all((not want[i]) or (ops.grad_sink(lins[i].down) is not None and ops.grad_sink(lins[i].up) is not None
+                                       and lins[i].rank == ops.RANK) for i in range(7))
+        items: list = []
+        shared: dict = {}
+
         def lora_grads(i, dout, t_side, inp, dt_side):
             l = lins[i]
-            if l.down is None or not (ctx.needs_input_grad[4 + 2 * i] or ctx.needs_input_grad[5 + 2 * i]):
+            if not want[i]:
                 return
-            grads[2 * i], grads[2 * i + 1] = ops.lora_param_grads(dout, t_side, inp, dt_side, l.down, l.up, l.rank)
+            if not direct:
+                grads[2 * i], grads[2 * i + 1] = ops.lora_param_grads(dout, t_side, inp, dt_side, l.down, l.up, l.rank)
+                return
+            items.append((dout, [t_side], [ops.grad_sink(l.up)], False))
+            grp = shared.get(inp.data_ptr())
+            if grp is None or len(grp[1]) == 3:
+                grp = (inp, [], [], True)
+                shared[inp.data_ptr()] = grp
+                items.append(grp)
+            grp[1].append(dt_side)
+            grp[2].append(ops.grad_sink(l.down))
 
         # MLP branch
         da, dt_3 = back(6, dy2)
@@ -295,6 +314,8 @@ class JiTBlockFn(torch.autograd.Function):
         lora_grads(0, dq_pre, t_q, h1, dt_q)
         lora_grads(1, dk_pre, t_k, h1, dt_k)
         lora_grads(2, dv2, t_v, h1, dt_v)
+        if items:
+            ops.lora_grad_batch(items)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.rmsnorm_bwd_raw(dh1, x2, n1w, rstd1, dx1, eps).view(B, L, D)

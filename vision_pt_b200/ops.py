@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import AttnTensorC, LinearArgsC, Nf4WeightC
+from ._lib import AttnTensorC, LinearArgsC, LoraGradItemC, Nf4WeightC
 
 RANK = 16  # LoRA rank of the fused kernels; smaller ranks are zero-padded
 
@@ -195,7 +195,9 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     ld_out = (n_out + 7) // 8 * 8
     out_full = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x2.device)
     out = out_full[:, :n_out] if ld_out != n_out else out_full
-    side = torch.empty((M, RANK), dtype=torch.bfloat16, device=x2.device) if (want_side and down is not None) else None
+    # the rank-16 projection, kept for the parameter gradients in the [16, M] layout vpt_lora_grad_batch reads by TMA
+    ld_side = (M + 7) // 8 * 8
+    side = torch.empty((RANK, ld_side), dtype=torch.bfloat16, device=x2.device) if (want_side and down is not None) else None
     args.bias = _p(bias)
     args.lora_down = _p(down)
     args.ld_lora_down = down.stride(0) if down is not None else 0
@@ -208,6 +210,7 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     args.residual = _p(residual)
     args.ld_res = residual.stride(0) if residual is not None and M > 1 else n_out
     args.side = _p(side)
+    args.ld_side = ld_side
     args.M = M
     args.tile_n = tile_n
     timer = GEMM_TIMER
@@ -226,12 +229,26 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     return out, side
 
 
-def lora_grad_raw(src2: torch.Tensor, small: torch.Tensor, out_f32: torch.Tensor, transposed: bool) -> None:
-    """out_f32 += src2^T small   ([P,16], or [16,P] when transposed)."""
-    M, P = src2.shape
-    ld_out = out_f32.shape[1] if transposed else RANK
-    _lib.call("vpt_lora_grad", _p(src2), src2.stride(0) if M > 1 else P, _p(small), _p(out_f32), M, P, int(transposed),
-              ld_out, _stream())
+def lora_grad_batch(items: list[tuple]) -> None:
+    """One launch of vpt_lora_grad_batch.  items: (src2 [M,P], [side tensors [16, ld]], [fp32 outputs], transposed);
+    out_i += src2^T side_i^T, written as [P,16] or, when transposed, as [16,P]."""
+    for lo in range(0, len(items), 16):
+        chunk = items[lo:lo + 16]
+        arr = (LoraGradItemC * len(chunk))()
+        for it, (src2, sides, outs, transposed) in zip(arr, chunk):
+            M, P = src2.shape
+            it.src = src2.data_ptr()
+            it.ld_src = src2.stride(0) if M > 1 else (P + 7) // 8 * 8
+            it.M, it.P, it.nsmall = M, P, len(sides)
+            for j, (sd, out) in enumerate(zip(sides, outs)):
+                if sd.shape[0] != RANK or sd.shape[1] < M or out.dtype != torch.float32 or not out.is_contiguous():
+                    raise ValueError("lora_grad_batch: side tensors are [16, >= M] bf16, outputs contiguous fp32")
+                it.small_t[j] = sd.data_ptr()
+                it.out[j] = out.data_ptr()
+            it.ld_small = sides[0].stride(0)
+            it.transposed = int(transposed)
+            it.ld_out = outs[0].shape[1] if transposed else RANK
+        _lib.call("vpt_lora_grad_batch", arr, len(chunk), _stream())
 
 
 def grad_sink(param: torch.Tensor | None) -> torch.Tensor | None:
@@ -245,14 +262,12 @@ def lora_param_grads(dy2, side, x2, dside, down, up, rank: int):
     accumulated into the flat fp32 buffer."""
     sink_d, sink_u = grad_sink(down), grad_sink(up)
     if sink_d is not None and sink_u is not None and rank == RANK:
-        lora_grad_raw(dy2, side, sink_u, transposed=False)
-        lora_grad_raw(x2, dside, sink_d, transposed=True)
+        lora_grad_batch([(dy2, [side], [sink_u], False), (x2, [dside], [sink_d], True)])
         return None, None
     N, K = dy2.shape[1], x2.shape[1]
     gup = torch.zeros((N, RANK), dtype=torch.float32, device=dy2.device)
     gdown = torch.zeros((RANK, K), dtype=torch.float32, device=dy2.device)
-    lora_grad_raw(dy2, side, gup, transposed=False)
-    lora_grad_raw(x2, dside, gdown, transposed=True)
+    lora_grad_batch([(dy2, [side], [gup], False), (x2, [dside], [gdown], True)])
     return gdown[:rank].to(down.dtype), gup[:, :rank].to(up.dtype)
 
 
