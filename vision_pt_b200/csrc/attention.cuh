@@ -94,30 +94,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t kIdS = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T   (both K-major)
-      constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O += P V    (V is MN-major)
-      const uint32_t sQ = smem_u32(smem + S::kQ), sP = smem_u32(smem + S::kP);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        const uint32_t sK = smem_u32(smem + S::kK + s * 16384), sV = smem_u32(smem + S::kV + s * 16384);
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
-        tc_fence_after_sync();
+    // converged warp, one elected lane issues (operands stay in uniform registers)
+    constexpr uint32_t kIdS = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T   (both K-major)
+    constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O += P V    (V is MN-major)
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
+    const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);
+    const uint64_t qd = dK_ + ((smem_base + S::kQ) >> 4), pd = dK_ + ((smem_base + S::kP) >> 4);
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      const uint64_t kd = dK_ + ((smem_base + S::kK + s * 16384) >> 4), vd = dMN + ((smem_base + S::kV + s * 16384) >> 4);
+      mbar_wait(&kv_full[s], (j >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, umma_smem_desc(sQ + k * 32, 16, 1024, kLayoutSW128),
-                  umma_smem_desc(sK + k * 32, 16, 1024, kLayoutSW128), kIdS, k != 0);
+        for (int k = 0; k < 4; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, kIdS, k != 0);
         umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after_sync();
+      }
+      __syncwarp();
+      mbar_wait(p_full, j & 1);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tO, umma_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kLayoutSW128),
-                  umma_smem_desc(sV + k * 2048, 8192, 1024, kLayoutSW128), kIdO, (j | k) != 0);
+        for (int k = 0; k < 8; ++k) umma_ss(tO, pd + (k >> 2) * 1024 + (k & 3) * 2, vd + k * 128, kIdO, (j | k) != 0);
         umma_commit(&kv_empty[s]);
         umma_commit(o_full);
       }
+      __syncwarp();
     }
   } else {
     // softmax warps 2..5: TMEM lane quarter = warp % 4

@@ -1,6 +1,7 @@
 // Host launchers for the attention kernels.
 #pragma once
 #include "attention.cuh"
+#include "attention_bwd.cuh"
 #include "host.cuh"
 
 namespace vpt {
@@ -64,7 +65,14 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   attn_bwd_delta_kernel<<<static_cast<unsigned>((groups * 8 + 255) / 256), 256, 0, stream>>>(dp);
   VPT_CUDA_OK(cudaGetLastError());
 
-  AttnBwdParams p{};
+  CUtensorMap tdq;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(kAttnHD), static_cast<uint64_t>(Lq), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(dq_f32.sl) * 4, static_cast<uint64_t>(dq_f32.sh) * 4, static_cast<uint64_t>(dq_f32.sb) * 4};
+    const uint32_t box[4] = {32, 32, 1, 1};
+    if (make_tmap_f32_4d(&tdq, dq_f32.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  AttnBwd2Params p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.seqlens_k = seqlens_k;
   p.scale = scale;
@@ -77,13 +85,16 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   p.dv = static_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr));
   p.dk_sb = dk.sb; p.dk_sl = dk.sl; p.dk_sh = dk.sh;
   p.dv_sb = dv.sb; p.dv_sl = dv.sl; p.dv_sh = dv.sh;
+  p.nk = (Lk + kAttnTile - 1) / kAttnTile;
+  p.nq = (Lq + kAttnTile - 1) / kAttnTile;
+  p.num_items = B * H * p.nk;
   static bool attr = false;
   if (!attr) {
-    VPT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdSmem::kTotal));
+    VPT_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwd2Smem::kTotal));
     attr = true;
   }
-  dim3 grid((Lk + kAttnTile - 1) / kAttnTile, H, B);
-  attn_bwd_kernel<<<grid, 192, AttnBwdSmem::kTotal, stream>>>(tq, tk, tv, tdo, p);
+  const int ctas = p.num_items < sm_count() ? p.num_items : sm_count();
+  attn_bwd2_kernel<<<ctas, 512, AttnBwd2Smem::kTotal, stream>>>(tq, tk, tv, tdo, tdq, p);
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -160,17 +160,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (leader CTA, one lane)
-    if (leader && lane == 0) {
+    // ============================================================ MMA issuer (leader CTA; converged warp, one elected lane)
+    if (leader) {
       uint32_t it = 0, lt = 0;
       bool lora_pending = false;
       uint32_t pend_buf = 0, pend_parity = 0;
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t ts_desc = umma_smem_desc(smem_base + S::kOffTs, 128, 256, kLayoutNone);
+      const uint64_t q_desc = umma_smem_desc(smem_base + S::kOffQ, 128, 256, kLayoutNone);
+      const uint64_t sw_desc = umma_smem_desc(0, 16, 1024, kLayoutSW128);   // + (address >> 4) per operand
       auto issue_lora = [&]() {
         tc_fence_after_sync();
-        const uint64_t adesc = umma_smem_desc(smem_u32(smem + S::kOffTs), 128, 256, kLayoutNone);
-        const uint64_t bdesc = umma_smem_desc(smem_u32(smem + S::kOffQ), 128, 256, kLayoutNone);
-        umma_ss_pair(tmem_base + pend_buf * 256, adesc, bdesc, kIdescLora, 1);
-        umma_commit_pair(&tmem_full2[pend_buf]);
+        if (elect_one_sync()) {
+          umma_ss_pair(tmem_base + pend_buf * 256, ts_desc, q_desc, kIdescLora, 1);
+          umma_commit_pair(&tmem_full2[pend_buf]);
+        }
+        __syncwarp();
         lora_pending = false;
       };
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
@@ -179,25 +184,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          if (kLoRA && lora_pending && mbar_test_wait(ts_full, pend_parity)) issue_lora();
+          if (kLoRA && lora_pending && __all_sync(0xffffffffu, mbar_test_wait(ts_full, pend_parity))) issue_lora();
           const int s = it % kStages;
           mbar_wait(&full[s], (it / kStages) & 1);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
-          const uint32_t sb = sa + S::kABytes;
+          const uint32_t sa = smem_base + s * S::kStageBytes;
+          const uint64_t adesc = sw_desc + (sa >> 4);
+          const uint64_t bdesc = sw_desc + ((sa + S::kABytes) >> 4);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
-            const uint64_t bdesc = umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
-            umma_ss_pair(d_tmem, adesc, bdesc, kIdescMain, (ks | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdescMain, (ks | k) != 0);
+            umma_commit_pair(&empty[s]);
           }
-          umma_commit_pair(&empty[s]);
+          __syncwarp();
         }
         if (kLoRA && lora_pending) {             // the previous tile's update must precede this tile's hand-over
           mbar_wait(ts_full, pend_parity);
           issue_lora();
         }
-        umma_commit_pair(&tmem_full[buf]);
+        if (elect_one_sync()) umma_commit_pair(&tmem_full[buf]);
+        __syncwarp();
         if (kLoRA) {
           lora_pending = true;
           pend_buf = buf;

@@ -110,6 +110,29 @@ inline int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t 
   return 0;
 }
 
+// 4-D fp32 tensor, d0 innermost (contiguous); byte strides for d1..d3.
+inline int make_tmap_f32_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                            const uint32_t box[4], CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail("cuTensorMapEncodeTiled unavailable");
+  for (int i = 0; i < 3; ++i)
+    if (strides_bytes[i] & 15) return fail("TMA needs 16-byte aligned strides");
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail("TMA needs a 16-byte aligned base");
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstride[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, b, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "CUresult %d", static_cast<int>(r));
+    return fail("cuTensorMapEncodeTiled(4d f32)", buf);
+  }
+  return 0;
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

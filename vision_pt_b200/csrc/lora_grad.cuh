@@ -96,21 +96,24 @@ lora_grad_kernel(const __grid_constant__ LoraGradBatch bp) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 16 * ns, 1, 0);   // A = Src tile viewed MN-major, B = Small^T rows K-major
-      for (int it = 0; it < nsteps; ++it) {
-        const int s = it % S::kStages;
-        mbar_wait(&full[s], (it / S::kStages) & 1);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_u32(smem + s * S::kStage), sb = sa + S::kA;
+    // converged warp, one elected lane issues
+    const uint32_t idesc = umma_idesc_bf16(128, 16 * ns, 1, 0);   // A = Src tile viewed MN-major, B = Small^T rows K-major
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128), dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it % S::kStages;
+      mbar_wait(&full[s], (it / S::kStages) & 1);
+      tc_fence_after_sync();
+      const uint64_t ad = dMN + ((smem_base + s * S::kStage) >> 4), bd = dK_ + ((smem_base + s * S::kStage + S::kA) >> 4);
+      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base, umma_smem_desc(sa + k * 2048, 8192, 1024, kLayoutSW128),
-                  umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128), idesc, (it | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base, ad + k * 128, bd + 2 * k, idesc, (it | k) != 0);
         umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
+      __syncwarp();
     }
+    if (elect_one_sync()) umma_commit(acc_full);
+    __syncwarp();
   } else if (warp >= 4) {
     const int qd = warp & 3;
     const int prow = p0 + qd * 32 + lane;
