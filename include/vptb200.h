@@ -126,8 +126,9 @@ typedef struct {
 } vpt_attn_tensor;
 int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v, const vpt_attn_tensor* o,
                  int32_t B, int32_t H, int32_t Lq, int32_t Lk, const int32_t* seqlens_k, float scale,
-                 float* lse2 /* [B,H,Lq] */, vpt_stream_t stream);
-/* dq is fp32 and must be zero on entry; delta_ws: [B,H,Lq] fp32 workspace. */
+                 float* lse2 /* [B,H,Lq rounded up to 128] */, vpt_stream_t stream);
+/* dq is fp32 and must be zero on entry; lse2 as written by vpt_attn_fwd; delta_ws: [B,H,Lq rounded up to 128] fp32
+ * workspace. */
 int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v, const vpt_attn_tensor* o,
                  const vpt_attn_tensor* d_o, const vpt_attn_tensor* dq_f32, const vpt_attn_tensor* dk,
                  const vpt_attn_tensor* dv, int32_t B, int32_t H, int32_t Lq, int32_t Lk, const int32_t* seqlens_k,

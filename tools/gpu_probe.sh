@@ -1,4 +1,2 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python tools/bench_attn.py 2>&1 | tail -3
-timeout 300 python tools/bench_attn.py --B 16 --H 16 --L 1100 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-300
+timeout 300 python tools/bench_attn.py --iters 2 > gpurun_out/plain3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:attn_bwd2 -s 2 -c 1 -o gpurun_out/r1e_attnbwd python tools/bench_attn.py --iters 2 > gpurun_out/r1e_ncu.log 2>&1

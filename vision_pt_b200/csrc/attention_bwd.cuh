@@ -12,8 +12,8 @@
 //   drain warps    dQ tile -> fp32 shared-memory slabs -> TMA reduce-add (dQ is summed across key tiles in global
 //                  memory; per-thread red.global measured ~10k cycles per tile on the LSU, profiles/r1e_attn_bwd.txt)
 //
-// Warp roles: 0 TMA producer (K/V double buffered across items, Q/dO two stages), 1 MMA issuer, 2 TMEM allocator,
-// 3 row statistics (lse, delta*scale -> shared memory), 4-7 warpgroup A, 8-11 warpgroup B, 12-15 dQ drain.
+// Warp roles: 0 TMA producer (K/V double buffered across items; Q/dO and the tile's lse / delta*scale rows in two
+// stages), 1 MMA issuer, 2 TMEM allocator, 4-7 warpgroup A, 8-11 warpgroup B, 12-15 drain (dQ per tile, dV / dK per item).
 // The last query tile is trimmed to a multiple of 16 queries (UMMA N / K granularity).
 #pragma once
 #include "sm100.cuh"
@@ -24,12 +24,10 @@ struct AttnBwd2Params {
   int B, H, Lq, Lk;
   const int* seqlens_k;
   float scale_log2, scale;
-  const float* lse2;           // [B, H, Lq]
-  const float* delta;          // [B, H, Lq]
+  const float* lse2;           // [B, H, nq * 128]  (+inf in the padding)
+  const float* delta;          // [B, H, nq * 128]  delta * scale (0 in the padding)
   float* dq;                   // fp32, zero-initialised by the caller; element strides below
   long dq_sb, dq_sl, dq_sh;
-  __nv_bfloat16 *dk, *dv;
-  long dk_sb, dk_sl, dk_sh, dv_sb, dv_sl, dv_sh;
   int nk, nq, num_items;       // key tiles, query tiles, B * H * nk
 };
 
@@ -53,10 +51,12 @@ __device__ __forceinline__ int attn_round16(int x) { return (x + 15) & ~15; }
 
 // tmQ / tmDO / tmK / tmV: 4-D bf16 maps (hd, L, H, B), box {64, 128, 1, 1}, SWIZZLE_128B
 // tmDQ: 4-D fp32 map (hd, Lq, H, B) of the dQ accumulator, box {32, 32, 1, 1}, SWIZZLE_128B
+// tmDK / tmDV: 4-D bf16 maps (hd, Lk, H, B) of the outputs, box {64, 32, 1, 1}, SWIZZLE_128B
 __global__ void __launch_bounds__(512, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwd2Params p) {
+                 const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                 const __grid_constant__ CUtensorMap tmDV, const AttnBwd2Params p) {
   using S = AttnBwd2Smem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -81,14 +81,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
-      mbar_init(&qdo_full[s], 2);
+      mbar_init(&qdo_full[s], 1);
       mbar_init(&qdo_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
     }
     mbar_init(mma2_done, 1);
     mbar_init(dq_free, 4);
-    mbar_init(dkv_free, 256);
+    mbar_init(dkv_free, 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -124,36 +124,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 0; i < nq; ++i, ++f) {
           const uint32_t s = f & 1;
           mbar_wait(&qdo_empty[s], ((f >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&qdo_full[s], 32768);
+          mbar_arrive_expect_tx(&qdo_full[s], 32768 + 1024);
           tma_load_4d(&tmQ, &qdo_full[s], smem + S::kQ + s * 16384, 0, i * 128, h, b);
           tma_load_4d(&tmDO, &qdo_full[s], smem + S::kDO + s * 16384, 0, i * 128, h, b);
+          const long srow = (static_cast<long>(b) * p.H + h) * (static_cast<long>(nq) * 128) + i * 128;
+          bulk_load_1d(smem + S::kStats + s * 1024, p.lse2 + srow, 512, &qdo_full[s]);
+          bulk_load_1d(smem + S::kStats + s * 1024 + 512, p.delta + srow, 512, &qdo_full[s]);
         }
-      }
-    }
-  } else if (warp == 3) {
-    // ============================================================ row statistics of each query tile
-    uint32_t f = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
-      const long base = (static_cast<long>(b) * p.H + h) * p.Lq;
-      for (int i = 0; i < nq; ++i, ++f) {
-        const uint32_t s = f & 1;
-        float l4[4], d4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {               // issue the loads before waiting for the slot
-          const int q = i * 128 + u * 32 + lane;
-          l4[u] = q < p.Lq ? __ldg(p.lse2 + base + q) : INFINITY;    // +inf -> p = exp2(-inf) = 0 for padded queries
-          d4[u] = q < p.Lq ? __ldg(p.delta + base + q) * p.scale : 0.f;
-        }
-        mbar_wait(&qdo_empty[s], ((f >> 1) & 1) ^ 1);
-        float* st = s_stats + s * 256;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          st[u * 32 + lane] = l4[u];
-          st[128 + u * 32 + lane] = d4[u];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&qdo_full[s]);
       }
     }
   } else if (warp == 1) {
@@ -255,10 +232,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t pt_row = smem_u32(smem + S::kPT) + X * 16384 + row * 128;
     const uint32_t dst_row = smem_u32(smem + S::kDST) + X * 16384 + row * 128;
     uint32_t f = 0, cx = 0, itn = 0;
+    auto klen_of = [&](int item) {
+      if (p.seqlens_k == nullptr || item >= p.num_items) return p.Lk;
+      const int kl = __ldg(p.seqlens_k + item / (p.nk * p.H));
+      return kl < p.Lk ? kl : p.Lk;
+    };
+    int klen_next = klen_of(blockIdx.x);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++itn) {
       const int kt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
-      int klen = p.seqlens_k ? p.seqlens_k[b] : p.Lk;
-      klen = klen < p.Lk ? klen : p.Lk;
+      const int klen = klen_next;
+      klen_next = klen_of(item + gridDim.x);       // fetched a whole item ahead of its first use
       const int key = kt * 128 + row;
       const bool key_ok = key < klen;
       for (int i = 0; i < nq; ++i, ++f) {
@@ -287,16 +270,22 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_wait_ld();
             uint32_t pk[16], dk[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int c0 = c * 32 + 2 * e;
-              const float2 ls = *reinterpret_cast<const float2*>(st + c0);
-              const float2 dl = *reinterpret_cast<const float2*>(st + 128 + c0);
-              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), p.scale_log2, -ls.x));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), p.scale_log2, -ls.y));
-              const float d0 = p0 * fmaf(__uint_as_float(dv[2 * e]), p.scale, -dl.x);
-              const float d1 = p1 * fmaf(__uint_as_float(dv[2 * e + 1]), p.scale, -dl.y);
-              pk[e] = key_ok ? pack_bf16x2(p0, p1) : 0u;   // padded keys: P = dS = 0 (exactly zero gradient)
-              dk[e] = key_ok ? pack_bf16x2(d0, d1) : 0u;
+            for (int e = 0; e < 8; ++e) {
+              const int c0 = c * 32 + 4 * e;
+              const float4 ls = *reinterpret_cast<const float4*>(st + c0);         // broadcast reads: 4 queries per LDS
+              const float4 dl = *reinterpret_cast<const float4*>(st + 128 + c0);
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[4 * e]), p.scale_log2, -ls.x));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[4 * e + 1]), p.scale_log2, -ls.y));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(sv[4 * e + 2]), p.scale_log2, -ls.z));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(sv[4 * e + 3]), p.scale_log2, -ls.w));
+              const float d0 = p0 * fmaf(__uint_as_float(dv[4 * e]), p.scale, -dl.x);
+              const float d1 = p1 * fmaf(__uint_as_float(dv[4 * e + 1]), p.scale, -dl.y);
+              const float d2 = p2 * fmaf(__uint_as_float(dv[4 * e + 2]), p.scale, -dl.z);
+              const float d3 = p3 * fmaf(__uint_as_float(dv[4 * e + 3]), p.scale, -dl.w);
+              pk[2 * e] = key_ok ? pack_bf16x2(p0, p1) : 0u;   // padded keys: P = dS = 0 (exactly zero gradient)
+              pk[2 * e + 1] = key_ok ? pack_bf16x2(p2, p3) : 0u;
+              dk[2 * e] = key_ok ? pack_bf16x2(d0, d1) : 0u;
+              dk[2 * e + 1] = key_ok ? pack_bf16x2(d2, d3) : 0u;
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -314,33 +303,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before_sync();
         mbar_arrive(&p_full[X]);
       }
-      // item finished: warpgroup A drains dV, warpgroup B drains dK
-      mbar_wait(mma2_done, (f - 1) & 1);
-      tc_fence_after_sync();
-      {
-        __nv_bfloat16* base = X == 0 ? p.dv + b * p.dv_sb + static_cast<long>(key) * p.dv_sl + h * p.dv_sh
-                                     : p.dk + b * p.dk_sb + static_cast<long>(key) * p.dk_sl + h * p.dk_sh;
-        const uint32_t tsrc = X == 0 ? tDV : tDK;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tsrc + lane_off + c * 32, v);
-          tmem_wait_ld();
-          if (key < p.Lk) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o4;
-              o4.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-              o4.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-              o4.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-              o4.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-              *reinterpret_cast<uint4*>(base + c * 32 + g * 8) = o4;
-            }
-          }
-        }
-      }
-      tc_fence_before_sync();
-      mbar_arrive(dkv_free);
     }
   } else if (warp >= 12) {
     // ============================================================ dQ drain
@@ -348,7 +310,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     uint8_t* slabs = smem + S::kDQ + qd * 8192;
     const uint32_t srow = smem_u32(slabs) + lane * 128;
-    if (warp == 12 && lane == 0) tma_prefetch_desc(&tmDQ);
+    if (warp == 12 && lane == 0) {
+      tma_prefetch_desc(&tmDQ);
+      tma_prefetch_desc(&tmDK);
+      tma_prefetch_desc(&tmDV);
+    }
     uint32_t f = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
@@ -379,6 +345,39 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
           tma_store_commit();
         }
+      }
+      // item finished (the wait above covered its last MMAs): dV, dK -> bf16 slabs -> TMA store, so that the softmax
+      // warpgroups go straight on to the next item
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32((t == 0 ? tDV : tDK) + lane_off + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + t * 4096 + (((c * 4 + g) ^ (lane & 7)) * 16)),
+                         "r"(pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]))),
+                         "r"(pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]))),
+                         "r"(pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]))),
+                         "r"(pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])))
+                         : "memory");
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(dkv_free);                       // the accumulators are read: the next item may overwrite them
+        const int kt = item % p.nk;
+        if (kt * 128 + qd * 32 < p.Lk) {             // rows past Lk inside the box are clipped by the TMA unit
+          tma_store_4d(&tmDV, slabs, 0, kt * 128 + qd * 32, h, b);
+          tma_store_4d(&tmDK, slabs + 4096, 0, kt * 128 + qd * 32, h, b);
+        }
+        tma_store_commit();
       }
     }
     if (lane == 0) tma_store_wait_all<0>();

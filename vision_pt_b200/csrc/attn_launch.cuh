@@ -11,12 +11,12 @@ struct AttnTensor {
   long sb, sl, sh;   // element strides of (batch, token, head); head_dim is contiguous
 };
 
-inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int L) {
+inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int L, int box_rows = kAttnTile) {
   const uint64_t dims[4] = {static_cast<uint64_t>(kAttnHD), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
                             static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(t.sl) * 2, static_cast<uint64_t>(t.sh) * 2,
                                static_cast<uint64_t>(t.sb) * 2};
-  const uint32_t box[4] = {kAttnHD, kAttnTile, 1, 1};
+  const uint32_t box[4] = {kAttnHD, static_cast<uint32_t>(box_rows), 1, 1};
   return make_tmap_bf16_4d(m, t.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -61,7 +61,9 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   dp.o_sb = o.sb; dp.o_sl = o.sl; dp.o_sh = o.sh;
   dp.do_sb = d_o.sb; dp.do_sl = d_o.sl; dp.do_sh = d_o.sh;
   dp.delta = delta;
-  const long groups = static_cast<long>(B) * H * Lq;
+  dp.Lq_pad = (Lq + kAttnTile - 1) / kAttnTile * kAttnTile;
+  dp.scale = scale;
+  const long groups = static_cast<long>(B) * H * dp.Lq_pad;
   attn_bwd_delta_kernel<<<static_cast<unsigned>((groups * 8 + 255) / 256), 256, 0, stream>>>(dp);
   VPT_CUDA_OK(cudaGetLastError());
 
@@ -81,10 +83,8 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   p.delta = delta;
   p.dq = static_cast<float*>(const_cast<void*>(dq_f32.ptr));
   p.dq_sb = dq_f32.sb; p.dq_sl = dq_f32.sl; p.dq_sh = dq_f32.sh;
-  p.dk = static_cast<__nv_bfloat16*>(const_cast<void*>(dk.ptr));
-  p.dv = static_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr));
-  p.dk_sb = dk.sb; p.dk_sl = dk.sl; p.dk_sh = dk.sh;
-  p.dv_sb = dv.sb; p.dv_sl = dv.sl; p.dv_sh = dv.sh;
+  CUtensorMap tdk, tdv;
+  if (make_attn_tmap(&tdk, dk, B, H, Lk, 32) || make_attn_tmap(&tdv, dv, B, H, Lk, 32)) return 1;
   p.nk = (Lk + kAttnTile - 1) / kAttnTile;
   p.nq = (Lq + kAttnTile - 1) / kAttnTile;
   p.num_items = B * H * p.nk;
@@ -94,7 +94,7 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
     attr = true;
   }
   const int ctas = p.num_items < sm_count() ? p.num_items : sm_count();
-  attn_bwd2_kernel<<<ctas, 512, AttnBwd2Smem::kTotal, stream>>>(tq, tk, tv, tdo, tdq, p);
+  attn_bwd2_kernel<<<ctas, 512, AttnBwd2Smem::kTotal, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -338,11 +338,11 @@ def _attn_ok(t: torch.Tensor) -> torch.Tensor:
 
 
 def attn_fwd_raw(q, k, v, seqlens_k, scale: float):
-    """q,k,v: [B,H,L,64] views.  Returns (o [B,H,Lq,64] view over token-major memory, lse2 [B,H,Lq])."""
+    """q,k,v: [B,H,L,64] views.  Returns (o [B,H,Lq,64] view over token-major memory, lse2 [B,H,Lq rounded up to 128])."""
     B, H, Lq, _ = q.shape
     Lk = k.shape[2]
     o = torch.empty((B, Lq, H, 64), dtype=torch.bfloat16, device=q.device).permute(0, 2, 1, 3)
-    lse2 = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    lse2 = torch.empty((B, H, (Lq + 127) // 128 * 128), dtype=torch.float32, device=q.device)
     tq, tk, tv, to = _at(q), _at(k), _at(v), _at(o)
     _lib.call("vpt_attn_fwd", C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, _p(seqlens_k),
               float(scale), _p(lse2), _stream())
@@ -357,7 +357,7 @@ def attn_bwd_raw(q, k, v, o, d_o, lse2, seqlens_k, scale: float):
     dq = torch.zeros((B, Lq, H, 64), dtype=torch.float32, device=dev).permute(0, 2, 1, 3)
     dk = torch.empty((B, Lk, H, 64), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
     dv = torch.empty((B, Lk, H, 64), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
-    delta = torch.empty((B, H, Lq), dtype=torch.float32, device=dev)
+    delta = torch.empty((B, H, (Lq + 127) // 128 * 128), dtype=torch.float32, device=dev)
     ts = [_at(t) for t in (q, k, v, o, d_o, dq, dk, dv)]
     _lib.call("vpt_attn_bwd", *[C.byref(t) for t in ts], B, H, Lq, Lk, _p(seqlens_k), float(scale), _p(lse2), _p(delta),
               _stream())
