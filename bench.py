@@ -35,7 +35,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default=None, help="JiT-B/16 | JiT-L/16 | JiT-H/16 (default: B at 1 GPU, L at >1)")
+    ap.add_argument("--model", default="JiT-B/16", help="JiT-B/16 | JiT-L/16 (the headline workload is JiT-B/16 at every N so that N = 1, 2, 4, 8 measure the same per-GPU work)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary JiT-L/16 data-parallel measurement at N > 1")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--rank", type=int, default=16)
@@ -113,6 +114,88 @@ def physical_gpu_index(local: int) -> int:
     return local
 
 
+# ------------------------------------------------------------------------------------------------ roofline
+def gemm_roofline(step, ops, torch):
+    ops.GEMM_TIMER = []
+    was = step.use_graph
+    step.use_graph = False
+    step.run()
+    torch.cuda.synchronize()
+    step.use_graph = was
+    recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+    tape = [r for r in recs if r["nf4"] and r["lora"] and r["scratch"]]
+    if not tape:
+        return None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pool: dict = {}
+
+    def buf(shape, stride, salt):
+        """A few distinct buffers per shape, rotated, so that consecutive calls do not find their input in L2."""
+        key = (tuple(shape), stride)
+        lst = pool.setdefault(key, [])
+        if len(lst) < 3:
+            t = torch.randn((shape[0], stride), device=dev).mul_(0.5).to(torch.bfloat16)[:, :shape[1]]
+            lst.append(t)
+        return lst[salt % len(lst)]
+
+    def replay(reuse: bool):
+        outs = []
+        for i, r in enumerate(tape):
+            shape, stride, w, bias, down, up, scale, has_res, want_side, backward = r["call"]
+            n_out = w.shape[1] if backward else w.shape[0]
+            res = buf((shape[0], n_out), (n_out + 7) // 8 * 8, i + 1) if has_res else None
+            outs.append(ops.linear_raw(buf(shape, stride, i), w, bias, down, up, scale, res, want_side=want_side,
+                                       backward=backward, reuse_scratch=reuse))
+        return outs
+
+    def timed(reuse: bool) -> float:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            replay(reuse)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = replay(reuse)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(3):
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del keep, g
+        return best
+
+    ms_gemm = timed(True)
+    ms_call = timed(False)
+    fl = sum(r["flops"] for r in tape)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained")
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long back-to-back sequence)"
+    if not peak:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_pair_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved = fl / (ms_gemm * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_pair_kernel (NF4 + LoRA linears of the blocks, forward and backward-dX)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "launches": len(tape), "avg_launch_us": 1e3 * ms_gemm / len(tape),
+            "flops_per_launch": fl / len(tape),
+            "with_dequant": {"avg_call_us": 1e3 * ms_call / len(tape), "achieved": fl / (ms_call * 1e-3) / 1e12,
+                             "note": "same calls including the per-call NF4 dequantisation kernel (HBM-bound, 0 FLOP counted)"},
+            "how": "CUDA-graph replay of the step's taped calls, inputs rotated over 3 buffers per shape, best of 3"}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args) -> None:
     """The reference's CPU implementation of the path on the host cores: oracle port (the reference is Python and its
@@ -122,7 +205,7 @@ def run_reference(args) -> None:
         return
     import torch
     from oracle import cpu_step
-    model = args.model or ("JiT-B/16" if args.gpus == 1 else "JiT-L/16")
+    model = args.model
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cb = min(args.cpu_batch, args.batch)
@@ -162,7 +245,7 @@ def run_ours(args) -> None:
     from vision_pt_b200 import ops
     from vision_pt_b200 import train as T
 
-    model_name = args.model or ("JiT-B/16" if world == 1 else "JiT-L/16")
+    model_name = args.model
     net = T.build_jit_qlora(model_name, rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
     step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
                                seed=42 + rank)
@@ -206,6 +289,7 @@ def run_ours(args) -> None:
     ms_step = ms_total / args.steps
     value = world * args.batch * args.steps / (ms_total * 1e-3)
     final_loss = float(step.loss.item())
+    loss_target = step.hp.loss_target
 
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> D2H loss, every step
     barrier()
@@ -223,36 +307,13 @@ def run_ours(args) -> None:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * args.batch * args.steps / (float(ms2.item()) * 1e-3)
 
-    # ---- roofline of the dominant kernel: every fused-linear launch of 2 eager steps bracketed by CUDA events
+    # ---- roofline of the dominant kernel (the CTA-pair NF4-LoRA GEMM): the fused-linear calls of one real step are taped,
+    # then replayed back to back from a CUDA graph on buffers of the same shapes (inputs rotate over > L2 worth of memory)
+    # and timed with CUDA events on the launching stream -- once GEMM only (`reuse_scratch`: the dequantised weight is
+    # already in the workspace) and once as issued in the step (dequantisation + GEMM).
     roof = None
     if rank == 0:
-        ops.GEMM_TIMER = []
-        was = step.use_graph
-        step.use_graph = False
-        for _ in range(2):
-            step.run()
-        torch.cuda.synchronize()
-        step.use_graph = was
-        recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
-        dom = [r for r in recs if r["nf4"] and r["lora"]]
-        t_ms = sum(r["e0"].elapsed_time(r["e1"]) for r in dom)
-        fl = sum(r["flops"] for r in dom)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = peaks.get("bf16_tflops_sustained")
-        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
-        if not peak:
-            peak, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-        achieved = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
-        all_ms = sum(r["e0"].elapsed_time(r["e1"]) for r in recs)
-        roof = {"bound": "tensor", "kernel": "gemm_nf4lora_kernel (NF4 + LoRA, fwd and bwd-dX launches of the block linears)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "launches": len(dom) // 2, "avg_launch_us": 1e3 * t_ms / max(len(dom), 1),
-                "gemm_ms_per_step": all_ms / 2, "flops_per_step": fl / 2}
-
+        roof = gemm_roofline(step, ops, torch)
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -265,8 +326,40 @@ def run_ours(args) -> None:
         cpu = {"value": r["images_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"{args.cpu_batch} images/step x {args.cpu_steps} steps of the same step (fp32, NF4 dequantised per call)"}
 
+    # ---- secondary workload at N > 1: BASELINE.json configs[2], JiT-L/16 data parallel (same step, same timing rules)
+    extra = None
+    if world > 1 and not args.no_extra and model_name != "JiT-L/16":
+        del step, net
+        torch.cuda.empty_cache()
+        net = T.build_jit_qlora("JiT-L/16", rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
+        step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
+                                   seed=42 + rank)
+        load_batch_l = lambda: (step.image.copy_(host[0], non_blocking=True), step.class_ids.copy_(host[1], non_blocking=True),
+                                step.attention_mask.copy_(host[2], non_blocking=True))
+        load_batch_l()
+        for _ in range(3):
+            step.run()
+        ksteps = max(3, args.steps // 2)
+        barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(ksteps):
+            step.run()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        msl = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(msl, op=dist.ReduceOp.MAX)
+        fl_l = T.step_flops(net.config, args.batch, args.res, args.res, rank=args.rank)
+        extra = {"workload": workload_name("JiT-L/16", args.batch, args.res, args.rank), "value": world * args.batch * ksteps / (float(msl.item()) * 1e-3),
+                 "unit": UNIT, "ms_per_step": float(msl.item()) / ksteps, "steps": ksteps,
+                 "achieved_tflops_step": world * fl_l["total"] / (float(msl.item()) / ksteps * 1e-3) / 1e12}
+        net_cfg_for_flops = T.MODEL_CONFIGS[model_name]()
+    else:
+        net_cfg_for_flops = net.config
+
     if rank == 0:
-        fl = T.step_flops(net.config, args.batch, args.res, args.res, rank=args.rank)
+        fl = T.step_flops(net_cfg_for_flops, args.batch, args.res, args.res, rank=args.rank)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -275,13 +368,14 @@ def run_ours(args) -> None:
                        "global_batch": world * args.batch, "parallelism": f"dp{world}",
                        "cuda_graph": not args.no_graph, "gradient_checkpointing": False,
                        "l2": "no flush: one step streams far more than the 126 MB L2 (saved activations of every block)",
-                       "optimizer": "AdamW over the flat LoRA buffer, clip_grad_norm 1.0", "loss": step.hp.loss_target},
+                       "optimizer": "AdamW over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "extra_workload": extra,
             "step_tflops_algorithmic": fl["total"] / 1e12,
             "achieved_tflops_step": world * fl["total"] / (ms_step * 1e-3) / 1e12,
             "final_loss": final_loss,

@@ -91,6 +91,8 @@ typedef struct {
   int64_t ld_scratch;          /* unused since ABI 2 (kept for layout compatibility) */
   int64_t scratch_bytes;       /* capacity of w_scratch */
   int64_t ld_side;             /* row pitch of `side` in elements */
+  int32_t reuse_scratch;       /* non-zero: w_scratch already holds this weight in this direction's layout (the previous
+                                * call on the stream used the same weight and direction): skip the dequantisation */
 } vpt_linear_args;
 
 int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K);

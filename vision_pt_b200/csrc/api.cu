@@ -116,8 +116,9 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
       const long n = static_cast<long>(N) * K;
       if (!bwd) {
         const long ldk = (K + 7) / 8 * 8;
-        nf4_dequant_pitched_kernel<<<blocks_for((n + 7) / 8, 256, 148 * 16), 256, 0, stream>>>(
-            a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, ws, n, K, ldk);
+        if (!a->reuse_scratch)
+          nf4_dequant_pitched_kernel<<<blocks_for((n + 7) / 8, 256, 148 * 16), 256, 0, stream>>>(
+              a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, ws, n, K, ldk);
         g.w = ws; g.ldw = ldk;
         g.p_rows = a->lora_down; g.ldp = a->ld_lora_down;
         g.p.q_rows = static_cast<const __nv_bfloat16*>(a->lora_up);
@@ -126,7 +127,8 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
         __nv_bfloat16* upT = ws + static_cast<long>(K) * ldn;       // [16, ldn]
         __nv_bfloat16* downT = upT + 16 * ldn;                      // [K, 16]
         const int tiles_k = (K + 63) / 64, tiles = ((N + 63) / 64) * tiles_k;
-        nf4_dequant_transposed_kernel<<<tiles + (lora ? 4 : 0), 256, 0, stream>>>(
+        if (!a->reuse_scratch)
+          nf4_dequant_transposed_kernel<<<tiles + (lora ? 4 : 0), 256, 0, stream>>>(
             a->w.packed, a->w.qabsmax, a->w.nested_absmax, a->w.nested_code, a->w.code, a->w.offset, ws, N, K, ldn, tiles_k,
             tiles, static_cast<const __nv_bfloat16*>(a->lora_up), upT, ldn, static_cast<const __nv_bfloat16*>(a->lora_down),
             static_cast<long>(a->ld_lora_down), downT);

@@ -167,9 +167,11 @@ def _pad_rank(down: torch.Tensor | None, up: torch.Tensor | None):
 
 
 def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, scale: float, residual=None,
-               want_side: bool = False, backward: bool = False, tile_n: int = 0):
-    """One launch of the fused kernel.  forward: x2 [M,K] -> y [M,N]; backward: x2 = dy [M,N] -> dx [M,K].
-    `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None)."""
+               want_side: bool = False, backward: bool = False, tile_n: int = 0, reuse_scratch: bool = False):
+    """One call of the fused linear.  forward: x2 [M,K] -> y [M,N]; backward: x2 = dy [M,N] -> dx [M,K].
+    `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None).
+    reuse_scratch: the previous call on this stream used the same weight and direction, so the dequantised copy in the
+    workspace is still valid and the dequantisation kernel is skipped."""
     _need_cuda(x2)
     if x2.dtype != torch.bfloat16:
         raise TypeError("fused linear runs in bfloat16")
@@ -187,6 +189,7 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
             args.w_scratch = _p(scratch)
             args.ld_scratch = (K + 7) // 8 * 8
             args.scratch_bytes = scratch.numel()
+            args.reuse_scratch = int(reuse_scratch)
     else:
         N, K = w.shape
         args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K), None, None, 0)
@@ -218,14 +221,15 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.call("vpt_nf4lora_linear_bwd_dx" if backward else "vpt_nf4lora_linear_fwd", C.byref(args), _stream())
-    if scratch is not None:
+    if scratch is not None and not reuse_scratch:
         _lib.add_launches(1)          # the per-call dequantisation kernel in front of the GEMM
     if timer is not None:
         e1.record()
         lora = down is not None
         flops = 2.0 * M * K * N + (2.0 * M * RANK * (K + N) if lora else 0.0)
         timer.append({"e0": e0, "e1": e1, "flops": flops, "M": M, "K": K, "N": N, "bwd": backward, "lora": lora,
-                      "nf4": isinstance(w, Nf4Tensors)})
+                      "nf4": isinstance(w, Nf4Tensors), "scratch": scratch is not None,
+                      "call": (x2.shape, x2.stride(0), w, bias, down, up, scale, residual is not None, want_side, backward)})
     return out, side
 
 
