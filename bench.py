@@ -115,7 +115,7 @@ def physical_gpu_index(local: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-def gemm_roofline(step, ops, torch):
+def gemm_roofline(step, ops, torch, replay_here: bool = True):
     ops.GEMM_TIMER = []
     was = step.use_graph
     step.use_graph = False
@@ -124,7 +124,7 @@ def gemm_roofline(step, ops, torch):
     step.use_graph = was
     recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
     tape = [r for r in recs if r["nf4"] and r["lora"] and r["scratch"]]
-    if not tape:
+    if not tape or not replay_here:
         return None
     dev = torch.device("cuda", torch.cuda.current_device())
     pool: dict = {}
@@ -233,13 +233,19 @@ def run_ours(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("VPT_DIST_BACKEND", "nccl") != "nccl":
+        local = 0
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (vision_pt_b200 has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        backend = os.environ.get("VPT_DIST_BACKEND", "nccl")     # "gloo" only to exercise the N > 1 path on a 1-GPU box
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend)
         group = dist.group.WORLD
 
     from vision_pt_b200 import ops
@@ -259,7 +265,7 @@ def run_ours(args) -> None:
 
     def barrier():
         if world > 1:
-            dist.barrier(device_ids=[local])
+            dist.barrier(device_ids=[local]) if dist.get_backend() == "nccl" else dist.barrier()
 
     load_batch()
     torch.cuda.synchronize()
@@ -311,9 +317,8 @@ def run_ours(args) -> None:
     # then replayed back to back from a CUDA graph on buffers of the same shapes (inputs rotate over > L2 worth of memory)
     # and timed with CUDA events on the launching stream -- once GEMM only (`reuse_scratch`: the dequantised weight is
     # already in the workspace) and once as issued in the step (dequantisation + GEMM).
-    roof = None
-    if rank == 0:
-        roof = gemm_roofline(step, ops, torch)
+    # Every rank runs the taping step (it contains the gradient all-reduce); only rank 0 replays and reports.
+    roof = gemm_roofline(step, ops, torch, replay_here=rank == 0)
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

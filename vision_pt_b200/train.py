@@ -174,12 +174,14 @@ class JiTQLoRATrainStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
         self.graph: torch.cuda.CUDAGraph | None = None
+        self.graph_update: torch.cuda.CUDAGraph | None = None
         self.kernel_launches = 0
         torch.manual_seed(seed)
         model.train()
 
     # ------------------------------------------------------------------ the step itself (eager or under capture)
-    def _step(self) -> None:
+    def _compute(self) -> None:
+        """Noise, forward, loss, backward: LoRA gradients end up in the flat fp32 buffer.  No communication."""
         hp = self.hp
         images = self.image
         B = images.shape[0]
@@ -196,7 +198,15 @@ class JiTQLoRATrainStep:
         loss.backward()
         if not self.flat.direct:
             self.flat.gather_autograd_grads()
-        scale = self.flat.all_reduce(self.group) if self.world > 1 else 1.0   # SUM; the mean is folded into grad_scale
+        self.loss.copy_(loss.detach())
+
+    def _exchange(self) -> float:
+        """The one collective of the step: SUM all-reduce of the flat LoRA-gradient buffer (NCCL); returns 1 / world."""
+        return self.flat.all_reduce(self.group) if self.world > 1 else 1.0
+
+    def _update(self, scale: float) -> None:
+        """Gradient-norm clipping + AdamW + zero_grad over the flat buffers (two kernels)."""
+        hp = self.hp
         sumsq = None
         if hp.clip_grad_norm is not None:
             self.sumsq.zero_()
@@ -205,10 +215,15 @@ class JiTQLoRATrainStep:
         self.step_t += 1
         ops.adamw_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.step_t, hp.lr, hp.betas, hp.eps,
                        hp.weight_decay, grad_scale=scale, sumsq=sumsq, max_norm=hp.clip_grad_norm or 0.0, zero_grad=True)
-        self.loss.copy_(loss.detach())
+
+    def _step(self) -> None:
+        self._compute()
+        self._update(self._exchange())
 
     def capture(self, warmup: int = 2) -> None:
-        """Eager warm-up on a side stream (one-time kernel attribute setup, allocator growth, NCCL init), then capture."""
+        """Eager warm-up on a side stream (one-time kernel attribute setup, allocator growth, NCCL init), then capture.
+        One graph at world size 1.  With data parallelism the step is two graphs (compute | update) with the NCCL
+        all-reduce launched between them on the same stream: three launches per step, and no collective inside a capture."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -218,8 +233,15 @@ class JiTQLoRATrainStep:
         torch.cuda.synchronize()
         before = ops._lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._step()
+        if self.world == 1:
+            with torch.cuda.graph(self.graph):
+                self._step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self._compute()
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+                self._update(1.0 / self.world)
         self.kernel_launches = ops._lib.launch_count() - before
 
     def run(self) -> torch.Tensor:
@@ -227,6 +249,9 @@ class JiTQLoRATrainStep:
             if self.graph is None:
                 self.capture()
             self.graph.replay()
+            if self.world > 1:
+                self._exchange()
+                self.graph_update.replay()
         else:
             before = ops._lib.launch_count()
             self._step()
