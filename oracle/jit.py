@@ -161,7 +161,7 @@ def jit_block(P: dict, prefix: str, x, freqs_cis, key_mask, num_heads: int, alph
 
 def timestep_embedding(t, dim: int = 256):
     half = dim // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(t.device)
     ang = t[:, None].float() * freqs[None, :]
     return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)   # flip_sin_to_cos=True
 
@@ -185,9 +185,10 @@ def jit_forward(P: dict, cfg: dict, image, timestep, context, original_size, tar
     patches = F.conv2d(image, P["patch_embedder.proj_1.weight"], None, stride=p)
     patches = F.conv2d(patches, P["patch_embedder.proj_2.weight"], P["patch_embedder.proj_2.bias"]).flatten(2).transpose(1, 2)
     n_patch, n_ctx = patches.shape[1], ctx.shape[1]
-    freqs = rope_freqs_cis(cfg, height, width, n_ctx)
-    ones = torch.ones(B, n_patch + 6 + time_tokens.shape[1])
-    mask = torch.cat([ones, context_mask.float() if context_mask is not None else torch.ones(B, n_ctx)], dim=1)
+    dev = image.device                                   # the checker runs wherever its inputs live (CPU in tests/, GPU for the 200-step curve)
+    freqs = rope_freqs_cis(cfg, height, width, n_ctx).to(dev)
+    ones = torch.ones(B, n_patch + 6 + time_tokens.shape[1], device=dev)
+    mask = torch.cat([ones, context_mask.float().to(dev) if context_mask is not None else torch.ones(B, n_ctx, device=dev)], dim=1)
     tokens = torch.cat([patches, size_tokens, time_tokens], dim=1)
     csb, fuse = cfg.get("context_start_block", 0), cfg.get("do_context_fuse", False)
     for i in range(cfg["depth"]):

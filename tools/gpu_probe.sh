@@ -1,1 +1,1 @@
-NCCL_DEBUG=WARN timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 6 --warmup 3 2>&1 | tail -4
+timeout 400 python -m pytest tests/test_gpu_train.py -x -q 2>&1 | grep -E "^E " | head -20
