@@ -96,6 +96,20 @@ typedef struct {
 } vpt_linear_args;
 
 int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K);
+
+/* Fills the workspaces of up to 8 linears in ONE launch (the seven NF4 weights of a transformer block): slot i gets what
+ * vpt_nf4lora_linear_fwd (transposed = 0) or _bwd_dx (transposed = 1; lora_down / lora_up given when the linear has
+ * LoRA) would dequantise into w_scratch itself; the linear calls then pass that slot with reuse_scratch = 1.  Bit-exact
+ * like vpt_nf4_dequant. */
+typedef struct {
+  vpt_nf4_weight w;
+  void* w_scratch;             /* vpt_linear_scratch_bytes(N, K) bytes, 16-byte aligned */
+  int64_t scratch_bytes;
+  const void* lora_down;       /* [16,K] bf16 pitch ld_lora_down, or NULL */
+  int64_t ld_lora_down;
+  const void* lora_up;         /* [N,16] bf16 */
+} vpt_nf4_dequant_item;
+int vpt_nf4_dequant_batch(const vpt_nf4_dequant_item* items, int32_t n_items, int32_t transposed, vpt_stream_t stream);
 int vpt_nf4lora_linear_fwd(const vpt_linear_args* a, vpt_stream_t stream);
 int vpt_nf4lora_linear_bwd_dx(const vpt_linear_args* a, vpt_stream_t stream);
 

@@ -1,1 +1,2 @@
-timeout 400 python -m pytest tests/test_gpu_train.py -x -q 2>&1 | grep -E "^E " | head -20
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-250

@@ -33,6 +33,11 @@ class LoraGradItemC(C.Structure):
                 ("ld_out", C.c_int64)]
 
 
+class DequantItemC(C.Structure):
+    _fields_ = [("w", Nf4WeightC), ("w_scratch", C.c_void_p), ("scratch_bytes", C.c_int64), ("lora_down", C.c_void_p),
+                ("ld_lora_down", C.c_int64), ("lora_up", C.c_void_p)]
+
+
 class AttnTensorC(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sl", C.c_int64), ("sh", C.c_int64)]
 
@@ -48,6 +53,7 @@ SIGNATURES: dict[str, list] = {
     "vpt_nf4lora_linear_fwd": [C.POINTER(LinearArgsC), _P],
     "vpt_nf4lora_linear_bwd_dx": [C.POINTER(LinearArgsC), _P],
     "vpt_lora_grad_batch": [C.POINTER(LoraGradItemC), _I32, _P],
+    "vpt_nf4_dequant_batch": [C.POINTER(DequantItemC), _I32, _I32, _P],
     "vpt_attn_fwd": [_AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P],
     "vpt_attn_bwd": [_AT, _AT, _AT, _AT, _AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P],
     "vpt_rmsnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _F, _P],

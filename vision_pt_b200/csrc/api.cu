@@ -84,6 +84,39 @@ extern "C" int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K) {
   const int64_t bwd = static_cast<int64_t>(K) * ldn + 16 * ldn + static_cast<int64_t>(K) * 16;
   return 2 * (fwd > bwd ? fwd : bwd) + 256;
 }
+extern "C" int vpt_nf4_dequant_batch(const vpt_nf4_dequant_item* items, int32_t n_items, int32_t transposed, vpt_stream_t stream) {
+  VPT_REQUIRE(items != nullptr && n_items > 0 && n_items <= kDqMaxItems, "vpt_nf4_dequant_batch: 1..8 items");
+  DequantBatch bp{};
+  int ctas = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const vpt_nf4_dequant_item& s = items[i];
+    const int N = s.w.N, K = s.w.K;
+    VPT_REQUIRE(N > 0 && K > 0 && s.w.packed && s.w.qabsmax && s.w.nested_absmax && s.w.nested_code && s.w.code && s.w_scratch,
+                "vpt_nf4_dequant_batch: NF4 tensors / workspace missing");
+    VPT_REQUIRE((reinterpret_cast<uintptr_t>(s.w_scratch) & 15) == 0 && s.scratch_bytes >= vpt_linear_scratch_bytes(N, K),
+                "vpt_nf4_dequant_batch: w_scratch must be 16-byte aligned and hold vpt_linear_scratch_bytes(N, K) bytes");
+    DequantItem& d = bp.items[i];
+    d.packed = s.w.packed; d.qabsmax = s.w.qabsmax; d.nested_absmax = s.w.nested_absmax; d.nested_code = s.w.nested_code;
+    d.code = s.w.code; d.offset = s.w.offset; d.N = N; d.K = K;
+    d.out = static_cast<__nv_bfloat16*>(s.w_scratch);
+    d.transposed = transposed ? 1 : 0;
+    d.ld = transposed ? (N + 7) / 8 * 8 : (K + 7) / 8 * 8;
+    d.tiles_k = (K + 63) / 64;
+    d.num_tiles = ((N + 63) / 64) * d.tiles_k;
+    d.cta_begin = ctas;
+    const bool lora = transposed && s.lora_down != nullptr;
+    if (lora) VPT_REQUIRE(s.lora_up != nullptr && s.ld_lora_down >= K, "vpt_nf4_dequant_batch: bad LoRA arguments");
+    d.up = lora ? static_cast<const __nv_bfloat16*>(s.lora_up) : nullptr;
+    d.down = lora ? static_cast<const __nv_bfloat16*>(s.lora_down) : nullptr;
+    d.ldd = s.ld_lora_down;
+    ctas += d.num_tiles + (lora ? 4 : 0);
+  }
+  bp.n_items = n_items;
+  nf4_dequant_batch_kernel<<<ctas, 256, 0, S(stream)>>>(bp);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream) {
   VPT_REQUIRE(a && a->in && a->out, "vpt_nf4lora_linear: null pointer");
   const int N = a->w.N, K = a->w.K;
@@ -235,7 +268,15 @@ extern "C" int vpt_rmsnorm_fwd(const void* x, const void* w, void* y, float* rst
 extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
                                float* dw, int64_t rows, int32_t D, int64_t ld, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && dx && rows > 0 && D % 8 == 0 && D <= 2048 && ld % 8 == 0, "vpt_rmsnorm_bwd: bad arguments");
-  rmsnorm_bwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(w), rstd, BF(dres), BFM(dx), dw, rows, D, ld, eps);
+  const unsigned grid = blocks_for(rows, kEwThreads / 32, 1L << 30);
+  const int nch = (D / 8 + 31) / 32;
+#define VPT_RMS_BWD(CH) rmsnorm_bwd_kernel<CH><<<grid, kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(w), rstd, BF(dres), BFM(dx), dw, rows, D, ld, eps)
+  if (nch <= 1) VPT_RMS_BWD(1);
+  else if (nch <= 3) VPT_RMS_BWD(3);
+  else if (nch <= 4) VPT_RMS_BWD(4);
+  else if (nch <= 5) VPT_RMS_BWD(5);
+  else VPT_RMS_BWD(8);
+#undef VPT_RMS_BWD
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -91,6 +91,9 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 }
 
 // dx = w*dy*rstd - x * rstd^3 * mean(w*dy*x)  (+ dres);  optional dw[D] += sum_rows dy * x * rstd (fp32 atomics)
+// kCh = 16-byte chunks per lane (D <= 256 * kCh): all three input rows (x, dy, dres) are requested before the first use,
+// so a warp has 3 * kCh independent 16-byte loads in flight instead of stalling once per phase.
+template <int kCh>
 __global__ void __launch_bounds__(kEwThreads)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
@@ -100,14 +103,23 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   const int nch = D >> 3;
   const bool live = row < rows;
-  uint4 vx[kEwMaxChunks], vg[kEwMaxChunks];
-  float dot = 0.f, ss = 0.f;
+  uint4 vx[kCh], vg[kCh], vr[kCh];
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
+    vx[i] = vg[i] = vr[i] = make_uint4(0, 0, 0, 0);
     if (live && c < nch) {
       vx[i] = ld_stream(x + row * ld + c * 8);
       vg[i] = ld_stream(dy + row * ld + c * 8);
+      if (dres != nullptr) vr[i] = ld_stream(dres + row * ld + c * 8);
+    }
+  }
+  const float rstd_given = (live && rstd_in != nullptr) ? rstd_in[row] : 0.f;
+  float dot = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCh; ++i) {
+    const int c = lane + i * 32;
+    if (live && c < nch) {
       float fx[8], fg[8], fw[8];
       ew_unpack8(vx[i], fx);
       ew_unpack8(vg[i], fg);
@@ -121,22 +133,19 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   }
   dot = warp_sum(dot);
   ss = warp_sum(ss);
-  const float rstd = !live ? 0.f : (rstd_in != nullptr ? rstd_in[row] : rsqrtf(ss / static_cast<float>(D) + eps));
+  const float rstd = !live ? 0.f : (rstd_in != nullptr ? rstd_given : rsqrtf(ss / static_cast<float>(D) + eps));
   const float coef = dot * rstd * rstd * rstd / static_cast<float>(D);
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (live && c < nch) {
       float fx[8], fg[8], fw[8], fr[8], o[8];
       ew_unpack8(vx[i], fx);
       ew_unpack8(vg[i], fg);
+      ew_unpack8(vr[i], fr);
       if (w != nullptr) ew_unpack8(*reinterpret_cast<const uint4*>(w + c * 8), fw);
-      if (dres != nullptr) ew_unpack8(ld_stream(dres + row * ld + c * 8), fr);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        o[e] = fg[e] * (w != nullptr ? fw[e] : 1.f) * rstd - fx[e] * coef;
-        if (dres != nullptr) o[e] += fr[e];
-      }
+      for (int e = 0; e < 8; ++e) o[e] = fg[e] * (w != nullptr ? fw[e] : 1.f) * rstd - fx[e] * coef + fr[e];
       st_stream(dx + row * ld + c * 8, ew_pack8(o));
       if (dw != nullptr) {
 #pragma unroll

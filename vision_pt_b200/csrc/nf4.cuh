@@ -206,6 +206,118 @@ nf4_dequant_transposed_kernel(const uint8_t* __restrict__ packed, const uint8_t*
   }
 }
 
+// Batched variant: every NF4 weight of a transformer block in ONE launch (7 per direction), each into its own workspace
+// slot in the layout the CTA-pair GEMM reads ([N, ldk] for the forward, transposed [K, ldn] + the two transposed LoRA
+// matrices for the backward).  Same arithmetic, hence the same bits, as nf4_dequant_kernel<bf16>.  One launch instead of
+// seven removes six launch gaps / tails per block and direction (profiles/r1f: 168 dequant launches = 1.07 ms per step).
+constexpr int kDqMaxItems = 8;
+struct DequantItem {
+  const uint8_t* packed;
+  const uint8_t* qabsmax;
+  const float* nested_absmax;
+  const float* nested_code;
+  const float* code;
+  float offset;
+  int N, K;
+  __nv_bfloat16* out;              // [N, ld] or, transposed, [K, ld]
+  long ld;
+  int transposed;
+  int tiles_k, cta_begin, num_tiles;
+  const __nv_bfloat16* up;         // transposed only: lora_up [N,16] -> upT [16, ld] at out + K*ld
+  const __nv_bfloat16* down;       //                  lora_down [16,K] pitch ldd -> downT [K,16] after upT
+  long ldd;
+};
+struct DequantBatch {
+  DequantItem items[kDqMaxItems];
+  int n_items;
+};
+
+__global__ void __launch_bounds__(256)
+nf4_dequant_batch_kernel(const __grid_constant__ DequantBatch bp) {
+  int ii = 0;
+  while (ii + 1 < bp.n_items && static_cast<int>(blockIdx.x) >= bp.items[ii + 1].cta_begin) ++ii;
+  const DequantItem& d = bp.items[ii];
+  const int local = blockIdx.x - d.cta_begin;
+  const int N = d.N, K = d.K;
+  const long ld = d.ld;
+  if (local >= d.num_tiles) {                       // the item's trailing blocks: LoRA transposes
+    if (d.up == nullptr) return;
+    __nv_bfloat16* upT = d.out + static_cast<long>(K) * ld;
+    __nv_bfloat16* downT = upT + 16 * ld;
+    const int t0 = (local - d.num_tiles) * blockDim.x + threadIdx.x;
+    const int stride = 4 * blockDim.x;
+    for (int i = t0; i < 16 * static_cast<int>(ld); i += stride) {
+      const int r = i / static_cast<int>(ld), n = i % static_cast<int>(ld);
+      upT[i] = n < N ? d.up[static_cast<long>(n) * 16 + r] : __float2bfloat16_rn(0.f);
+    }
+    for (int i = t0; i < K * 16; i += stride) {
+      const int k = i >> 4, r = i & 15;
+      downT[i] = d.down[static_cast<long>(r) * d.ldd + k];
+    }
+    return;
+  }
+  __shared__ float s_code[16];
+  __shared__ float s_ncode[256];
+  __shared__ unsigned short tile[64][66];
+  if (threadIdx.x < 16) s_code[threadIdx.x] = d.code[threadIdx.x];
+  s_ncode[threadIdx.x] = d.nested_code[threadIdx.x];
+  __syncthreads();
+  const int n0 = (local / d.tiles_k) * 64, k0 = (local % d.tiles_k) * 64;
+  const bool aligned = (K & 7) == 0;
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int r = i >> 3, g = i & 7;
+    const int n = n0 + r, k = k0 + g * 8;
+    unsigned short v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0;
+    if (n < N && k < K) {
+      const long flat = static_cast<long>(n) * K + k;
+      if (aligned) {                               // 8 codes = one 32-bit word inside one 64-block
+        const long blk = flat >> 6;
+        const float am = __fadd_rn(__fmul_rn(s_ncode[d.qabsmax[blk]], d.nested_absmax[blk >> 8]), d.offset);
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(d.packed + (flat >> 1));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t byte = (w >> (8 * b)) & 0xffu;
+          v[2 * b] = __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s_code[byte >> 4], am)));
+          v[2 * b + 1] = __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s_code[byte & 15u], am)));
+        }
+      } else {
+        for (int e = 0; e < 8 && k + e < K; ++e) {
+          const long f = flat + e;
+          const long blk = f >> 6;
+          const float am = __fadd_rn(__fmul_rn(s_ncode[d.qabsmax[blk]], d.nested_absmax[blk >> 8]), d.offset);
+          const uint32_t byte = d.packed[f >> 1];
+          const uint32_t nib = (f & 1) ? (byte & 15u) : (byte >> 4);
+          v[e] = __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s_code[nib], am)));
+        }
+      }
+    }
+    if (!d.transposed) {
+      // row-major slot: columns k .. k+7 of row n (ld is a multiple of 8 >= K, so a full 16-byte store stays in the row)
+      if (n < N && k < ld)
+        *reinterpret_cast<uint4*>(d.out + static_cast<long>(n) * ld + k) =
+            make_uint4(v[0] | (uint32_t(v[1]) << 16), v[2] | (uint32_t(v[3]) << 16), v[4] | (uint32_t(v[5]) << 16),
+                       v[6] | (uint32_t(v[7]) << 16));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tile[r][g * 8 + e] = v[e];
+    }
+  }
+  if (!d.transposed) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int kk = i >> 3, g = i & 7;
+    const int k = k0 + kk, n = n0 + g * 8;
+    if (k >= K || n >= ld) continue;
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = static_cast<uint32_t>(tile[g * 8 + 2 * e][kk]) | (static_cast<uint32_t>(tile[g * 8 + 2 * e + 1][kk]) << 16);
+    *reinterpret_cast<uint4*>(d.out + static_cast<long>(k) * ld + n) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Load-time repack for ragged in_features (K % 64 != 0, e.g. the SwiGLU hidden 2730 / 3413 of JiT-L / -H): bitsandbytes
 // packs the FLATTENED [N,K] weight, so rows start at arbitrary nibbles and 64-blocks straddle rows.  The GEMM producers
 // want 16-byte aligned rows: codes are re-packed row by row with pitch K_pad/2 bytes (K_pad = K rounded up to 64, padding

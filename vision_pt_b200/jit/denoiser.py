@@ -212,7 +212,7 @@ class JiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cos_sin, seqlens, spec, *lora):
-        lins, n1w, n2w, qnw, knw, H, eps = spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _ = spec
         B, L, D = x.shape
         M = B * L
         x2 = x.reshape(M, D)
@@ -220,9 +220,14 @@ class JiTBlockFn(torch.autograd.Function):
             x2 = x2.contiguous()
         pads = [ops._pad_rank(l.down, l.up) for l in lins]
 
+        # all seven NF4 weights of the block dequantised by one launch into L2-resident slots
+        slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=False) \
+            if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue" else None
+
         def lin(i, inp, residual=None):
             l = lins[i]
-            return ops.linear_raw(inp, l.w, l.bias, pads[i][0], pads[i][1], l.scale, residual, want_side=True)
+            return ops.linear_raw(inp, l.w, l.bias, pads[i][0], pads[i][1], l.scale, residual, want_side=True,
+                                  scratch=slots[i] if slots is not None else None)
 
         h1, rstd1 = ops.rmsnorm_fwd_raw(x2, n1w, eps)
         q_pre, t_q = lin(0, h1)
@@ -244,13 +249,19 @@ class JiTBlockFn(torch.autograd.Function):
         ctx.seqlens, ctx.cos_sin = seqlens, cos_sin
         ctx.save_for_backward(x2, rstd1, h1, q_pre, k_pre, v, q, k, o2, lse2, x1, rstd2, h2, g, u, a,
                               t_q, t_k, t_v, t_o, t_g, t_u, t_3)
-        return y.view(B, L, D)
+        y3 = y.view(B, L, D)
+        if tail is not None:
+            # JiT re-appends the ORIGINAL context tokens in front of every block >= context_start_block and strips the
+            # block's outputs for them (reference denoiser.py:1092-1113): with the slots kept in the buffer that is one small
+            # strided copy here (and zeroing their gradient in backward) instead of a torch.cat of all tokens per block
+            y3[:, n_keep:].copy_(tail)
+        return y3
 
     @staticmethod
     def backward(ctx, dy):
         (x2, rstd1, h1, q_pre, k_pre, v, q, k, o2, lse2, x1, rstd2, h2, g, u, a,
          t_q, t_k, t_v, t_o, t_g, t_u, t_3) = ctx.saved_tensors
-        lins, n1w, n2w, qnw, knw, H, eps = ctx.spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in = ctx.spec
         pads = ctx.pads
         B, L, D = ctx.dims
         M = B * L
@@ -260,9 +271,13 @@ class JiTBlockFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         grads: list = [None] * 14
 
+        slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=True) \
+            if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue" else None
+
         def back(i, dout, residual=None):
             l = lins[i]
-            return ops.linear_raw(dout, l.w, None, pads[i][0], pads[i][1], l.scale, residual, want_side=True, backward=True)
+            return ops.linear_raw(dout, l.w, None, pads[i][0], pads[i][1], l.scale, residual, want_side=True, backward=True,
+                                  scratch=slots[i] if slots is not None else None)
 
         # LoRA parameter gradients: collected over the block and reduced by ONE batched launch at the end; linears that
         # share their input (q/k/v <- h1, w_1/w_2 <- h2) form one item so the activation is read once
@@ -319,6 +334,10 @@ class JiTBlockFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.rmsnorm_bwd_raw(dh1, x2, n1w, rstd1, dx1, eps).view(B, L, D)
+            if fresh_in:
+                # this block's input had its context slots REPLACED by the previous block's epilogue: no gradient flows
+                # through them into that block (the reference strips those rows, denoiser.py:1111-1113)
+                dx[:, n_keep:].zero_()
         return (dx, None, None, None, *grads)
 
 
@@ -346,18 +365,25 @@ class JiTBlock(nn.Module):
                 and all(_linear_ok(l) for l in self._linears())
                 and self.attn.attn_dropout.p == 0 and self.attn.proj_dropout.p == 0 and self.mlp.ffn_dropout.p == 0)
 
-    def forward(self, hidden_states, cos_sin, seqlens=None):
+    def forward(self, hidden_states, cos_sin, seqlens=None, ctx_tail=None, n_keep=0, fresh_in=False):
+        """ctx_tail [B, L - n_keep, D]: when given, rows n_keep.. of the OUTPUT are replaced by it (fresh context tokens for
+        the next block).  fresh_in: rows n_keep.. of the INPUT were produced that way by the previous block, so the
+        gradient with respect to them is dropped."""
         if self.fused_eligible(hidden_states):
             lins = [_Lin(l) for l in self._linears()]
             bf = lambda w: w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
             spec = (lins, bf(self.norm1.weight), bf(self.norm2.weight), bf(self.attn.q_norm.weight),
-                    bf(self.attn.k_norm.weight), self.attn.num_heads, self.eps)
+                    bf(self.attn.k_norm.weight), self.attn.num_heads, self.eps,
+                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in))
             lora = []
             for l in lins:
                 lora += [l.down, l.up]
             return JiTBlockFn.apply(hidden_states, cos_sin, seqlens, spec, *lora)
         hidden_states = hidden_states + self.attn(self.norm1(hidden_states), cos_sin, seqlens)
-        return hidden_states + self.mlp(self.norm2(hidden_states))
+        out = hidden_states + self.mlp(self.norm2(hidden_states))
+        if ctx_tail is not None:
+            out = torch.cat([out[:, :n_keep], ctx_tail.detach()], dim=1)     # autograd drops the replaced rows' gradient
+        return out
 
 
 class JiT(nn.Module):
@@ -433,11 +459,11 @@ class JiT(nn.Module):
         size_info = torch.cat([original_size, target_size, crop_coords], dim=1).view(-1)
         return self.image_size_embedder(size_info).view(-1, 6, self.config.hidden_size)
 
-    def forward_block(self, block, tokens, cos_sin, seqlens):
+    def forward_block(self, block, tokens, cos_sin, seqlens, ctx_tail=None, n_keep=0, fresh_in=False):
         if self.gradient_checkpointing and self.training:
             import torch.utils.checkpoint as checkpoint
-            return checkpoint.checkpoint(block, tokens, cos_sin, seqlens, use_reentrant=False)
-        return block(tokens, cos_sin, seqlens)
+            return checkpoint.checkpoint(block, tokens, cos_sin, seqlens, ctx_tail, n_keep, fresh_in, use_reentrant=False)
+        return block(tokens, cos_sin, seqlens, ctx_tail, n_keep, fresh_in)
 
     def forward(self, image, timestep, context, original_size, target_size, crop_coords, context_mask=None):
         cfg = self.config
@@ -461,14 +487,20 @@ class JiT(nn.Module):
             seq_ctx = None
 
         tokens = torch.cat([patches, size_embed, time_tokens], dim=1)
+        # context slots stay in the token buffer between blocks (JiTBlock.forward: ctx_tail) when nothing upstream trains
+        keep_slots = not cfg.do_context_fuse and not context_embed.requires_grad
+        fresh = False
         for i, block in enumerate(self.blocks):
             with_ctx = i == cfg.context_start_block or (not cfg.do_context_fuse and i >= cfg.context_start_block)
-            if with_ctx:
+            if with_ctx and tokens.shape[1] == pre_ctx:
                 tokens = torch.cat([tokens, context_embed], dim=1)
             L = tokens.shape[1]
             has_ctx = L > pre_ctx
-            tokens = self.forward_block(block, tokens, cos_sin[:L], seq_ctx if has_ctx else None)
-            if not cfg.do_context_fuse and i >= cfg.context_start_block:
+            refresh = keep_slots and has_ctx and i >= cfg.context_start_block
+            tokens = self.forward_block(block, tokens, cos_sin[:L], seq_ctx if has_ctx else None,
+                                        context_embed if refresh else None, pre_ctx, fresh)
+            fresh = refresh
+            if not cfg.do_context_fuse and i >= cfg.context_start_block and not keep_slots:
                 tokens = tokens[:, :-ctx_len, :]
         patches = self.final_layer(tokens[:, :n_patch, :])
         return self.unpatchify(patches, height=height, width=width)

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import AttnTensorC, LinearArgsC, LoraGradItemC, Nf4WeightC
+from ._lib import AttnTensorC, DequantItemC, LinearArgsC, LoraGradItemC, Nf4WeightC
 
 RANK = 16  # LoRA rank of the fused kernels; smaller ranks are zero-padded
 
@@ -32,6 +32,38 @@ def _weight_scratch(device: torch.device, nbytes: int) -> torch.Tensor:
         buf = torch.empty(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return buf
+
+
+_ARENA: dict[tuple, torch.Tensor] = {}
+
+
+def dequant_block(weights: list, downs: list, ups: list, transposed: bool) -> list[torch.Tensor] | None:
+    """Dequantises the NF4 weights of one transformer block with ONE launch (vpt_nf4_dequant_batch), each into its own
+    slot of a per-stream arena; the slots are then handed to linear_raw(scratch=...).  Returns None when the block is not
+    made of NF4 weights only (the caller falls back to per-call dequantisation)."""
+    if not weights or len(weights) > 8 or not all(isinstance(w, Nf4Tensors) for w in weights):
+        return None
+    lib = _lib.load()
+    dev = weights[0].packed.device
+    sizes = [(int(lib.vpt_linear_scratch_bytes(w.shape[0], w.shape[1])) + 255) // 256 * 256 for w in weights]
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, bool(transposed))
+    arena = _ARENA.get(key)
+    if arena is None or arena.numel() < sum(sizes):
+        arena = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+        _ARENA[key] = arena
+    arr = (DequantItemC * len(weights))()
+    slots, off = [], 0
+    for it, w, d, u, sz in zip(arr, weights, downs, ups, sizes):
+        slot = arena[off:off + sz]
+        off += sz
+        slots.append(slot)
+        it.w = w.c_struct()
+        it.w_scratch = slot.data_ptr()
+        it.scratch_bytes = sz
+        if transposed and d is not None:
+            it.lora_down, it.ld_lora_down, it.lora_up = d.data_ptr(), d.stride(0), u.data_ptr()
+    _lib.call("vpt_nf4_dequant_batch", arr, len(weights), int(transposed), _stream())
+    return slots
 
 
 # bench.py sets this to a list to bracket every fused-linear launch with CUDA events on the launching stream
@@ -167,25 +199,29 @@ def _pad_rank(down: torch.Tensor | None, up: torch.Tensor | None):
 
 
 def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, scale: float, residual=None,
-               want_side: bool = False, backward: bool = False, tile_n: int = 0, reuse_scratch: bool = False):
+               want_side: bool = False, backward: bool = False, tile_n: int = 0, reuse_scratch: bool = False,
+               scratch: torch.Tensor | None = None):
     """One call of the fused linear.  forward: x2 [M,K] -> y [M,N]; backward: x2 = dy [M,N] -> dx [M,K].
     `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None).
     reuse_scratch: the previous call on this stream used the same weight and direction, so the dequantised copy in the
-    workspace is still valid and the dequantisation kernel is skipped."""
+    workspace is still valid and the dequantisation kernel is skipped.  scratch: a slot filled by dequant_block for this
+    weight and direction (implies reuse)."""
     _need_cuda(x2)
     if x2.dtype != torch.bfloat16:
         raise TypeError("fused linear runs in bfloat16")
     args = LinearArgsC()
     M = x2.shape[0]
-    scratch = None
+    prefilled = scratch is not None
+    if prefilled:
+        reuse_scratch = True
     if isinstance(w, Nf4Tensors):
         N, K = w.shape
-        use_scratch = NF4_GEMM_MODE == "scratch" or (NF4_GEMM_MODE == "auto" and M >= NF4_SCRATCH_MIN_M)
+        use_scratch = prefilled or NF4_GEMM_MODE == "scratch" or (NF4_GEMM_MODE == "auto" and M >= NF4_SCRATCH_MIN_M)
         args.w = w.c_struct(for_gemm=not use_scratch)
         args.w_bf16 = None
         if use_scratch:
-            need = int(_lib.load().vpt_linear_scratch_bytes(N, K))
-            scratch = _weight_scratch(x2.device, need)
+            if not prefilled:
+                scratch = _weight_scratch(x2.device, int(_lib.load().vpt_linear_scratch_bytes(N, K)))
             args.w_scratch = _p(scratch)
             args.ld_scratch = (K + 7) // 8 * 8
             args.scratch_bytes = scratch.numel()
