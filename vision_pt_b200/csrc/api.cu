@@ -112,8 +112,7 @@ extern "C" int vpt_nf4_dequant_batch(const vpt_nf4_dequant_item* items, int32_t 
     ctas += d.num_tiles + (lora ? 4 : 0);
   }
   bp.n_items = n_items;
-  nf4_dequant_batch_kernel<<<ctas, 256, 0, S(stream)>>>(bp);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(nf4_dequant_batch_kernel, dim3(ctas), dim3(256), 0, S(stream), bp));
   return 0;
 }
 
@@ -261,8 +260,7 @@ extern "C" int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, 
 extern "C" int vpt_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int64_t rows, int32_t D, int64_t ldx,
                                int64_t ldy, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(x && y && rows > 0 && D > 0 && D % 8 == 0 && D <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_rmsnorm_fwd: bad arguments");
-  rmsnorm_fwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(w), BFM(y), rstd_out, rows, D, ldx, ldy, eps);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(rmsnorm_fwd_kernel, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(x), BF(w), BFM(y), rstd_out, static_cast<long>(rows), D, static_cast<long>(ldx), static_cast<long>(ldy), eps));
   return 0;
 }
 extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
@@ -270,7 +268,7 @@ extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
   VPT_REQUIRE(dy && x && dx && rows > 0 && D % 8 == 0 && D <= 2048 && ld % 8 == 0, "vpt_rmsnorm_bwd: bad arguments");
   const unsigned grid = blocks_for(rows, kEwThreads / 32, 1L << 30);
   const int nch = (D / 8 + 31) / 32;
-#define VPT_RMS_BWD(CH) rmsnorm_bwd_kernel<CH><<<grid, kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(w), rstd, BF(dres), BFM(dx), dw, rows, D, ld, eps)
+#define VPT_RMS_BWD(CH) VPT_CUDA_OK(launch_pdl(rmsnorm_bwd_kernel<CH>, dim3(grid), dim3(kEwThreads), 0, S(stream), BF(dy), BF(x), BF(w), rstd, BF(dres), BFM(dx), dw, static_cast<long>(rows), D, static_cast<long>(ld), eps))
   if (nch <= 1) VPT_RMS_BWD(1);
   else if (nch <= 3) VPT_RMS_BWD(3);
   else if (nch <= 4) VPT_RMS_BWD(4);
@@ -283,8 +281,7 @@ extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
 extern "C" int vpt_qknorm_rope_fwd(const void* x, const void* w, const float* cos_sin, void* y, int64_t tokens, int32_t H,
                                    int32_t L, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(x && w && cos_sin && y && tokens > 0 && H > 0 && L > 0 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_qknorm_rope_fwd: bad arguments");
-  qknorm_rope_fwd_kernel<<<blocks_for(tokens * H * 8, 256, 1L << 30), 256, 0, S(stream)>>>(BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(qknorm_rope_fwd_kernel, dim3(blocks_for(tokens * H * 8, 256, 1L << 30)), dim3(256), 0, S(stream), BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps));
   return 0;
 }
 extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void* x, const void* w, const float* cos_sin,
@@ -293,10 +290,9 @@ extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void
   VPT_REQUIRE(dy && x && w && cos_sin && dx && tokens > 0 && H > 0 && L > 0, "vpt_qknorm_rope_bwd: bad arguments");
   const unsigned grid = blocks_for(tokens * H * 8, 256, 1L << 30);
   if (dy_is_f32)
-    qknorm_rope_bwd_kernel<true><<<grid, 256, 0, S(stream)>>>(dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps);
+    VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<true>, dim3(grid), dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps));
   else
-    qknorm_rope_bwd_kernel<false><<<grid, 256, 0, S(stream)>>>(dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps);
-  VPT_CUDA_OK(cudaGetLastError());
+    VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<false>, dim3(grid), dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps));
   return 0;
 }
 extern "C" int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t rows, int32_t F, int64_t ldg, int64_t ldu,
@@ -304,8 +300,7 @@ extern "C" int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t row
   const int64_t f8 = (F + 7) / 8 * 8;
   VPT_REQUIRE(g && u && a && rows > 0 && F > 0 && ldg % 8 == 0 && ldu % 8 == 0 && lda % 8 == 0 && ldg >= f8 && ldu >= f8 && lda >= f8,
               "vpt_swiglu_fwd: bad arguments (row pitches must be multiples of 8 and cover F rounded up to 8)");
-  swiglu_fwd_kernel<<<blocks_for(rows * (f8 / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(g), BF(u), BFM(a), rows, F, ldg, ldu, lda);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(swiglu_fwd_kernel, dim3(blocks_for(rows * (f8 / 8), 256, 148 * 32)), dim3(256), 0, S(stream), BF(g), BF(u), BFM(a), rows, F, ldg, ldu, lda));
   return 0;
 }
 extern "C" int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void* dg, void* du, int64_t rows, int32_t F,
@@ -314,8 +309,7 @@ extern "C" int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void
   VPT_REQUIRE(da && g && u && dg && du && rows > 0 && F > 0 && ldda >= f8 && ldg >= f8 && ldu >= f8 && lddg >= f8 && lddu >= f8 &&
                   (ldda | ldg | ldu | lddg | lddu) % 8 == 0,
               "vpt_swiglu_bwd: bad arguments");
-  swiglu_bwd_kernel<<<blocks_for(rows * (f8 / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(da), BF(g), BF(u), BFM(dg), BFM(du), rows, F, ldda, ldg, ldu, lddg, lddu);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(swiglu_bwd_kernel, dim3(blocks_for(rows * (f8 / 8), 256, 148 * 32)), dim3(256), 0, S(stream), BF(da), BF(g), BF(u), BFM(dg), BFM(du), rows, F, ldda, ldg, ldu, lddg, lddu));
   return 0;
 }
 extern "C" int vpt_ln_modulate_fwd(const void* x, const void* scale, const void* shift, void* y, float* mean, float* rstd,

@@ -54,6 +54,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
+  pdl_wait();                                    // seqlens_k may come from the kernel just before
   int klen = p.seqlens_k ? p.seqlens_k[b] : p.Lk;
   klen = klen < p.Lk ? klen : p.Lk;
   const int nblk = (klen + kAttnTile - 1) / kAttnTile;
@@ -75,6 +76,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -248,6 +251,8 @@ struct AttnDeltaParams {
   float* delta;                // [B, H, Lq_pad]
 };
 __global__ void attn_bwd_delta_kernel(const AttnDeltaParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one 8-lane group per (b, h, q): 8 lanes x 8 elements = 64
   const long gid = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;

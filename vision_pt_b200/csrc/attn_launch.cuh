@@ -40,8 +40,7 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
     attr = true;
   }
   dim3 grid((Lq + kAttnTile - 1) / kAttnTile, H, B);
-  attn_fwd_kernel<<<grid, 192, AttnFwdSmem::kTotal, stream>>>(tq, tk, tv, p);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, grid, dim3(192), AttnFwdSmem::kTotal, stream, tq, tk, tv, p));
   return 0;
 }
 
@@ -64,8 +63,7 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   dp.Lq_pad = (Lq + kAttnTile - 1) / kAttnTile * kAttnTile;
   dp.scale = scale;
   const long groups = static_cast<long>(B) * H * dp.Lq_pad;
-  attn_bwd_delta_kernel<<<static_cast<unsigned>((groups * 8 + 255) / 256), 256, 0, stream>>>(dp);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(attn_bwd_delta_kernel, dim3(static_cast<unsigned>((groups * 8 + 255) / 256)), dim3(256), 0, stream, dp));
 
   CUtensorMap tdq;
   {
@@ -94,8 +92,7 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
     attr = true;
   }
   const int ctas = p.num_items < sm_count() ? p.num_items : sm_count();
-  attn_bwd2_kernel<<<ctas, 512, AttnBwd2Smem::kTotal, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(attn_bwd2_kernel, dim3(ctas), dim3(512), AttnBwd2Smem::kTotal, stream, tq, tk, tv, tdo, tdq, tdk, tdv, p));
   return 0;
 }
 

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sm100.cuh"
+
 namespace vpt {
 
 __device__ __forceinline__ float ew_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -51,6 +53,8 @@ constexpr int kEwThreads = 256;   // 8 rows per CTA
 __global__ void __launch_bounds__(kEwThreads)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
                    float* __restrict__ rstd_out, long rows, int D, long ldx, long ldy, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -99,6 +103,8 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
                    const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
                    long rows, int D, long ld, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   const int nch = D >> 3;
@@ -162,6 +168,8 @@ __global__ void __launch_bounds__(256)
 qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ cs /* [L, 32, 2] */, __nv_bfloat16* __restrict__ y, long tokens, int H,
                        int L, long ldx, long ldy, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
   const bool live = g < tokens * H;
@@ -201,6 +209,8 @@ __global__ void __launch_bounds__(256)
 qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ cs, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, long tokens,
                        int H, int L, long lddy, long ldx, long lddx, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
   const bool live = g < tokens * H;
@@ -256,6 +266,8 @@ qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ a,
                   long rows, int F, long ldg, long ldu, long lda) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nch = (F + 7) >> 3;
   const long total = rows * nch;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -274,6 +286,8 @@ __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ u,
                   __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ du, long rows, int F, long ldda, long ldg,
                   long ldu, long lddg, long lddu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nch = (F + 7) >> 3;
   const long total = rows * nch;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {

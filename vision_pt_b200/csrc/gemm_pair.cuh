@@ -132,6 +132,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();                           // the peer's barriers exist before anything remote touches them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                                   // set-up above overlapped the previous kernel; its data is visible now
 
   if (warp == 0) {
     // ============================================================ TMA producer (both CTAs)

@@ -55,8 +55,7 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
   int pairs = p.num_m_pairs * p.num_n_tiles;
   const int cap = sm_count() / 2;
   if (pairs > cap) pairs = cap;
-  kern<<<2 * pairs, kPairThreads, S::kTotal, stream>>>(tmA, tmB0, tmB1, tmP, tmD, tmR, p);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(kPairThreads), S::kTotal, stream, tmA, tmB0, tmB1, tmP, tmD, tmR, p));
   return 0;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -131,6 +132,24 @@ inline int make_tmap_f32_4d(CUtensorMap* out, const void* base, const uint64_t d
     return fail("cuTensorMapEncodeTiled(4d f32)", buf);
   }
   return 0;
+}
+
+// Launch with programmatic stream serialisation (see pdl_wait / pdl_launch_dependents in sm100.cuh).  VPT_NO_PDL=1 in the
+// environment turns the attribute off (A/B measurements).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool enabled = getenv("VPT_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 inline int sm_count() {

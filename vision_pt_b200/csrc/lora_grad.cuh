@@ -79,6 +79,8 @@ lora_grad_kernel(const __grid_constant__ LoraGradBatch bp) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -199,8 +201,7 @@ inline int launch_lora_grad_batch(const LoraGradDesc* d, int n, cudaStream_t str
     VPT_CUDA_OK(cudaFuncSetAttribute(lora_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LoraGradSmem::kTotal));
     attr = true;
   }
-  lora_grad_kernel<<<ctas, 256, LoraGradSmem::kTotal, stream>>>(bp);
-  VPT_CUDA_OK(cudaGetLastError());
+  VPT_CUDA_OK(launch_pdl(lora_grad_kernel, dim3(ctas), dim3(256), LoraGradSmem::kTotal, stream, bp));
   return 0;
 }
 

@@ -234,6 +234,8 @@ struct DequantBatch {
 
 __global__ void __launch_bounds__(256)
 nf4_dequant_batch_kernel(const __grid_constant__ DequantBatch bp) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int ii = 0;
   while (ii + 1 < bp.n_items && static_cast<int>(blockIdx.x) >= bp.items[ii + 1].cta_begin) ++ii;
   const DequantItem& d = bp.items[ii];

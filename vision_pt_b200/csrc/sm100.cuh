@@ -22,6 +22,13 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// Programmatic dependent launch: a kernel launched with the attribute may start while its predecessor on the stream is
+// still draining.  `pdl_launch_dependents` lets the successor's CTAs take SMs as this grid's CTAs retire (its barrier /
+// TMEM / descriptor set-up then overlaps our tail); `pdl_wait` blocks until every predecessor grid has completed and its
+// memory is visible -- every global access of a kernel sits behind it.  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a converged warp.  tcgen05 / TMA instructions take their operands from uniform registers: issued under
 // `if (lane == 0)` every operand is first moved there lane by lane (ELECT + R2UR.BROADCAST, ~35 SASS instructions per
 // MMA, which made the single issuing thread the bottleneck: profiles/r1e_attn_bwd.txt); issued by a converged warp under
