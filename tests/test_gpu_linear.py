@@ -139,3 +139,28 @@ def test_residual_and_linearity(mode, monkeypatch):
     y2 = ops.nf4_lora_linear(x * 2, *args)
     b = layer.linear.bias.float()
     assert rel_err(y2.float() - b, 2 * (y.float() - b)) <= 1e-2
+
+
+@pytest.mark.parametrize("K,N,bias", [(640, 640, False), (640, 640, True), (2048, 640, False), (640, 5120, True), (2560, 640, True),
+                                      (1280, 1280, False), (2048, 1280, False), (1280, 10240, True), (5120, 1280, True)])
+@pytest.mark.parametrize("rank", [4, 16])
+def test_sdxl_transformer_block_linears(K, N, bias, rank):
+    """BASELINE.json configs[4] / SURVEY 8a12: the NF4 + LoRA linears of an SDXL TransformerBlock (attn1.to_q/k/v and attn2.to_q
+    without bias, attn2.to_k/v from the 2048-wide context, to_out.0 with bias, GEGLU ff.net.0.proj D -> 8D, ff.net.2 4D -> D;
+    src/models/sdxl/denoiser.py:32-207) at D = 640 and 1280, LoRA ranks 4 and 16 (configs/sdxl/*.yml)."""
+    M = 1024 + 77
+    layer, w_ref, x = _make(M, K, N, rank, True, bias=bias, seed=K + N)
+    xg = x.cuda().requires_grad_(True)
+    y = layer(xg)
+    dy = torch.randn(M, N).to(torch.bfloat16)
+    y.backward(dy.cuda())
+    xr = x.clone().float().requires_grad_(True)
+    down = layer.lora_down.weight.detach().cpu().float().requires_grad_(True)
+    up = layer.lora_up.weight.detach().cpu().float().requires_grad_(True)
+    b = layer.linear.bias.detach().cpu().float() if bias else None
+    yr = oj.lora_linear(xr, oj.dense_weight(w_ref).float(), b, down, up, alpha=2.0)
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= TOL
+    assert rel_err(xg.grad, xr.grad) <= TOL
+    assert rel_err(layer.lora_down.weight.grad, down.grad) <= TOL
+    assert rel_err(layer.lora_up.weight.grad, up.grad) <= TOL

@@ -1,3 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-250
-VPT_NO_PDL=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-250
+timeout 600 python -m pytest tests/test_gpu_linear.py -x -q -k sdxl 2>&1 | tail -5
