@@ -9,7 +9,7 @@
 // two directions are the same kernel.
 //
 // Why pairs: with one CTA per 128x192 tile the main loop pulls 104 B per SM-cycle out of L2 and measured 49 % tensor-pipe
-// activity at 48 % L2 throughput (profiles/r1b_gemm_1cta.txt).  A pair computes a 256 x BN tile: each CTA loads its own 128
+// activity at 48 % L2 throughput (profiles/r1_gemm_1cta_ncu.txt).  A pair computes a 256 x BN tile: each CTA loads its own 128
 // rows of A and HALF of the B rows; the tensor cores of both SMs read both halves.  L2 bytes per FLOP drop by 1.45x.
 //
 // Per CTA, 8 warps: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) + TMEM allocator, warps 4-7 epilogue
