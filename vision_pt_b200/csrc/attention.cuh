@@ -5,8 +5,7 @@
 // q/k/v/o are addressed as 4-D tensors (hd, L, H, B) with arbitrary strides for L, H, B (hd contiguous), so both the
 // reference's [B,H,L,hd] layout and the token-major [B,L,H,hd] layout the fused block uses are accepted without copies.
 //
-// Forward: CTA = (128-query tile, head, sample).  S = Q K^T lives in TMEM (128 cols), one softmax thread per query
-// row, P is written as a bf16 A-operand tile in shared memory, O accumulates in TMEM (64 cols) with online rescale.
+// Forward: attn_fwd_kernel below.
 // Backward: attention_bwd.cuh.
 #pragma once
 #include "sm100.cuh"
@@ -29,14 +28,23 @@ struct AttnFwdSmem {
   static constexpr int kQ = 0;
   static constexpr int kK = 16384;            // 2 stages
   static constexpr int kV = kK + 2 * 16384;   // 2 stages
-  static constexpr int kP = kV + 2 * 16384;   // 2 K-atoms of [128 x 64]
+  static constexpr int kP = kV + 2 * 16384;   // P_A, P_B: [128 queries x 64 keys] bf16 each
+  static constexpr int kStat = kP;            // (m, l) of both streams per query row, [2][128] float2: reuses P at the end
   static constexpr int kBars = kP + 32768;
-  static constexpr int kNumBars = 8;
+  static constexpr int kNumBars = 13;         // q_full q_empty kv_full[2] kv_empty[2] s_full[2] p_full[2] pv_done[2] o_free
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemSlot + 16;   // no alignment slack: two CTAs must fit in one SM's 228 KB
 };
 
-__global__ void __launch_bounds__(192, 2)
+// Persistent CTAs (one per SM) walk work items (128-query tile, head, sample).  Every 128-key block is split into two
+// 64-key halves A and B, each an independent online-softmax stream with its own warpgroup, running maximum, row sum and O
+// accumulator (S_A, S_B, O_A, O_B: 64 TMEM columns each); the tensor core ping-pongs between the streams, and the two
+// partial results are merged at the end of the item (O = (O_A w_A + O_B w_B) / (l_A w_A + l_B w_B)).  A stream rescales
+// its accumulator only when its maximum grows by more than 2^8 (P stays <= 256: exact in the fp32 sums, safe in bf16).
+// Sequences here are short (330 tokens = 2.6 key blocks per item), so the loop over items matters: the next item's Q / K / V
+// are already in flight while the current one finishes, instead of one CTA launch + pipeline fill per 2.6 blocks.
+// Warps: 0 TMA producer, 1 MMA issuer + TMEM allocator, 2-5 stream A, 6-9 stream B.
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   using S = AttnFwdSmem;
@@ -45,29 +53,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need a 1024B-aligned base
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [2]
+  uint64_t* kv_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;     // [2] A, B
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* pv_done = bars + 10;   // [2]
+  uint64_t* o_free = bars + 12;    // the merge has read O_A / O_B: the next item may overwrite them
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+  float2* s_stat = reinterpret_cast<float2*>(smem + S::kStat);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
-  pdl_wait();                                    // seqlens_k may come from the kernel just before
-  int klen = p.seqlens_k ? p.seqlens_k[b] : p.Lk;
-  klen = klen < p.Lk ? klen : p.Lk;
-  const int nblk = (klen + kAttnTile - 1) / kAttnTile;
+  const int nqt = (p.Lq + kAttnTile - 1) / kAttnTile;
+  const int num_items = nqt * p.H * p.B;
+  auto klen_of = [&](int item) {
+    if (item >= num_items) return 0;
+    if (p.seqlens_k == nullptr) return p.Lk;
+    const int kl = __ldg(p.seqlens_k + item / (nqt * p.H));
+    return kl < p.Lk ? kl : p.Lk;
+  };
+  // keys of block j that stream X covers, rounded up to the UMMA granularity (0 = none)
+  auto sub_n = [](int klen, int j, int X) {
+    const int valid = min(128, klen - j * 128) - X * 64;
+    return valid <= 0 ? 0 : min(64, (valid + 15) & ~15);
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(o_free, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
@@ -75,7 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;   // S_A 0, S_B 64, O_A 128, O_B 192
   pdl_launch_dependents();
   pdl_wait();
 
@@ -84,154 +105,226 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      mbar_arrive_expect_tx(q_full, 16384);
-      tma_load_4d(&tmQ, q_full, smem + S::kQ, 0, q0, h, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 32768);
-        tma_load_4d(&tmK, &kv_full[s], smem + S::kK + s * 16384, 0, j * kAttnTile, h, b);
-        tma_load_4d(&tmV, &kv_full[s], smem + S::kV + s * 16384, 0, j * kAttnTile, h, b);
+      uint32_t jj = 0, itn = 0;
+      int klen = klen_of(blockIdx.x);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn) {
+        const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
+        const int nblk = (klen + kAttnTile - 1) / kAttnTile;
+        klen = klen_of(item + gridDim.x);
+        mbar_wait(q_empty, (itn & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, 16384);
+        tma_load_4d(&tmQ, q_full, smem + S::kQ, 0, qt * kAttnTile, h, b);
+        for (int j = 0; j < nblk; ++j, ++jj) {
+          const uint32_t s = jj & 1;
+          mbar_wait(&kv_empty[s], ((jj >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 32768);
+          tma_load_4d(&tmK, &kv_full[s], smem + S::kK + s * 16384, 0, j * kAttnTile, h, b);
+          tma_load_4d(&tmV, &kv_full[s], smem + S::kV + s * 16384, 0, j * kAttnTile, h, b);
+        }
       }
     }
   } else if (warp == 1) {
     // converged warp, one elected lane issues (operands stay in uniform registers)
-    constexpr uint32_t kIdS = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T   (both K-major)
-    constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O += P V    (V is MN-major)
+    constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O_X += P_X V_X  (V is MN-major)
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
     const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);
-    const uint64_t qd = dK_ + ((smem_base + S::kQ) >> 4), pd = dK_ + ((smem_base + S::kP) >> 4);
-    mbar_wait(q_full, 0);
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      const uint64_t kd = dK_ + ((smem_base + S::kK + s * 16384) >> 4), vd = dMN + ((smem_base + S::kV + s * 16384) >> 4);
-      mbar_wait(&kv_full[s], (j >> 1) & 1);
-      tc_fence_after_sync();
-      if (elect_one_sync()) {
+    const uint64_t qd = dK_ + ((smem_base + S::kQ) >> 4);
+    uint32_t jj = 0, itn = 0;
+    uint32_t cnt[2] = {0, 0};
+    int klen = klen_of(blockIdx.x);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn) {
+      const int nblk = (klen + kAttnTile - 1) / kAttnTile;
+      const int kl = klen;
+      klen = klen_of(item + gridDim.x);
+      auto issue_s = [&](int j, uint32_t s, uint32_t sp, int X) {     // S_X = Q K_X^T
+        const int n = sub_n(kl, j, X);
+        if (n == 0) return;
+        mbar_wait(&kv_full[s], sp);
+        tc_fence_after_sync();
+        const uint64_t kd = dK_ + ((smem_base + S::kK + s * 16384 + X * 8192) >> 4);
+        const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, kIdS, k != 0);
-        umma_commit(s_full);
+          for (int k = 0; k < 4; ++k) umma_ss(tS + X * 64, qd + 2 * k, kd + 2 * k, idesc, k != 0);
+          umma_commit(&s_full[X]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, itn & 1);
+      if (nblk > 0) {
+        issue_s(0, jj & 1, (jj >> 1) & 1, 0);
+        issue_s(0, jj & 1, (jj >> 1) & 1, 1);
       }
-      __syncwarp();
-      mbar_wait(p_full, j & 1);
-      tc_fence_after_sync();
-      if (elect_one_sync()) {
+      if (nblk <= 1) {                             // every S MMA of this item is issued: Q may be replaced
+        if (elect_one_sync()) umma_commit(q_empty);
+        __syncwarp();
+      }
+      bool first[2] = {true, true};
+      for (int j = 0; j < nblk; ++j, ++jj) {
+        const uint32_t s = jj & 1;
+        const uint64_t vd = dMN + ((smem_base + S::kV + s * 16384) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_ss(tO, pd + (k >> 2) * 1024 + (k & 3) * 2, vd + k * 128, kIdO, (j | k) != 0);
-        umma_commit(&kv_empty[s]);
-        umma_commit(o_full);
+        for (int X = 0; X < 2; ++X) {
+          const int n = sub_n(kl, j, X);
+          if (n > 0) {
+            mbar_wait(&p_full[X], cnt[X] & 1);
+            ++cnt[X];
+            if (first[X] && itn > 0 && X == 0) mbar_wait(o_free, (itn - 1) & 1);   // previous item's merge has read O
+            tc_fence_after_sync();
+            const uint64_t pd = dK_ + ((smem_base + S::kP + X * 16384) >> 4);
+            const uint32_t acc0 = first[X] ? 0u : 1u;
+            first[X] = false;
+            if (elect_one_sync()) {
+              for (int k = 0; k < n / 16; ++k) umma_ss(tO + X * 64, pd + 2 * k, vd + (X * 4 + k) * 128, kIdO, acc0 | (k != 0));
+              umma_commit(&pv_done[X]);
+            }
+            __syncwarp();
+          }
+          if (X == 1) {
+            if (elect_one_sync()) umma_commit(&kv_empty[s]);
+            __syncwarp();
+          }
+          if (j + 1 < nblk) {
+            issue_s(j + 1, (jj + 1) & 1, ((jj + 1) >> 1) & 1, X);    // the other stream's softmax runs meanwhile
+            if (X == 1 && j + 2 == nblk) {
+              if (elect_one_sync()) umma_commit(q_empty);
+              __syncwarp();
+            }
+          }
+        }
       }
-      __syncwarp();
     }
   } else {
-    // softmax warps 2..5: TMEM lane quarter = warp % 4
-    const int qd = warp & 3;
+    // ============================================================ softmax streams: A = warps 2-5, B = warps 6-9
+    const int X = (warp - 2) >> 2;
+    const int qd = warp & 3;                      // TMEM lane quarter
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t p_row = smem_u32(smem + S::kP) + row * 128;
+    const uint32_t p_row = smem_u32(smem + S::kP) + X * 16384 + row * 128;
     const int rin = row & 7;
-    float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after_sync();
-      const int kbase = j * kAttnTile;
-      // pass 1: block max (log2 domain)
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (kbase + c * 32 + i < klen) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-          mx = fmaxf(mx, s);
-        }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = fast_exp2(m_run - m_use);   // m_run = -inf -> 0
-      // P(j-1) must have been consumed, and O must be final for block j-1, before they are touched
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+    uint32_t cx = 0;
+    int klen_next = klen_of(blockIdx.x);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
+      const int klen = klen_next;
+      klen_next = klen_of(item + gridDim.x);
+      const int nblk = (klen + kAttnTile - 1) / kAttnTile;
+      float m_ref = -INFINITY, l_run = 0.f;
+      bool first = true;
+      for (int j = 0; j < nblk; ++j) {
+        const int n = sub_n(klen, j, X);
+        if (n == 0) continue;
+        mbar_wait(&s_full[X], cx & 1);
         tc_fence_after_sync();
-      }
-      // pass 2: p = exp2(s - m), row sum, bf16 P tile
-      float psum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
+        const int nvalid = min(64, klen - j * 128 - X * 64);     // < n only in the last block
+        uint32_t v[64];
+        tmem_ld32(tS + X * 64 + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        if (n > 32) tmem_ld32(tS + X * 64 + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_wait_ld();
-        uint32_t pk[16];
+        if (nvalid < 64) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int key = kbase + c * 32 + 2 * i;
-          const float p0 = key < klen ? fast_exp2(__uint_as_float(v[2 * i]) * p.scale_log2 - m_use) : 0.f;
-          const float p1 = key + 1 < klen ? fast_exp2(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_use) : 0.f;
-          psum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 64; ++i)
+            if (i >= nvalid) v[i] = 0xff800000u;   // -inf: padded / masked keys
         }
-        // keys c*32 .. c*32+31 -> K-atom c/2, 16B chunks (c%2)*4 .. +3 of this row
-        const uint32_t base = p_row + (c >> 1) * 16384;
+        float mx = -INFINITY;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + g) ^ rin);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * g]),
-                       "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        mx *= p.scale_log2;                         // scale > 0: the maximum commutes with the scaling
+        // lazy rescale: keep the reference maximum unless the true one outgrew it by 2^8
+        const bool grow = mx > m_ref + 8.f;
+        const float m_new = grow ? mx : m_ref;
+        if (cx > 0) {
+          // P_X of the previous block (possibly the previous item's) is consumed before it is overwritten, and O_X is
+          // final for it before it is rescaled
+          mbar_wait(&pv_done[X], (cx - 1) & 1);
+          tc_fence_after_sync();
+        }
+        if (!first && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_ref - m_new) : 1.f;
+          l_run *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + X * 64 + lane_off + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + X * 64 + lane_off + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+        first = false;
+        m_ref = m_new;
+        const float neg_m = -m_ref;
+        float psum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.scale_log2, neg_m));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.scale_log2, neg_m));
+            psum += p0 + p1;
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((g ^ rin) * 16)), "r"(pk[0]), "r"(pk[1]),
+                       "r"(pk[2]), "r"(pk[3])
                        : "memory");
         }
+        l_run += psum;
+        ++cx;
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(&p_full[X]);
       }
-      l_run = l_run * alpha + psum;
-      m_run = m_new;
-      if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tO + lane_off + c * 32, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tO + lane_off + c * 32, v);
-        }
-        tmem_wait_st();
+      // ---- merge the two streams
+      if (!first) {
+        mbar_wait(&pv_done[X], (cx - 1) & 1);
+        tc_fence_after_sync();
       }
-      fence_proxy_async_smem();
+      named_bar_sync(1, 256);                       // both streams' last P V MMA has read the P tiles: reuse them
+      s_stat[X * 128 + row] = make_float2(m_ref, l_run);
+      named_bar_sync(1, 256);
+      const float2 sa = s_stat[row], sb = s_stat[128 + row];
+      const float m = fmaxf(sa.x, sb.x);
+      const float wa = sa.y > 0.f ? fast_exp2(sa.x - m) : 0.f;     // a stream without keys has l = 0
+      const float wb = sb.y > 0.f ? fast_exp2(sb.x - m) : 0.f;
+      const float l = sa.y * wa + sb.y * wb;
+      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      const int q = qt * kAttnTile + row;
+      if (X == 0)   // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
+        p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
+            q < p.Lq ? (l > 0.f ? m + log2f(l) : -INFINITY) : INFINITY;
+      // stream X writes output columns X*32 .. X*32+31, reading that slice of both accumulators
+      const bool has_a = klen > 0, has_b = klen > 64;               // CTA-uniform: the .sync.aligned loads stay convergent
+      uint32_t oa[32], ob[32];
+      if (has_a) tmem_ld32(tO + lane_off + X * 32, oa);
+      if (has_b) tmem_ld32(tO + 64 + lane_off + X * 32, ob);
+      tmem_wait_ld();
       tc_fence_before_sync();
-      mbar_arrive(p_full);
-    }
-    // epilogue
-    if (nblk > 0) {
-      mbar_wait(o_full, (nblk - 1) & 1);
-      tc_fence_after_sync();
-    }
-    const int q = q0 + row;
-    const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
-    __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh;
-    // row pitch = Lq rounded up to 128 so that the backward can fetch a tile's 128 statistics with one bulk copy;
-    // padded queries get +inf (their recomputed probabilities are exp2(-inf) = 0)
-    p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(gridDim.x) * kAttnTile) + q] =
-        q < p.Lq ? ((l_run > 0.f) ? m_run + log2f(l_run) : -INFINITY) : INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      if (nblk > 0) {                       // CTA-uniform: the .sync.aligned TMEM load stays warp-convergent
-        tmem_ld32(tO + lane_off + c * 32, v);
-        tmem_wait_ld();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0;
-      }
+      named_bar_sync(1, 256);                       // the statistics are read too: the next item may write P again
+      if (lane == 0) mbar_arrive(o_free);
       if (q < p.Lq) {
+        __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh + X * 32;
+        const float fa = wa * inv_l, fb = wb * inv_l;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 o4;
-          o4.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
-          o4.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
-          o4.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
-          o4.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o4;
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = 0.f, x1 = 0.f;
+            if (has_a) {
+              x0 = __uint_as_float(oa[g * 8 + 2 * e]) * fa;
+              x1 = __uint_as_float(oa[g * 8 + 2 * e + 1]) * fa;
+            }
+            if (has_b) {
+              x0 = fmaf(__uint_as_float(ob[g * 8 + 2 * e]), fb, x0);
+              x1 = fmaf(__uint_as_float(ob[g * 8 + 2 * e + 1]), fb, x1);
+            }
+            w[e] = pack_bf16x2(x0, x1);
+          }
+          *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     }

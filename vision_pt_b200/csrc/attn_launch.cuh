@@ -39,8 +39,9 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
     VPT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
     attr = true;
   }
-  dim3 grid((Lq + kAttnTile - 1) / kAttnTile, H, B);
-  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, grid, dim3(192), AttnFwdSmem::kTotal, stream, tq, tk, tv, p));
+  const int items = ((Lq + kAttnTile - 1) / kAttnTile) * H * B;
+  const int slots = sm_count();
+  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(items < slots ? items : slots), dim3(320), AttnFwdSmem::kTotal, stream, tq, tk, tv, p));
   return 0;
 }
 
