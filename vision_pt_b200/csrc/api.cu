@@ -281,18 +281,26 @@ extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
 extern "C" int vpt_qknorm_rope_fwd(const void* x, const void* w, const float* cos_sin, void* y, int64_t tokens, int32_t H,
                                    int32_t L, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(x && w && cos_sin && y && tokens > 0 && H > 0 && L > 0 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_qknorm_rope_fwd: bad arguments");
-  VPT_CUDA_OK(launch_pdl(qknorm_rope_fwd_kernel, dim3(blocks_for(tokens * H * 8, 256, 1L << 30)), dim3(256), 0, S(stream), BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps));
+  const int hp = H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 1);
+  const dim3 grid(blocks_for(tokens * (H / hp) * 8, 256, 1L << 30));
+#define VPT_QK_FWD(HP) VPT_CUDA_OK(launch_pdl(qknorm_rope_fwd_kernel<HP>, grid, dim3(256), 0, S(stream), BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps))
+  if (hp == 4) VPT_QK_FWD(4); else if (hp == 2) VPT_QK_FWD(2); else VPT_QK_FWD(1);
+#undef VPT_QK_FWD
   return 0;
 }
 extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void* x, const void* w, const float* cos_sin,
                                    void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int64_t lddy, int64_t ldx,
                                    int64_t lddx, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && w && cos_sin && dx && tokens > 0 && H > 0 && L > 0, "vpt_qknorm_rope_bwd: bad arguments");
-  const unsigned grid = blocks_for(tokens * H * 8, 256, 1L << 30);
-  if (dy_is_f32)
-    VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<true>, dim3(grid), dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps));
-  else
-    VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<false>, dim3(grid), dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps));
+  const int hp = H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 1);
+  const dim3 grid(blocks_for(tokens * (H / hp) * 8, 256, 1L << 30));
+#define VPT_QK_BWD(F32, HP) VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<F32, HP>, grid, dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps))
+  if (dy_is_f32) {
+    if (hp == 4) VPT_QK_BWD(true, 4); else if (hp == 2) VPT_QK_BWD(true, 2); else VPT_QK_BWD(true, 1);
+  } else {
+    if (hp == 4) VPT_QK_BWD(false, 4); else if (hp == 2) VPT_QK_BWD(false, 2); else VPT_QK_BWD(false, 1);
+  }
+#undef VPT_QK_BWD
   return 0;
 }
 extern "C" int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t rows, int32_t F, int64_t ldg, int64_t ldu,
@@ -345,6 +353,21 @@ extern "C" int vpt_gate_residual_bwd(const void* dy, const void* h, const void* 
 static int patch_common(const void* src, void* dst, int B, int C, int H, int W, int p, int order, bool to_patches, cudaStream_t s) {
   VPT_REQUIRE(src && dst && B > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0 && (order == 0 || order == 1), "patchify: bad arguments");
   const long total = static_cast<long>(B) * C * H * W;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (p % 8 == 0 && C >= 1 && C <= 4 && aligned) {
+    const unsigned g = blocks_for(static_cast<long>(B) * H * (W / 8), 256, 148 * 32);
+    const uint16_t* s_ = static_cast<const uint16_t*>(src);
+    uint16_t* d_ = static_cast<uint16_t*>(dst);
+#define VPT_PATCH(TP, CC) patch_permute_vec_kernel<TP, CC><<<g, 256, 0, s>>>(s_, d_, B, H, W, p, order)
+    if (to_patches) {
+      if (C == 1) VPT_PATCH(true, 1); else if (C == 2) VPT_PATCH(true, 2); else if (C == 3) VPT_PATCH(true, 3); else VPT_PATCH(true, 4);
+    } else {
+      if (C == 1) VPT_PATCH(false, 1); else if (C == 2) VPT_PATCH(false, 2); else if (C == 3) VPT_PATCH(false, 3); else VPT_PATCH(false, 4);
+    }
+#undef VPT_PATCH
+    VPT_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const unsigned grid = blocks_for(total, 256, 148 * 64);
   if (to_patches)
     patch_permute_kernel<true><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), B, C, H, W, p, order);

@@ -163,100 +163,123 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 
 // ------------------------------------------------------------------------------------------- QK-norm + RoPE
 // x: [tokens = B*L, H, 64] (row pitch ld elements); per head: n = bf16(rmsnorm(x) * w); rotate interleaved pairs
-// (n[2i], n[2i+1]) by (cos, sin)[l, i]; l = token % L.  One 8-lane group per (token, head).
+// (n[2i], n[2i+1]) by (cos, sin)[l, i]; l = token % L.  One 8-lane group per (token, HP consecutive heads): the rotation
+// table and the norm weight are fetched once for the HP heads and their 16-byte loads are all in flight together.
+template <int HP>
 __global__ void __launch_bounds__(256)
 qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ cs /* [L, 32, 2] */, __nv_bfloat16* __restrict__ y, long tokens, int H,
                        int L, long ldx, long ldy, float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  const int hg = H / HP;
   const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
-  const bool live = g < tokens * H;
-  const long tok = live ? g / H : 0;
-  const int h = live ? static_cast<int>(g % H) : 0;
-  float f[8];
-  float ss = 0.f;
-  if (live) {
-    ew_unpack8(ld_stream(x + tok * ldx + h * 64 + sub * 8), f);
+  const bool live = g < tokens * hg;
+  const long tok = live ? g / hg : 0;
+  const int h0 = live ? static_cast<int>(g % hg) * HP : 0;
+  uint4 v[HP];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
-  }
-  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-  if (!live) return;
-  const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+  for (int j = 0; j < HP; ++j) v[j] = live ? ld_stream(x + tok * ldx + (h0 + j) * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
   float fw[8];
   ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
   const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
   const float4 t0 = t[0], t1 = t[1];
   const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
-  float o[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = ew_round((f[2 * i] * rstd) * fw[2 * i]);       // the reference rounds to bf16 between norm and rope
-    const float b = ew_round((f[2 * i + 1] * rstd) * fw[2 * i + 1]);
-    o[2 * i] = a * c[i] - b * s[i];
-    o[2 * i + 1] = a * s[i] + b * c[i];
+  for (int j = 0; j < HP; ++j) {
+    float f[8];
+    ew_unpack8(v[j], f);
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = ew_round((f[2 * i] * rstd) * fw[2 * i]);       // the reference rounds to bf16 between norm and rope
+      const float b = ew_round((f[2 * i + 1] * rstd) * fw[2 * i + 1]);
+      o[2 * i] = a * c[i] - b * s[i];
+      o[2 * i + 1] = a * s[i] + b * c[i];
+    }
+    if (live) st_stream(y + tok * ldy + (h0 + j) * 64 + sub * 8, ew_pack8(o));
   }
-  st_stream(y + tok * ldy + h * 64 + sub * 8, ew_pack8(o));
 }
 
 // dy is fp32 (the attention dQ accumulator) or bf16.  dn = R^T dy ; dx = rmsnorm_bwd(dn) with weight w.
-template <bool kDyF32>
+template <bool kDyF32, int HP>
 __global__ void __launch_bounds__(256)
 qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ cs, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, long tokens,
                        int H, int L, long lddy, long ldx, long lddx, float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  const int hg = H / HP;
   const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
-  const bool live = g < tokens * H;
-  const long tok = live ? g / H : 0;
-  const int h = live ? static_cast<int>(g % H) : 0;
-  float f[8], d[8], fw[8], dn[8];
-  float ss = 0.f, dot = 0.f;
-  if (live) {
-    ew_unpack8(ld_stream(x + tok * ldx + h * 64 + sub * 8), f);
-    if (kDyF32) {
-      const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + tok * lddy + h * 64 + sub * 8);
-      const float4 a = p[0], b = p[1];
-      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
-    } else {
-      ew_unpack8(ld_stream(static_cast<const __nv_bfloat16*>(dy_) + tok * lddy + h * 64 + sub * 8), d);
+  const bool live = g < tokens * hg;
+  const long tok = live ? g / hg : 0;
+  const int h0 = live ? static_cast<int>(g % hg) * HP : 0;
+  uint4 vx[HP];
+  float d[HP][8];
+#pragma unroll
+  for (int j = 0; j < HP; ++j) {
+    vx[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[j][e] = 0.f;
+    if (live) {
+      vx[j] = ld_stream(x + tok * ldx + (h0 + j) * 64 + sub * 8);
+      if (kDyF32) {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + tok * lddy + (h0 + j) * 64 + sub * 8);
+        const float4 a = p[0], b = p[1];
+        d[j][0] = a.x; d[j][1] = a.y; d[j][2] = a.z; d[j][3] = a.w; d[j][4] = b.x; d[j][5] = b.y; d[j][6] = b.z; d[j][7] = b.w;
+      } else {
+        ew_unpack8(ld_stream(static_cast<const __nv_bfloat16*>(dy_) + tok * lddy + (h0 + j) * 64 + sub * 8), d[j]);
+      }
     }
-    ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
-    const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
-    const float4 t0 = t[0], t1 = t[1];
-    const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+  }
+  float fw[8];
+  ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
+  const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
+  const float4 t0 = t[0], t1 = t[1];
+  const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+  float dwacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < HP; ++j) {
+    float f[8], dn[8];
+    ew_unpack8(vx[j], f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      dn[2 * i] = d[2 * i] * c[i] + d[2 * i + 1] * s[i];
-      dn[2 * i + 1] = -d[2 * i] * s[i] + d[2 * i + 1] * c[i];
+      dn[2 * i] = d[j][2 * i] * c[i] + d[j][2 * i + 1] * s[i];
+      dn[2 * i + 1] = -d[j][2 * i] * s[i] + d[j][2 * i + 1] * c[i];
     }
+    float ss = 0.f, dot = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       ss += f[e] * f[e];
       dot += dn[e] * fw[e] * f[e];
     }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+    const float coef = dot * rstd * rstd * rstd * (1.f / 64.f);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = dn[e] * fw[e] * rstd - f[e] * coef;
+      dwacc[e] += dn[e] * f[e] * rstd;
+    }
+    if (live) st_stream(dx + tok * lddx + (h0 + j) * 64 + sub * 8, ew_pack8(o));
   }
+  if (live && dw != nullptr) {
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  }
-  if (!live) return;
-  const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
-  const float coef = dot * rstd * rstd * rstd * (1.f / 64.f);
-  float o[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = dn[e] * fw[e] * rstd - f[e] * coef;
-  st_stream(dx + tok * lddx + h * 64 + sub * 8, ew_pack8(o));
-  if (dw != nullptr) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(dw + sub * 8 + e, dn[e] * f[e] * rstd);
+    for (int e = 0; e < 8; ++e) atomicAdd(dw + sub * 8 + e, dwacc[e]);
   }
 }
 
@@ -488,6 +511,69 @@ patch_permute_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ ds
     const long e = order == 0 ? (static_cast<long>(c) * p + py) * p + px : (static_cast<long>(py) * p + px) * C + c;
     const long j = (b * hp * wp + n) * (static_cast<long>(C) * p * p) + e;
     if (kToPatches) dst[j] = src[i]; else dst[i] = src[j];
+  }
+}
+
+// Vector form for p % 8 == 0 (the JiT / CogView patch sizes after packing) and C <= 4: one thread moves the 8 pixels x..x+7
+// of one image row for ALL channels -- C 16-byte accesses on the image side, and on the patch side either C separate
+// 16-byte runs (order 0: c outermost) or one contiguous 16*C-byte run with the channels interleaved (order 1: c innermost).
+template <bool kToPatches, int C>
+__global__ void __launch_bounds__(256)
+patch_permute_vec_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int B, int Himg, int Wimg, int p, int order) {
+  const int wp = Wimg / p, hp = Himg / p;
+  const int w8 = Wimg >> 3;
+  const long total = static_cast<long>(B) * Himg * w8;
+  const long plane = static_cast<long>(Himg) * Wimg;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w8) << 3;
+    const int yh = static_cast<int>((i / w8) % Himg);
+    const long b = i / (static_cast<long>(w8) * Himg);
+    const int py = yh % p, px = x % p;
+    const long n = static_cast<long>(yh / p) * wp + x / p;
+    const long pbase = (b * hp * wp + n) * (static_cast<long>(C) * p * p);
+    const long ibase = b * C * plane + static_cast<long>(yh) * Wimg + x;
+    const uint16_t* img_c = kToPatches ? src : dst;
+    uint16_t* img_m = const_cast<uint16_t*>(img_c);
+    const uint16_t* pat_c = kToPatches ? dst : src;
+    uint16_t* pat_m = const_cast<uint16_t*>(pat_c);
+    if (order == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const long pj = pbase + (static_cast<long>(c) * p + py) * p + px;
+        if (kToPatches) *reinterpret_cast<uint4*>(pat_m + pj) = ld_stream(img_c + ibase + c * plane);
+        else st_stream(img_m + ibase + c * plane, *reinterpret_cast<const uint4*>(pat_c + pj));
+      }
+    } else {
+      const long pj = pbase + (static_cast<long>(py) * p + px) * C;      // 8 pixels x C channels contiguous
+      uint16_t v[8 * C];
+      if (kToPatches) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const uint4 q = ld_stream(img_c + ibase + c * plane);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e * C + c] = static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1)));
+        }
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+          *reinterpret_cast<uint4*>(pat_m + pj + k * 8) =
+              make_uint4(v[k * 8 + 0] | (uint32_t(v[k * 8 + 1]) << 16), v[k * 8 + 2] | (uint32_t(v[k * 8 + 3]) << 16),
+                         v[k * 8 + 4] | (uint32_t(v[k * 8 + 5]) << 16), v[k * 8 + 6] | (uint32_t(v[k * 8 + 7]) << 16));
+      } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          const uint4 q = *reinterpret_cast<const uint4*>(pat_c + pj + k * 8);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[k * 8 + e] = static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1)));
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          st_stream(img_m + ibase + c * plane,
+                    make_uint4(v[0 * C + c] | (uint32_t(v[1 * C + c]) << 16), v[2 * C + c] | (uint32_t(v[3 * C + c]) << 16),
+                               v[4 * C + c] | (uint32_t(v[5 * C + c]) << 16), v[6 * C + c] | (uint32_t(v[7 * C + c]) << 16)));
+      }
+    }
   }
 }
 
