@@ -101,7 +101,7 @@ extern "C" int vpt_nf4_dequant_batch(const vpt_nf4_dequant_item* items, int32_t 
     d.out = static_cast<__nv_bfloat16*>(s.w_scratch);
     d.transposed = transposed ? 1 : 0;
     d.ld = transposed ? (N + 7) / 8 * 8 : (K + 7) / 8 * 8;
-    d.tiles_k = (K + 63) / 64;
+    d.tiles_k = (K + 255) / 256;                  // a CTA walks 4 consecutive 64-wide k-tiles of one 64-row band
     d.num_tiles = ((N + 63) / 64) * d.tiles_k;
     d.cta_begin = ctas;
     const bool lora = transposed && s.lora_down != nullptr;
@@ -292,13 +292,13 @@ extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void
                                    void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int64_t lddy, int64_t ldx,
                                    int64_t lddx, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && w && cos_sin && dx && tokens > 0 && H > 0 && L > 0, "vpt_qknorm_rope_bwd: bad arguments");
-  const int hp = H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 1);
+  const int hp = H % 2 == 0 ? 2 : 1;            // 4 heads per lane group cost occupancy here (measured slower)
   const dim3 grid(blocks_for(tokens * (H / hp) * 8, 256, 1L << 30));
 #define VPT_QK_BWD(F32, HP) VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<F32, HP>, grid, dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps))
   if (dy_is_f32) {
-    if (hp == 4) VPT_QK_BWD(true, 4); else if (hp == 2) VPT_QK_BWD(true, 2); else VPT_QK_BWD(true, 1);
+    if (hp == 2) VPT_QK_BWD(true, 2); else VPT_QK_BWD(true, 1);
   } else {
-    if (hp == 4) VPT_QK_BWD(false, 4); else if (hp == 2) VPT_QK_BWD(false, 2); else VPT_QK_BWD(false, 1);
+    if (hp == 2) VPT_QK_BWD(false, 2); else VPT_QK_BWD(false, 1);
   }
 #undef VPT_QK_BWD
   return 0;

@@ -264,8 +264,11 @@ nf4_dequant_batch_kernel(const __grid_constant__ DequantBatch bp) {
   if (threadIdx.x < 16) s_code[threadIdx.x] = d.code[threadIdx.x];
   s_ncode[threadIdx.x] = d.nested_code[threadIdx.x];
   __syncthreads();
-  const int n0 = (local / d.tiles_k) * 64, k0 = (local % d.tiles_k) * 64;
+  const int n0 = (local / d.tiles_k) * 64;
   const bool aligned = (K & 7) == 0;
+  for (int kt = 0; kt < 4; ++kt) {
+  const int k0 = (local % d.tiles_k) * 256 + kt * 64;
+  if (k0 >= K) break;
   for (int i = threadIdx.x; i < 512; i += 256) {
     const int r = i >> 3, g = i & 7;
     const int n = n0 + r, k = k0 + g * 8;
@@ -306,7 +309,7 @@ nf4_dequant_batch_kernel(const __grid_constant__ DequantBatch bp) {
       for (int e = 0; e < 8; ++e) tile[r][g * 8 + e] = v[e];
     }
   }
-  if (!d.transposed) return;
+  if (!d.transposed) continue;
   __syncthreads();
   for (int i = threadIdx.x; i < 512; i += 256) {
     const int kk = i >> 3, g = i & 7;
@@ -317,6 +320,8 @@ nf4_dequant_batch_kernel(const __grid_constant__ DequantBatch bp) {
     for (int e = 0; e < 4; ++e)
       o[e] = static_cast<uint32_t>(tile[g * 8 + 2 * e][kk]) | (static_cast<uint32_t>(tile[g * 8 + 2 * e + 1][kk]) << 16);
     *reinterpret_cast<uint4*>(d.out + static_cast<long>(k) * ld + n) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();                                  // the tile buffer is reused by the next k-tile
   }
 }
 
