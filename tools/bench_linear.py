@@ -98,6 +98,22 @@ for si, (K, N) in enumerate(shapes):
             tot = min(tot, e0.elapsed_time(e1))
         del keep, graph
         us = 1e3 * tot / args.iters
+        # vendor reference on the same shape: torch.matmul (cuBLAS) bf16, no LoRA / bias / residual, weight already dense
+        wden = torch.randn(cout, cin, device=dev).to(torch.bfloat16)
+        xs_c = [t.contiguous() for t in xs_]
+        g2 = torch.cuda.CUDAGraph()
+        for i in range(2):
+            torch.matmul(xs_c[i % nset], wden.t())
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g2):
+            keep2 = [torch.matmul(xs_c[i % nset], wden.t()) for i in range(args.iters)]
+        g2.replay(); torch.cuda.synchronize()
+        best2 = 1e30
+        for _ in range(3):
+            e0.record(); g2.replay(); e1.record(); torch.cuda.synchronize()
+            best2 = min(best2, e0.elapsed_time(e1))
+        us_cublas = 1e3 * best2 / args.iters
+        del keep2, g2
         fl = 2.0 * M * K * N + 2.0 * M * 16 * (K + N)
-        print(f"K={K:5d} N={N:5d} {'bwd' if bwd else 'fwd'} tile={args.tile:3d}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF   "
+        print(f"K={K:5d} N={N:5d} {'bwd' if bwd else 'fwd'} tile={args.tile:3d}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF   [cuBLAS plain GEMM {us_cublas:6.1f} us {2.0 * M * K * N / us_cublas / 1e6:7.1f} TF]  "
               f"rel err {err:.2e} side {serr if not args.no_check else float('nan'):.2e} tail {tail if not args.no_check else float('nan'):.2e}", flush=True)

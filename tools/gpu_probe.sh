@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-250
+timeout 200 python tools/bench_linear.py --model B --no-check --no-res 2>&1 | tail -6
+timeout 200 python tools/bench_linear.py --model L --no-check --no-res 2>&1 | tail -6

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvptb200.so")
+LIB_PATH = os.environ.get("VPT_LIB") or os.path.join(_HERE, "libvptb200.so")   # VPT_LIB: A/B builds of the same library
 
 VPT_BF16, VPT_F16, VPT_F32 = 0, 1, 2
 

@@ -1,88 +1,57 @@
-// LoRA GEMM on CTA pairs (tcgen05 cta_group::2): the large-M (training) route of the fused NF4-LoRA linear.
+// LoRA GEMM on clusters of FOUR CTAs = two CTA pairs (tcgen05 cta_group::2) that share the weight tile by TMA multicast.
+// Same math, warp roles and epilogue as gemm_pair.cuh (read that file first); what changes is the operand traffic:
 //
-//   D[M, NO] = A[M, R] * Bw[NO, R]^T + bias + Ts * Q[NO, 16]^T (+ residual),   Ts = bf16(scale * A * P[16, R]^T)
+//   pair p (ranks 2p, 2p+1) computes rows [512 q + 256 p, +256) of the SAME 192-column tile as the other pair, so both
+//   pairs need the same B rows.  B-half h (rank & 1) lands in the CTAs {h, h+2}: each of the two loads a part of it
+//   (56 + 48 rows, or 56 + 32 + the 16 LoRA rows) and multicasts it to both.  Per k-step an SM pulls 16 KB of A and
+//   6.5 KB of B out of L2 instead of 16 + 13 KB: 55 instead of 72 B per SM-cycle.  The pair kernel measured 60 % tensor-pipe
+//   activity at exactly the L2 rate that 72 B/cycle implies (and BN = 128, 89 B/cycle, was 1.24x slower: L2-bound).
 //
-// forward :  A = x,  Bw = dequantised weight [N, K],            P = lora_down [16, K],   Q = lora_up [N, 16]
-// backward:  A = dy, Bw = dequantised weight transposed [K, N], P = lora_up^T [16, N],   Q = lora_down^T [K, 16]
-// (src/modules/quant/bnb.py:37-129 + src/modules/peft/lora.py:92-104 of the reference and their autograd).  The weight
-// arrives as the bf16 workspace the NF4 dequantiser filled for this call (nf4.cuh), so every operand is K-major and the
-// two directions are the same kernel.
-//
-// Why pairs: with one CTA per 128x192 tile the main loop pulls 104 B per SM-cycle out of L2 and measured 49 % tensor-pipe
-// activity at 48 % L2 throughput (profiles/r1_gemm_1cta_ncu.txt).  A pair computes a 256 x BN tile: each CTA loads its own 128
-// rows of A and HALF of the B rows; the tensor cores of both SMs read both halves.  L2 bytes per FLOP drop by 1.45x.
-//
-// Per CTA, 8 warps: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) + TMEM allocator, warps 4-7 epilogue
-// (TMEM -> registers -> 128B-swizzled smem slabs -> TMA store).  Accumulators are double buffered in TMEM (2 x 256 columns);
-// the 16 LoRA columns ride in the same UMMA (N = BN + 16), the rank-16 update is one more K=16 UMMA issued while the next
-// tile's main loop is already running.
+// Plain (Hopper-style) TMA: every byte that lands in a CTA is credited to THAT CTA's local_full barrier; the follower of a
+// pair forwards "my stage is complete" to its leader with one remote arrive per stage (warp 2), and the MMA issuer waits
+// for its own and the follower's.  A stage is free again when BOTH pairs have consumed it: each leader's tcgen05.commit
+// multicasts to the empty barrier (count 2) of all four CTAs.
 #pragma once
-#include "sm100.cuh"
+#include "gemm_pair.cuh"
 
 namespace vpt {
 
-constexpr int kPairThreads = 256;
-constexpr int kPairEpiWarp0 = 4;
-constexpr int kPairRank = 16;
+constexpr int kQuadStagesMax = 6;
 
-struct PairParams {
-  int M, NO, R;
-  const __nv_bfloat16* bias;       // [NO] or nullptr
-  const __nv_bfloat16* residual;   // [M, NO] pitch ldr, or nullptr
-  int ldr;
-  const __nv_bfloat16* q_rows;     // [NO, 16] second-phase LoRA operand
-  float scale;
-  __nv_bfloat16* side;             // Ts^T [16, ld_side] or nullptr (the layout lora_grad reads by TMA)
-  long ld_side;
-  int num_m_pairs, num_n_tiles;
+// extra barriers of the quad kernel live after the pair kernel's: local_full[stages], peer_full[stages]
+template <int BN, bool kLoRA>
+struct QuadSmem : PairSmem<BN, kLoRA> {
+  using P = PairSmem<BN, kLoRA>;
+  static constexpr int kOffBars2 = P::kOffTmemSlot + 16;
+  static constexpr int kTotal = kOffBars2 + 2 * P::kStages * 8 + 1024;
 };
 
-template <int BN, bool kLoRA>
-struct PairSmem {
-  static constexpr int kNT = BN + (kLoRA ? kPairRank : 0);   // UMMA N
-  static constexpr int kNH = kNT / 2;                         // B rows held by each CTA
-  static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = (kNH * 128 + 1023) / 1024 * 1024;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSlabBytes = 32 * 128;                 // one warp's [32 rows x 64 cols] bf16 output slab
-#ifndef VPT_PAIR_SLABS
-#define VPT_PAIR_SLABS 4
-#endif
-#ifndef VPT_PAIR_MAX_STAGES
-#define VPT_PAIR_MAX_STAGES 6
-#endif
-  static constexpr int kSlabs = VPT_PAIR_SLABS;               // per epilogue warp (residual prefetch distance 2)
-  static constexpr int kOutBytes = 4 * kSlabs * kSlabBytes;
-  static constexpr int kTsBytes = 128 * 32;
-  static constexpr int kQBytes = (BN / 2) * 32;
-  static constexpr int kBiasBytes = BN * 4;
-  static constexpr int kFixed = kOutBytes + kTsBytes + kQBytes + kBiasBytes + 256 + 1024;
-  static constexpr int kStagesRaw = (227 * 1024 - kFixed) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > VPT_PAIR_MAX_STAGES ? VPT_PAIR_MAX_STAGES : kStagesRaw;
-  static constexpr int kOffOut = kStages * kStageBytes;
-  static constexpr int kOffTs = kOffOut + kOutBytes;
-  static constexpr int kOffQ = kOffTs + kTsBytes;
-  static constexpr int kOffBias = kOffQ + kQBytes;
-  static constexpr int kOffBars = kOffBias + kBiasBytes;
-  static constexpr int kNumBars = 2 * kStages + 7 + 4 * kSlabs;
-  static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
-  static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
-  static_assert(kStages >= 3, "pipeline too shallow");
-};
+// Multicast form of tma_load_2d: the tile lands at the same offset in every CTA of `mask` and each of them gets the
+// bytes credited to the barrier at `bar`'s offset in ITS OWN shared memory.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in the CTAs of `mask`
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 
-// tmA : A [M, R],           box {64, 128}
-// tmB0: Bw [NO, R],         box {64, kNH}            rows o0 .. o0 + kNH            (CTA 0)
-// tmB1: Bw [NO, R],         box {64, kNH - 16 | kNH} rows o0 + kNH .. o0 + BN       (CTA 1)
-// tmP : P [16, R],          box {64, 16}             appended below CTA 1's weight rows
-// tmD : D [M, NO],          box {64, 32}             (store)
-// tmR : residual [M, NO],   box {64, 32}             (prefetched into the output slabs)   all SWIZZLE_128B
+// tmA : A [M, R], box {64, 128};  tmB56 / tmB48 / tmB32: Bw [NO, R] with 56 / 48 / 32-row boxes;  tmP: P [16, R], box {64, 16};
+// tmD / tmR: D and residual [M, NO], box {64, 32}.  All SWIZZLE_128B.
 template <int BN, bool kLoRA>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
-                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmP,
-                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
-                 const PairParams p) {
-  using S = PairSmem<BN, kLoRA>;
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB56,
+                 const __grid_constant__ CUtensorMap tmB48, const __grid_constant__ CUtensorMap tmB32,
+                 const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmD,
+                 const __grid_constant__ CUtensorMap tmR, const PairParams p) {
+  using S = QuadSmem<BN, kLoRA>;
+  static_assert(BN == 192, "the row split of the multicast loads is written for BN = 192");
   static_assert(BN % 64 == 0 && BN >= 64 && S::kNT <= 256, "unsupported BN");
   constexpr int kStages = S::kStages;
   constexpr uint32_t kIdescMain = umma_idesc_bf16(256, S::kNT, 0, 0);
@@ -92,8 +61,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBars);
-  uint64_t* full = bars;                       // [kStages] leader's copy is the live one (count 2 + both CTAs' bytes)
-  uint64_t* empty = bars + kStages;            // [kStages] per CTA, arrived by the multicast commit
+  uint64_t* bars2 = reinterpret_cast<uint64_t*>(smem + S::kOffBars2);
+  uint64_t* local_full = bars2;                // [kStages] per CTA: every byte that lands in this CTA (A, both B parts)
+  uint64_t* peer_full = bars2 + kStages;       // [kStages] leader's: the follower's stage is complete (remote arrive)
+  uint64_t* empty = bars + kStages;            // [kStages] per CTA, count 2: both pairs' leaders commit to all four CTAs
   uint64_t* tmem_full = bars + 2 * kStages;    // [2] per CTA: main loop of a tile finished
   uint64_t* tmem_full2 = tmem_full + 2;        // [2] per CTA: rank-16 update finished
   uint64_t* tmem_empty = tmem_full2 + 2;       // [2] leader's: 8 epilogue warps (both CTAs) drained the buffer
@@ -105,16 +76,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-  const int num_tiles = p.num_m_pairs * p.num_n_tiles;
+  const uint32_t pair = rank >> 1, half = rank & 1;
+  const bool leader = half == 0;
+  const uint32_t leader_rank = rank & ~1u;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
+  const int cluster_id = blockIdx.x >> 2;
+  const int num_clusters = gridDim.x >> 2;
+  const int num_m_quads = (p.num_m_pairs + 1) / 2;
+  const int num_tiles = num_m_quads * p.num_n_tiles;
   const int ksteps = (p.R + 63) / 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 2);
-      mbar_init(&empty[s], 1);
+      mbar_init(&local_full[s], 1);
+      mbar_init(&peer_full[s], 1);
+      mbar_init(&empty[s], 2);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -127,8 +103,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(leader ? &tmB0 : &tmB1);
-    if (kLoRA && !leader) tma_prefetch_desc(&tmP);
+    tma_prefetch_desc(&tmB56);
+    tma_prefetch_desc(&tmB48);
+    if (kLoRA && !leader) {
+      tma_prefetch_desc(&tmB32);
+      tma_prefetch_desc(&tmP);
+    }
     tma_prefetch_desc(&tmD);
     if (p.residual != nullptr) tma_prefetch_desc(&tmR);
   }
@@ -142,28 +122,46 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_wait();                                   // set-up above overlapped the previous kernel; its data is visible now
 
   if (warp == 0) {
-    // ============================================================ TMA producer (both CTAs)
+    // ============================================================ TMA producer (all four CTAs)
     if (lane == 0) {
       uint32_t it = 0;
+      const uint16_t mc = static_cast<uint16_t>((1u << half) | (1u << (half + 2)));   // the two CTAs that hold B-half `half`
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128;
+        const int m0 = (tile / p.num_n_tiles) * 512 + static_cast<int>(pair) * 256 + static_cast<int>(half) * 128;
         const int o0 = (tile % p.num_n_tiles) * BN;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const int s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-          const uint32_t bar = mapa_shared(smem_u32(&full[s]), 0);
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);          // both pairs are done with this stage, in all four CTAs
           uint8_t* sa = smem + s * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if (leader) {
-            mbar_arrive_expect_tx(&full[s], 2 * kStageTx);
-            tma_load_2d_pair(&tmA, bar, sa, ks * 64, m0);
-            tma_load_2d_pair(&tmB0, bar, sb, ks * 64, o0);
+          mbar_arrive_expect_tx(&local_full[s], kStageTx);
+          tma_load_2d(&tmA, &local_full[s], sa, ks * 64, m0);
+          const int r0 = o0 + static_cast<int>(half) * S::kNH;     // first weight row of this B-half
+          if (kLoRA) {
+            // half 0: 104 weight rows = 56 (pair 0) + 48 (pair 1); half 1: 88 weight rows = 56 + 32, then the 16 LoRA rows
+            if (pair == 0) {
+              tma_load_2d_mc(&tmB56, &local_full[s], sb, ks * 64, r0, mc);
+            } else if (half == 0) {
+              tma_load_2d_mc(&tmB48, &local_full[s], sb + 56 * 128, ks * 64, r0 + 56, mc);
+            } else {
+              tma_load_2d_mc(&tmB32, &local_full[s], sb + 56 * 128, ks * 64, r0 + 56, mc);
+              tma_load_2d_mc(&tmP, &local_full[s], sb + 88 * 128, ks * 64, 0, mc);
+            }
           } else {
-            mbar_arrive_cluster(bar);
-            tma_load_2d_pair(&tmA, bar, sa, ks * 64, m0);
-            tma_load_2d_pair(&tmB1, bar, sb, ks * 64, o0 + S::kNH);
-            if (kLoRA) tma_load_2d_pair(&tmP, bar, sb + (S::kNH - kPairRank) * 128, ks * 64, 0);
+            tma_load_2d_mc(&tmB48, &local_full[s], sb + static_cast<int>(pair) * 48 * 128, ks * 64, r0 + static_cast<int>(pair) * 48, mc);
           }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ follower: forward "my stage landed" to the pair's leader
+    if (!leader && lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&local_full[s], (it / kStages) & 1);
+          mbar_arrive_cluster(mapa_shared(smem_u32(&peer_full[s]), leader_rank));
         }
       }
     }
@@ -181,7 +179,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after_sync();
         if (elect_one_sync()) {
           umma_ss_pair(tmem_base + pend_buf * 256, ts_desc, q_desc, kIdescLora, 1);
-          umma_commit_pair(&tmem_full2[pend_buf]);
+          umma_commit_mask(&tmem_full2[pend_buf], pair_mask);
         }
         __syncwarp();
         lora_pending = false;
@@ -194,7 +192,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           if (kLoRA && lora_pending && __all_sync(0xffffffffu, mbar_test_wait(ts_full, pend_parity))) issue_lora();
           const int s = it % kStages;
-          mbar_wait(&full[s], (it / kStages) & 1);
+          mbar_wait(&local_full[s], (it / kStages) & 1);
+          mbar_wait(&peer_full[s], (it / kStages) & 1);
           tc_fence_after_sync();
           const uint32_t sa = smem_base + s * S::kStageBytes;
           const uint64_t adesc = sw_desc + (sa >> 4);
@@ -202,7 +201,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdescMain, (ks | k) != 0);
-            umma_commit_pair(&empty[s]);
+            umma_commit_mask(&empty[s], 0xF);
           }
           __syncwarp();
         }
@@ -210,7 +209,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(ts_full, pend_parity);
           issue_lora();
         }
-        if (elect_one_sync()) umma_commit_pair(&tmem_full[buf]);
+        if (elect_one_sync()) umma_commit_mask(&tmem_full[buf], pair_mask);
         __syncwarp();
         if (kLoRA) {
           lora_pending = true;
@@ -228,7 +227,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp - kPairEpiWarp0;          // TMEM lane quarter == warp % 4
     const int row = q * 32 + lane;
     const int et = threadIdx.x - kPairEpiWarp0 * 32;
-    const uint32_t ts_bar = mapa_shared(smem_u32(ts_full), 0);
+    const uint32_t ts_bar = mapa_shared(smem_u32(ts_full), leader_rank);
     uint8_t* slab0 = smem + S::kOffOut + q * S::kSlabs * S::kSlabBytes;
     uint64_t* my_res = res_full + q * S::kSlabs;
     constexpr int kChunks = BN / 64;             // 64-column output chunks per tile
@@ -241,7 +240,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t = cluster_id + static_cast<int>(c / kChunks) * num_clusters;
       if (t >= num_tiles) return;
       const int g = static_cast<int>(c % kChunks);
-      const int rm0 = (t / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128 + q * 32;
+      const int rm0 = (t / p.num_n_tiles) * 512 + static_cast<int>(pair) * 256 + static_cast<int>(half) * 128 + q * 32;
       const int ro0 = (t % p.num_n_tiles) * BN + g * 64;
       const uint32_t sl = c % S::kSlabs;
       mbar_arrive_expect_tx(&my_res[sl], S::kSlabBytes);
@@ -252,7 +251,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       prefetch_res(1);
     }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
-      const int m0 = (tile / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int m0 = (tile / p.num_n_tiles) * 512 + static_cast<int>(pair) * 256 + static_cast<int>(half) * 128;
       const int nt = tile % p.num_n_tiles;
       const int o0 = nt * BN;
       const uint32_t buf = lt & 1;
@@ -264,7 +263,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kLoRA) {
         // this CTA's half of Q: rows o0 + rank*BN/2 + r  -> K-major no-swizzle: (r/8)*256 + c*128 + (r%8)*16
         const uint32_t q_s = smem_u32(smem + S::kOffQ);
-        const int qrow0 = o0 + static_cast<int>(rank) * (BN / 2);
+        const int qrow0 = o0 + static_cast<int>(half) * (BN / 2);
         for (int i = et; i < BN; i += 128) {       // BN/2 rows x 2 chunks
           const int r = i >> 1, c = i & 1;
           uint4 v = make_uint4(0, 0, 0, 0);
@@ -341,7 +340,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // every TMEM read of this tile has retired: hand the accumulator buffer back before the last store goes out
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[buf]), 0));
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[buf]), leader_rank));
         }
         fence_proxy_async_smem();
         __syncwarp();
