@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--rank", type=int, default=16)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--checkpointing", action="store_true", help="gradient checkpointing per block (the reference's shipped YAML sets it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -253,6 +254,7 @@ def run_ours(args) -> None:
 
     model_name = args.model
     net = T.build_jit_qlora(model_name, rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
+    net.set_gradient_checkpointing(args.checkpointing)
     step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
                                seed=42 + rank)
     host = T.synthetic_batch(args.batch, args.res, args.res, seed=1000 + rank)
@@ -371,7 +373,7 @@ def run_ours(args) -> None:
             "data": "synthetic",
             "config": {"workload": workload_name(model_name, args.batch, args.res, args.rank),
                        "global_batch": world * args.batch, "parallelism": f"dp{world}",
-                       "cuda_graph": not args.no_graph, "gradient_checkpointing": False,
+                       "cuda_graph": not args.no_graph, "gradient_checkpointing": bool(args.checkpointing),
                        "l2": "no flush: one step streams far more than the 126 MB L2 (saved activations of every block)",
                        "optimizer": "AdamW over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target},
             "clocks": clocks,

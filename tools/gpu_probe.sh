@@ -1,2 +1,1 @@
-timeout 200 python tools/bench_linear.py --model B --no-check --no-res 2>&1 | tail -6
-timeout 200 python tools/bench_linear.py --model L --no-check --no-res 2>&1 | tail -6
+timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --checkpointing 2>&1 | tail -2 | cut -c1-300
