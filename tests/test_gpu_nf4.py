@@ -95,3 +95,42 @@ def test_linear_module_state_dict_interchange():
     assert torch.equal(net.linear.dequantize().cpu(), on.dequantize_nf4(st))
     # fp16 in -> fp16 out
     assert net.linear(x.half()).dtype == torch.float16
+
+
+@pytest.mark.parametrize("shapes", [[(768, 768), (2048, 768), (768, 2048)], [(1024, 2730), (2730, 1024), (192, 341)],
+                                    [(1280, 3413), (3413, 1280)]])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_batched_dequant_slots_bit_exact(shapes, transposed):
+    """vpt_nf4_dequant_batch (the per-block launch that feeds the CTA-pair GEMM): every slot holds exactly the oracle's
+    dequantised weight -- row-major [N, ld] for the forward, transposed [K, ld] for the backward -- including the ragged
+    2730 / 3413 / 341 widths whose 64-blocks and bytes straddle rows; with LoRA given, the transposed slot also carries
+    lora_up^T and lora_down^T behind the weight."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(len(shapes) * 7 + int(transposed))
+    qs, refs, downs, ups = [], [], [], []
+    for (N, K) in shapes:
+        w = (torch.randn(N, K) * 0.05).to(torch.bfloat16)
+        st = on.quantize_nf4(w)
+        refs.append(on.dequantize_nf4(st))
+        qs.append(ops.Nf4Tensors(st.packed.cuda(), st.absmax.cuda(), st.nested_absmax.cuda(), st.nested_code.cuda(), st.code.cuda(),
+                                 float(st.offset), (N, K), torch.bfloat16))
+        kp = (K + 7) // 8 * 8
+        d = torch.zeros(16, kp, dtype=torch.bfloat16)
+        d[:, :K] = torch.randn(16, K).to(torch.bfloat16)
+        downs.append(d.cuda()[:, :K])
+        ups.append(torch.randn(N, 16).to(torch.bfloat16).cuda())
+    slots = ops.dequant_block(qs, downs, ups, transposed)
+    torch.cuda.synchronize()
+    for (N, K), slot, ref, d, u in zip(shapes, slots, refs, downs, ups):
+        buf = slot.view(torch.bfloat16)
+        if not transposed:
+            ld = (K + 7) // 8 * 8
+            got = buf[:N * ld].view(N, ld)[:, :K]
+            assert torch.equal(got.cpu(), ref), (N, K)
+        else:
+            ld = (N + 7) // 8 * 8
+            got = buf[:K * ld].view(K, ld)[:, :N]
+            assert torch.equal(got.cpu(), ref.t()), (N, K)
+            upT = buf[K * ld:K * ld + 16 * ld].view(16, ld)[:, :N]
+            downT = buf[K * ld + 16 * ld:K * ld + 16 * ld + K * 16].view(K, 16)
+            assert torch.equal(upT.cpu(), u.cpu().t()) and torch.equal(downT.cpu(), d.cpu().t()), (N, K)
