@@ -29,9 +29,9 @@ struct AttnFwdSmem {
   static constexpr int kK = 16384;            // 2 stages
   static constexpr int kV = kK + 2 * 16384;   // 2 stages
   static constexpr int kP = kV + 2 * 16384;   // P_A, P_B: [128 queries x 64 keys] bf16 each
-  static constexpr int kStat = kP;            // (m, l) of both streams per query row, [2][128] float2: reuses P at the end
-  static constexpr int kBars = kP + 32768;
-  static constexpr int kNumBars = 13;         // q_full q_empty kv_full[2] kv_empty[2] s_full[2] p_full[2] pv_done[2] o_free
+  static constexpr int kStat = kP + 32768;    // (m, l) of both streams per query row, [2 item parities][2 streams][128] float2
+  static constexpr int kBars = kStat + 4096;
+  static constexpr int kNumBars = 15;         // q_full q_empty kv_full[2] kv_empty[2] s_full[2] p_full[2] pv_done[2] o_free s_free[2]
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemSlot + 16;   // no alignment slack: two CTAs must fit in one SM's 228 KB
 };
@@ -60,6 +60,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = bars + 8;     // [2]
   uint64_t* pv_done = bars + 10;   // [2]
   uint64_t* o_free = bars + 12;    // the merge has read O_A / O_B: the next item may overwrite them
+  uint64_t* s_free = bars + 13;    // [2] the stream has S_X in registers: the next S_X may be computed while it works
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
   float2* s_stat = reinterpret_cast<float2*>(smem + S::kStat);
 
@@ -87,6 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&pv_done[s], 1);
+      mbar_init(&s_free[s], 128);
     }
     mbar_init(o_free, 8);
     fence_mbar_init();
@@ -131,15 +133,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);
     const uint64_t qd = dK_ + ((smem_base + S::kQ) >> 4);
     uint32_t jj = 0, itn = 0;
-    uint32_t cnt[2] = {0, 0};
+    uint32_t cnt[2] = {0, 0};                     // P tiles consumed per stream
+    uint32_t s_issued[2] = {0, 0};                // S_X MMAs issued per stream (each is answered by one s_free phase)
     int klen = klen_of(blockIdx.x);
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn) {
       const int nblk = (klen + kAttnTile - 1) / kAttnTile;
       const int kl = klen;
       klen = klen_of(item + gridDim.x);
-      auto issue_s = [&](int j, uint32_t s, uint32_t sp, int X) {     // S_X = Q K_X^T
+      // S_X = Q K_X^T for block j.  It overwrites the stream's single S buffer, which is free as soon as the stream has
+      // LOADED the previous S_X into registers (s_free) -- long before its exponentials are done -- so the next block's
+      // scores are already waiting when the stream comes back for them.
+      auto issue_s = [&](int j, uint32_t s, uint32_t sp, int X) {
         const int n = sub_n(kl, j, X);
         if (n == 0) return;
+        if (s_issued[X] > 0) mbar_wait(&s_free[X], (s_issued[X] - 1) & 1);
+        ++s_issued[X];
         mbar_wait(&kv_full[s], sp);
         tc_fence_after_sync();
         const uint64_t kd = dK_ + ((smem_base + S::kK + s * 16384 + X * 8192) >> 4);
@@ -164,6 +172,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < nblk; ++j, ++jj) {
         const uint32_t s = jj & 1;
         const uint64_t vd = dMN + ((smem_base + S::kV + s * 16384) >> 4);
+        if (j + 1 < nblk) {
+          issue_s(j + 1, (jj + 1) & 1, ((jj + 1) >> 1) & 1, 0);
+          issue_s(j + 1, (jj + 1) & 1, ((jj + 1) >> 1) & 1, 1);
+          if (j + 2 == nblk) {
+            if (elect_one_sync()) umma_commit(q_empty);
+            __syncwarp();
+          }
+        }
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
           const int n = sub_n(kl, j, X);
@@ -185,13 +201,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (elect_one_sync()) umma_commit(&kv_empty[s]);
             __syncwarp();
           }
-          if (j + 1 < nblk) {
-            issue_s(j + 1, (jj + 1) & 1, ((jj + 1) >> 1) & 1, X);    // the other stream's softmax runs meanwhile
-            if (X == 1 && j + 2 == nblk) {
-              if (elect_one_sync()) umma_commit(q_empty);
-              __syncwarp();
-            }
-          }
         }
       }
     }
@@ -204,11 +213,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t p_row = smem_u32(smem + S::kP) + X * 16384 + row * 128;
     const int rin = row & 7;
     uint32_t cx = 0;
-    int klen_next = klen_of(blockIdx.x);
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    int klen_next = klen_of(blockIdx.x), klen_next2 = klen_of(blockIdx.x + gridDim.x);
+    uint32_t itn_s = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn_s) {
       const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
       const int klen = klen_next;
-      klen_next = klen_of(item + gridDim.x);
+      klen_next = klen_next2;
+      klen_next2 = klen_of(item + 2 * gridDim.x);   // fetched two items ahead of its first use
       const int nblk = (klen + kAttnTile - 1) / kAttnTile;
       float m_ref = -INFINITY, l_run = 0.f;
       bool first = true;
@@ -222,6 +233,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tS + X * 64 + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         if (n > 32) tmem_ld32(tS + X * 64 + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_wait_ld();
+        tc_fence_before_sync();
+        mbar_arrive(&s_free[X]);                    // the scores are in registers: the tensor core may write the next S_X
         if (nvalid < 64) {
 #pragma unroll
           for (int i = 0; i < 64; ++i)
@@ -283,10 +296,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&pv_done[X], (cx - 1) & 1);
         tc_fence_after_sync();
       }
-      named_bar_sync(1, 256);                       // both streams' last P V MMA has read the P tiles: reuse them
-      s_stat[X * 128 + row] = make_float2(m_ref, l_run);
+      // one barrier per item: the statistics are double-buffered by item parity (a thread is never more than one
+      // item ahead of another, since every item has this exchange)
+      float2* stat = s_stat + (itn_s & 1) * 256;
+      stat[X * 128 + row] = make_float2(m_ref, l_run);
       named_bar_sync(1, 256);
-      const float2 sa = s_stat[row], sb = s_stat[128 + row];
+      const float2 sa = stat[row], sb = stat[128 + row];
       const float m = fmaxf(sa.x, sb.x);
       const float wa = sa.y > 0.f ? fast_exp2(sa.x - m) : 0.f;     // a stream without keys has l = 0
       const float wb = sb.y > 0.f ? fast_exp2(sb.x - m) : 0.f;
@@ -303,7 +318,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (has_b) tmem_ld32(tO + 64 + lane_off + X * 32, ob);
       tmem_wait_ld();
       tc_fence_before_sync();
-      named_bar_sync(1, 256);                       // the statistics are read too: the next item may write P again
+      __syncwarp();
       if (lane == 0) mbar_arrive(o_free);
       if (q < p.Lq) {
         __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh + X * 32;
