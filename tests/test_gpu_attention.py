@@ -9,7 +9,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk,lens", [(2, 3, 330, 330, [330, 285]), (1, 2, 128, 128, None), (2, 2, 266, 266, None),
-                                           (2, 1, 200, 77, [77, 40]), (1, 2, 1100, 1100, [1093])])
+                                           (2, 1, 200, 77, [77, 40]), (1, 2, 1100, 1100, [1093]),
+                                           # SDXL TransformerBlock at D=1280 (20 heads of 64): self-attention over ~1024 latent
+                                           # tokens and cross-attention to 77 / 231 text tokens (src/models/sdxl/denoiser.py:32-172)
+                                           (1, 20, 1056, 1056, None), (2, 20, 1024, 231, None), (1, 10, 2112, 77, None)])
 @pytest.mark.parametrize("layout", ["bhld", "blhd"])
 def test_attention_fwd_bwd(B, H, Lq, Lk, lens, layout):
     from vision_pt_b200 import ops
