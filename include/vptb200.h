@@ -133,22 +133,23 @@ int vpt_lora_grad_batch(const vpt_lora_grad_item* items, int32_t n_items, vpt_st
 
 /* ------------------------------------------------------------------------------------------------ attention
  * scaled_dot_product_attention(q, k, v, mask=key padding) (src/modules/attention.py:98-129) as used by
- * Attention.forward (src/models/jit/denoiser.py:351-397); head_dim 64; the bool key-padding mask is given as
- * seqlens_k[b] = number of leading valid keys (NULL = all).  Tensors are (batch, token, head, 64) with element
- * strides (sb, sl, sh); both [B,H,L,64] and [B,L,H,64] memory layouts are accepted. */
+ * Attention.forward (src/models/jit/denoiser.py:351-397); the bool key-padding mask is given as seqlens_k[b] = number
+ * of leading valid keys (NULL = all).  Tensors are (batch, token, head, head_dim) with element strides (sb, sl, sh);
+ * both [B,H,L,hd] and [B,L,H,hd] memory layouts are accepted.  head_dim 64 runs the tcgen05 kernels (JiT-B/L, SDXL);
+ * 32 / 80 / 96 / 128 (JiT-H: 80) run CUDA-core kernels for now. */
 typedef struct {
   const void* ptr;
   int64_t sb, sl, sh;
 } vpt_attn_tensor;
 int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v, const vpt_attn_tensor* o,
-                 int32_t B, int32_t H, int32_t Lq, int32_t Lk, const int32_t* seqlens_k, float scale,
+                 int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t head_dim, const int32_t* seqlens_k, float scale,
                  float* lse2 /* [B,H,Lq rounded up to 128] */, vpt_stream_t stream);
 /* dq is fp32 and must be zero on entry; lse2 as written by vpt_attn_fwd; delta_ws: [B,H,Lq rounded up to 128] fp32
  * workspace. */
 int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v, const vpt_attn_tensor* o,
                  const vpt_attn_tensor* d_o, const vpt_attn_tensor* dq_f32, const vpt_attn_tensor* dk,
-                 const vpt_attn_tensor* dv, int32_t B, int32_t H, int32_t Lq, int32_t Lk, const int32_t* seqlens_k,
-                 float scale, const float* lse2, float* delta_ws, vpt_stream_t stream);
+                 const vpt_attn_tensor* dv, int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t head_dim,
+                 const int32_t* seqlens_k, float scale, const float* lse2, float* delta_ws, vpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ norms etc.
  * FP32RMSNorm.forward (src/modules/norm.py:20-27). rstd_out may be NULL. w may be NULL (no affine). */
@@ -157,12 +158,13 @@ int vpt_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int6
 /* dx = rmsnorm_bwd(dy) (+ dres); dw (fp32 [D], accumulated) may be NULL; rstd may be NULL (recomputed). */
 int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
                     float* dw, int64_t rows, int32_t D, int64_t ld, float eps, vpt_stream_t stream);
-/* q_norm/k_norm + apply_rope (src/models/jit/denoiser.py:98-111,365-373) on [tokens, H, 64]; cos_sin: [L,32,2] fp32 */
+/* q_norm/k_norm + apply_rope (src/models/jit/denoiser.py:98-111,365-373) on [tokens, H, head_dim]; cos_sin:
+ * [L, head_dim/2, 2] fp32; head_dim 64, 80, 96 or 128 */
 int vpt_qknorm_rope_fwd(const void* x, const void* w, const float* cos_sin, void* y, int64_t tokens, int32_t H,
-                        int32_t L, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream);
+                        int32_t L, int32_t head_dim, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream);
 int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void* x, const void* w, const float* cos_sin,
-                        void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int64_t lddy, int64_t ldx,
-                        int64_t lddx, float eps, vpt_stream_t stream);
+                        void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int32_t head_dim, int64_t lddy,
+                        int64_t ldx, int64_t lddx, float eps, vpt_stream_t stream);
 /* SwiGLU.forward gate: a = silu(g) * u (src/models/jit/denoiser.py:502) */
 int vpt_swiglu_fwd(const void* g, const void* u, void* a, int64_t rows, int32_t F, int64_t ldg, int64_t ldu,
                    int64_t lda, vpt_stream_t stream);

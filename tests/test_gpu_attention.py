@@ -54,3 +54,28 @@ def test_reference_sdpa_vector(golden):
         scaled_dot_product_attention(g["q"].cuda(), g["k"].cuda(), g["v"].cuda(), mask=torch.ones(B, H, L, L, dtype=torch.bool, device="cuda"))
     with pytest.raises(ValueError):
         scaled_dot_product_attention(g["q"].cuda(), g["k"].cuda(), g["v"].cuda(), backend="nope")
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,lens,hd", [(2, 3, 300, 300, [300, 251], 80), (1, 2, 1100, 1100, [1093], 80),
+                                              (2, 2, 200, 77, [77, 40], 80), (1, 2, 130, 130, None, 128), (1, 1, 64, 40, None, 32)])
+def test_attention_other_head_dims(B, H, Lq, Lk, lens, hd):
+    """head_dim != 64 (JiT-H: 80, BASELINE.json configs[3]) runs the CUDA-core kernels of attention_simple.cuh: same
+    contract and the same tolerance as the tcgen05 path."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(B * 100 + Lq + hd)
+    mk = lambda L: torch.randn(B, H, L, hd).to(torch.bfloat16)
+    q, k, v, d_o = mk(Lq) * 1.5, mk(Lk) * 1.5, mk(Lk), mk(Lq)
+    seq = None if lens is None else torch.tensor(lens, dtype=torch.int32)
+    dev = lambda t: t.permute(0, 2, 1, 3).contiguous().cuda().permute(0, 2, 1, 3).requires_grad_(True)
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    o = ops.attention(qg, kg, vg, None if seq is None else seq.cuda())
+    o.backward(d_o.cuda())
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    orf = oj.attention_explicit(qr, kr, vr, None if seq is None else seq.long())
+    orf.backward(d_o.float())
+    assert rel_err(o, orf) <= 2e-2
+    assert rel_err(qg.grad, qr.grad) <= 2e-2 and rel_err(kg.grad, kr.grad) <= 2e-2 and rel_err(vg.grad, vr.grad) <= 2e-2
+    if seq is not None:
+        for b, n in enumerate(lens):
+            if n < Lk:
+                assert kg.grad[b, :, n:].abs().max() == 0 and vg.grad[b, :, n:].abs().max() == 0

@@ -169,3 +169,50 @@ def test_fused_block_equals_per_op_block_at_bench_shape():
     assert set(g1) == set(g2) and len(g1) == 14
     for n in g1:
         assert rel_err(g1[n], g2[n]) <= 2e-2, n
+
+
+def test_jit_h_like_denoiser_head_dim_80():
+    """A JiT-H-shaped model in miniature (head_dim 80, rope_axes_dims [16, 32, 32], ragged SwiGLU width, NF4 + LoRA): the
+    fused block path runs, and prediction / loss / LoRA gradients match the fp32 oracle on the same weights."""
+    from vision_pt_b200 import ops
+    from vision_pt_b200 import train as T
+    from vision_pt_b200.jit import DenoiserConfig
+    dev = torch.device("cuda")
+    cfg = DenoiserConfig(patch_size=16, in_channels=3, out_channels=3, hidden_size=320, depth=2, num_heads=4, mlp_ratio=4.0,
+                         bottleneck_dim=32, num_time_tokens=4, rope_axes_dims=[16, 32, 32], context_dim=64,
+                         context_start_block=1)
+    cfgd = cfg.model_dump()
+    net = T.build_jit_qlora(cfg, rank=16, alpha=16.0, device=dev, seed=21, lora_up_std=0.02)
+    assert all(b.fused_eligible(torch.empty(1, 1, 320, device=dev, dtype=torch.bfloat16)) for b in net.blocks)
+    B, H, W, Tn = 3, 64, 96, 16
+    g = torch.Generator().manual_seed(2)
+    image = torch.randn(B, 3, H, W, generator=g).to(torch.bfloat16)
+    t = torch.rand(B, generator=g).to(torch.bfloat16)
+    ctx = (torch.randn(B, Tn, 64, generator=g) * 0.5).to(torch.bfloat16)
+    mask = (torch.arange(Tn).unsqueeze(0) < torch.tensor([16, 9, 3]).unsqueeze(1)).to(torch.int64)
+    size = torch.tensor([[H, W]]).repeat(B, 1)
+    clean = torch.randn(B, 3, H, W, generator=g).to(torch.bfloat16)
+    pred = net(image=image.to(dev), timestep=t.to(dev), context=ctx.to(dev), original_size=size.to(dev), target_size=size.to(dev),
+               crop_coords=torch.zeros_like(size).to(dev), context_mask=mask.to(dev))
+    loss = ops.flow_loss(pred, clean.to(dev), loss_target="image")
+    loss.backward()
+    P = {}
+    for name, p in net.state_dict().items():
+        if ".weight." not in name:
+            P[name] = p.detach().float().cpu()
+    for name, mod in net.named_modules():
+        qs = getattr(mod, "quant_state", None)
+        if qs is not None:
+            st = on.Nf4State(packed=qs.packed.cpu(), absmax=qs.absmax.cpu(), nested_absmax=qs.nested_absmax.cpu(),
+                             nested_code=qs.nested_code.cpu(), code=qs.code.cpu(), offset=float(qs.offset),
+                             shape=tuple(qs.shape), dtype=qs.dtype)
+            P[f"{name}.weight"] = on.dequantize_nf4(st).float()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if "lora_down" in k or "lora_up" in k}
+    P.update(leaves)
+    y = oj.jit_forward(P, cfgd, image.float(), t.float(), ctx.float(), size, size, torch.zeros_like(size), context_mask=mask, alpha=16.0)
+    ref_loss = torch.nn.functional.mse_loss(y, clean.float())
+    ref_loss.backward()
+    assert rel_err(pred, y) <= 3e-2
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss))
+    worst = max(rel_err(p.grad, leaves[n].grad) for n, p in net.named_parameters() if p.requires_grad)
+    assert worst <= 5e-2, worst

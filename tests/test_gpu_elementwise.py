@@ -132,3 +132,24 @@ def test_patch_module_api(golden):
     assert torch.equal(unpatchify(out.patches, 2, 3, 16, 3).image.cpu(), g["image"])
     with pytest.raises(ValueError):
         patchify(torch.zeros(4, device="cuda"), 2)
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 70, 4), (1, 33, 3)])
+def test_qknorm_rope_head_dim_80(B, L, H):
+    """JiT-H (BASELINE.json configs[3]): head_dim 80, rope_axes_dims [16, 32, 32] (src/models/jit/config.py)."""
+    from vision_pt_b200 import ops
+    cfg = dict(patch_size=16, rope_theta=256.0, rope_axes_dims=[16, 32, 32], num_time_tokens=4)
+    torch.manual_seed(L + H)
+    f = oj.rope_freqs_cis(cfg, 16 * 4, 16 * ((L + 3) // 4), 8)[:L]
+    cs = torch.stack([f.real, f.imag], dim=-1).contiguous().float()
+    x = torch.randn(B, L, H, 80).to(torch.bfloat16)
+    w = (torch.randn(80) * 0.2 + 1).to(torch.bfloat16)
+    dy = torch.randn(B, L, H, 80).to(torch.bfloat16)
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    y = ops.qknorm_rope(xg, wg, cs.cuda(), 1e-6)
+    y.backward(dy.cuda())
+    ref = oj.apply_rope(oj.rms_norm_fp32(x.permute(0, 2, 1, 3), w), f).permute(0, 2, 1, 3)
+    assert rel_err(y, ref) <= 1e-2
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    oj.apply_rope(oj.rms_norm_fp32(xr.permute(0, 2, 1, 3), wr), f).permute(0, 2, 1, 3).backward(dy.float())
+    assert rel_err(xg.grad, xr.grad) <= 2e-2 and rel_err(wg.grad, wr.grad) <= 2e-2

@@ -54,12 +54,12 @@ SIGNATURES: dict[str, list] = {
     "vpt_nf4lora_linear_bwd_dx": [C.POINTER(LinearArgsC), _P],
     "vpt_lora_grad_batch": [C.POINTER(LoraGradItemC), _I32, _P],
     "vpt_nf4_dequant_batch": [C.POINTER(DequantItemC), _I32, _I32, _P],
-    "vpt_attn_fwd": [_AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P],
-    "vpt_attn_bwd": [_AT, _AT, _AT, _AT, _AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P],
+    "vpt_attn_fwd": [_AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _I32, _P, _F, _P, _P],
+    "vpt_attn_bwd": [_AT, _AT, _AT, _AT, _AT, _AT, _AT, _AT, _I32, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P],
     "vpt_rmsnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _F, _P],
     "vpt_rmsnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I64, _F, _P],
-    "vpt_qknorm_rope_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _I64, _I64, _F, _P],
-    "vpt_qknorm_rope_bwd": [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _I64, _I64, _F, _P],
+    "vpt_qknorm_rope_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I64, _I64, _F, _P],
+    "vpt_qknorm_rope_bwd": [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I64, _I64, _I64, _F, _P],
     "vpt_swiglu_fwd": [_P, _P, _P, _I64, _I32, _I64, _I64, _I64, _P],
     "vpt_swiglu_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _I64, _I64, _I64, _I64, _I64, _P],
     "vpt_ln_modulate_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],

@@ -22,7 +22,7 @@ static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
 }
 
 extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
-extern "C" int vpt_abi_version(void) { return 2; }
+extern "C" int vpt_abi_version(void) { return 3; }
 
 // ---------------------------------------------------------------------------------------------------- NF4
 extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
@@ -239,19 +239,23 @@ extern "C" int vpt_lora_grad_batch(const vpt_lora_grad_item* items, int32_t n_it
 // ---------------------------------------------------------------------------------------------------- attention
 static inline AttnTensor AT(const vpt_attn_tensor* t) { return AttnTensor{t->ptr, static_cast<long>(t->sb), static_cast<long>(t->sl), static_cast<long>(t->sh)}; }
 extern "C" int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v,
-                            const vpt_attn_tensor* o, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                            const vpt_attn_tensor* o, int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t head_dim,
                             const int32_t* seqlens_k, float scale, float* lse2, vpt_stream_t stream) {
   VPT_REQUIRE(q && k && v && o && lse2 && B > 0 && H > 0 && Lq > 0 && Lk > 0, "vpt_attn_fwd: bad arguments");
-  return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream));
+  if (head_dim == 64) return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream));
+  return launch_attn_simple_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, head_dim, seqlens_k, scale, lse2, S(stream));
 }
 extern "C" int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v,
                             const vpt_attn_tensor* o, const vpt_attn_tensor* d_o, const vpt_attn_tensor* dq_f32,
                             const vpt_attn_tensor* dk, const vpt_attn_tensor* dv, int32_t B, int32_t H, int32_t Lq,
-                            int32_t Lk, const int32_t* seqlens_k, float scale, const float* lse2, float* delta_ws,
-                            vpt_stream_t stream) {
+                            int32_t Lk, int32_t head_dim, const int32_t* seqlens_k, float scale, const float* lse2,
+                            float* delta_ws, vpt_stream_t stream) {
   VPT_REQUIRE(q && k && v && o && d_o && dq_f32 && dk && dv && lse2 && delta_ws, "vpt_attn_bwd: null pointer");
-  return launch_attn_bwd(AT(q), AT(k), AT(v), AT(o), AT(d_o), AT(dq_f32), AT(dk), AT(dv), B, H, Lq, Lk, seqlens_k, scale, lse2,
-                         delta_ws, S(stream));
+  if (head_dim == 64)
+    return launch_attn_bwd(AT(q), AT(k), AT(v), AT(o), AT(d_o), AT(dq_f32), AT(dk), AT(dv), B, H, Lq, Lk, seqlens_k, scale, lse2,
+                           delta_ws, S(stream));
+  return launch_attn_simple_bwd(AT(q), AT(k), AT(v), AT(o), AT(d_o), AT(dq_f32), AT(dk), AT(dv), B, H, Lq, Lk, head_dim, seqlens_k,
+                                scale, lse2, delta_ws, S(stream));
 }
 
 // ---------------------------------------------------------------------------------------------------- elementwise
@@ -279,27 +283,40 @@ extern "C" int vpt_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
   return 0;
 }
 extern "C" int vpt_qknorm_rope_fwd(const void* x, const void* w, const float* cos_sin, void* y, int64_t tokens, int32_t H,
-                                   int32_t L, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream) {
+                                   int32_t L, int32_t head_dim, int64_t ldx, int64_t ldy, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(x && w && cos_sin && y && tokens > 0 && H > 0 && L > 0 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_qknorm_rope_fwd: bad arguments");
-  const int hp = H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 1);
-  const dim3 grid(blocks_for(tokens * (H / hp) * 8, 256, 1L << 30));
-#define VPT_QK_FWD(HP) VPT_CUDA_OK(launch_pdl(qknorm_rope_fwd_kernel<HP>, grid, dim3(256), 0, S(stream), BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps))
-  if (hp == 4) VPT_QK_FWD(4); else if (hp == 2) VPT_QK_FWD(2); else VPT_QK_FWD(1);
+  VPT_REQUIRE(head_dim == 64 || head_dim == 80 || head_dim == 96 || head_dim == 128, "vpt_qknorm_rope_fwd: head_dim must be 64, 80, 96 or 128");
+  const int hp = head_dim == 64 ? (H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 1)) : (H % 2 == 0 ? 2 : 1);
+  const int gl = head_dim == 64 ? 8 : 16;
+  const dim3 grid(blocks_for(tokens * (H / hp) * gl, 256, 1L << 30));
+#define VPT_QK_FWD(HP, HD) VPT_CUDA_OK(launch_pdl(qknorm_rope_fwd_kernel<HP, HD>, grid, dim3(256), 0, S(stream), BF(x), BF(w), cos_sin, BFM(y), tokens, H, L, ldx, ldy, eps))
+#define VPT_QK_FWD_HD(HD) do { if (hp == 2) VPT_QK_FWD(2, HD); else VPT_QK_FWD(1, HD); } while (0)
+  if (head_dim == 64) {
+    if (hp == 4) VPT_QK_FWD(4, 64); else VPT_QK_FWD_HD(64);
+  } else if (head_dim == 80) VPT_QK_FWD_HD(80);
+  else if (head_dim == 96) VPT_QK_FWD_HD(96);
+  else VPT_QK_FWD_HD(128);
+#undef VPT_QK_FWD_HD
 #undef VPT_QK_FWD
   return 0;
 }
 extern "C" int vpt_qknorm_rope_bwd(const void* dy, int32_t dy_is_f32, const void* x, const void* w, const float* cos_sin,
-                                   void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int64_t lddy, int64_t ldx,
-                                   int64_t lddx, float eps, vpt_stream_t stream) {
+                                   void* dx, float* dw, int64_t tokens, int32_t H, int32_t L, int32_t head_dim, int64_t lddy,
+                                   int64_t ldx, int64_t lddx, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && w && cos_sin && dx && tokens > 0 && H > 0 && L > 0, "vpt_qknorm_rope_bwd: bad arguments");
+  VPT_REQUIRE(head_dim == 64 || head_dim == 80 || head_dim == 96 || head_dim == 128, "vpt_qknorm_rope_bwd: head_dim must be 64, 80, 96 or 128");
   const int hp = H % 2 == 0 ? 2 : 1;            // 4 heads per lane group cost occupancy here (measured slower)
-  const dim3 grid(blocks_for(tokens * (H / hp) * 8, 256, 1L << 30));
-#define VPT_QK_BWD(F32, HP) VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<F32, HP>, grid, dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps))
-  if (dy_is_f32) {
-    if (hp == 2) VPT_QK_BWD(true, 2); else VPT_QK_BWD(true, 1);
-  } else {
-    if (hp == 2) VPT_QK_BWD(false, 2); else VPT_QK_BWD(false, 1);
-  }
+  const int gl = head_dim == 64 ? 8 : 16;
+  const dim3 grid(blocks_for(tokens * (H / hp) * gl, 256, 1L << 30));
+#define VPT_QK_BWD(F32, HP, HD) VPT_CUDA_OK(launch_pdl(qknorm_rope_bwd_kernel<F32, HP, HD>, grid, dim3(256), 0, S(stream), dy, BF(x), BF(w), cos_sin, BFM(dx), dw, tokens, H, L, lddy, ldx, lddx, eps))
+#define VPT_QK_BWD_HD(HD) do { \
+    if (dy_is_f32) { if (hp == 2) VPT_QK_BWD(true, 2, HD); else VPT_QK_BWD(true, 1, HD); } \
+    else { if (hp == 2) VPT_QK_BWD(false, 2, HD); else VPT_QK_BWD(false, 1, HD); } } while (0)
+  if (head_dim == 64) VPT_QK_BWD_HD(64);
+  else if (head_dim == 80) VPT_QK_BWD_HD(80);
+  else if (head_dim == 96) VPT_QK_BWD_HD(96);
+  else VPT_QK_BWD_HD(128);
+#undef VPT_QK_BWD_HD
 #undef VPT_QK_BWD
   return 0;
 }

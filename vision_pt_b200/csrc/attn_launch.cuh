@@ -2,6 +2,7 @@
 #pragma once
 #include "attention.cuh"
 #include "attention_bwd.cuh"
+#include "attention_simple.cuh"
 #include "host.cuh"
 
 namespace vpt {
@@ -96,5 +97,65 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   VPT_CUDA_OK(launch_pdl(attn_bwd2_kernel, dim3(ctas), dim3(512), AttnBwd2Smem::kTotal, stream, tq, tk, tv, tdo, tdq, tdk, tdv, p));
   return 0;
 }
+
+// ---- head_dim != 64: CUDA-core kernels (attention_simple.cuh)
+inline SimpleAttnTensor SAT(const AttnTensor& t) { return SimpleAttnTensor{static_cast<const __nv_bfloat16*>(t.ptr), t.sb, t.sl, t.sh}; }
+
+template <int HD>
+int launch_attn_simple_fwd_t(const SimpleAttnParams& p, cudaStream_t stream) {
+  dim3 grid((p.Lq + kSaRows - 1) / kSaRows, p.H, p.B);
+  attn_simple_fwd_kernel<HD><<<grid, kSaRows, 0, stream>>>(p);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <int HD>
+int launch_attn_simple_bwd_t(const SimpleAttnParams& p, float* delta, cudaStream_t stream) {
+  const long total = static_cast<long>(p.B) * p.H * p.Lq_pad;
+  attn_simple_delta_kernel<HD><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p, delta);
+  dim3 gq((p.Lq + kSaRows - 1) / kSaRows, p.H, p.B), gk((p.Lk + kSaRows - 1) / kSaRows, p.H, p.B);
+  attn_simple_bwd_dq_kernel<HD><<<gq, kSaRows, 0, stream>>>(p);
+  attn_simple_bwd_dkv_kernel<HD, true><<<gk, kSaRows, 0, stream>>>(p);
+  attn_simple_bwd_dkv_kernel<HD, false><<<gk, kSaRows, 0, stream>>>(p);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+#define VPT_SIMPLE_HD(CALL)                                                                   \
+  switch (head_dim) {                                                                         \
+    case 32: return CALL(32);                                                                 \
+    case 80: return CALL(80);                                                                 \
+    case 96: return CALL(96);                                                                 \
+    case 128: return CALL(128);                                                               \
+    default: return fail("attention: head_dim must be 64 (tcgen05 kernels) or 32 / 80 / 96 / 128 (CUDA-core kernels)"); \
+  }
+
+inline int launch_attn_simple_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,
+                                  int H, int Lq, int Lk, int head_dim, const int* seqlens_k, float scale, float* lse2,
+                                  cudaStream_t stream) {
+  SimpleAttnParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.Lq_pad = (Lq + 127) / 128 * 128;
+  p.seqlens_k = seqlens_k; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.q = SAT(q); p.k = SAT(k); p.v = SAT(v); p.o = SAT(o);
+  p.lse2 = lse2;
+#define VPT_CALL(HD) launch_attn_simple_fwd_t<HD>(p, stream)
+  VPT_SIMPLE_HD(VPT_CALL)
+#undef VPT_CALL
+}
+inline int launch_attn_simple_bwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o,
+                                  const AttnTensor& d_o, const AttnTensor& dq_f32, const AttnTensor& dk, const AttnTensor& dv,
+                                  int B, int H, int Lq, int Lk, int head_dim, const int* seqlens_k, float scale,
+                                  const float* lse2, float* delta, cudaStream_t stream) {
+  SimpleAttnParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.Lq_pad = (Lq + 127) / 128 * 128;
+  p.seqlens_k = seqlens_k; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.q = SAT(q); p.k = SAT(k); p.v = SAT(v); p.o = SAT(o); p.d_o = SAT(d_o);
+  p.lse2 = const_cast<float*>(lse2); p.delta = delta;
+  p.dq = static_cast<float*>(const_cast<void*>(dq_f32.ptr)); p.dq_sb = dq_f32.sb; p.dq_sl = dq_f32.sl; p.dq_sh = dq_f32.sh;
+  p.dk = static_cast<__nv_bfloat16*>(const_cast<void*>(dk.ptr)); p.dk_sb = dk.sb; p.dk_sl = dk.sl; p.dk_sh = dk.sh;
+  p.dv = static_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr)); p.dv_sb = dv.sb; p.dv_sl = dv.sl; p.dv_sh = dv.sh;
+#define VPT_CALL(HD) launch_attn_simple_bwd_t<HD>(p, delta, stream)
+  VPT_SIMPLE_HD(VPT_CALL)
+#undef VPT_CALL
+}
+#undef VPT_SIMPLE_HD
 
 }  // namespace vpt

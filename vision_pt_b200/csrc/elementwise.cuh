@@ -162,30 +162,39 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------- QK-norm + RoPE
-// x: [tokens = B*L, H, 64] (row pitch ld elements); per head: n = bf16(rmsnorm(x) * w); rotate interleaved pairs
-// (n[2i], n[2i+1]) by (cos, sin)[l, i]; l = token % L.  One 8-lane group per (token, HP consecutive heads): the rotation
-// table and the norm weight are fetched once for the HP heads and their 16-byte loads are all in flight together.
-template <int HP>
+// x: [tokens = B*L, H, HD] (row pitch ld elements); per head: n = bf16(rmsnorm(x) * w); rotate interleaved pairs
+// (n[2i], n[2i+1]) by (cos, sin)[l, i]; l = token % L.  One GL-lane group per (token, HP consecutive heads), 8 elements per
+// lane (GL = 8 for head_dim 64, 16 with the upper lanes idle for 80 / 96 / 128): the rotation table and the norm weight are
+// fetched once for the HP heads and their 16-byte loads are all in flight together.
+template <int HP, int HD>
 __global__ void __launch_bounds__(256)
 qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                       const float* __restrict__ cs /* [L, 32, 2] */, __nv_bfloat16* __restrict__ y, long tokens, int H,
+                       const float* __restrict__ cs /* [L, HD/2, 2] */, __nv_bfloat16* __restrict__ y, long tokens, int H,
                        int L, long ldx, long ldy, float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  constexpr int GL = HD <= 64 ? 8 : 16;
+  constexpr int GS = GL == 8 ? 3 : 4;
   const int hg = H / HP;
-  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
+  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> GS;
+  const int sub = threadIdx.x & (GL - 1);
+  const bool lane_on = sub * 8 < HD;
   const bool live = g < tokens * hg;
+  const bool act = live && lane_on;
   const long tok = live ? g / hg : 0;
   const int h0 = live ? static_cast<int>(g % hg) * HP : 0;
   uint4 v[HP];
 #pragma unroll
-  for (int j = 0; j < HP; ++j) v[j] = live ? ld_stream(x + tok * ldx + (h0 + j) * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
-  float fw[8];
-  ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
-  const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
-  const float4 t0 = t[0], t1 = t[1];
-  const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+  for (int j = 0; j < HP; ++j) v[j] = act ? ld_stream(x + tok * ldx + (h0 + j) * HD + sub * 8) : make_uint4(0, 0, 0, 0);
+  float fw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float c[4] = {0.f, 0.f, 0.f, 0.f}, s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane_on) {
+    ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
+    const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * (HD / 2) + sub * 4) * 2);
+    const float4 t0 = t[0], t1 = t[1];
+    c[0] = t0.x; c[1] = t0.z; c[2] = t1.x; c[3] = t1.z;
+    s[0] = t0.y; s[1] = t0.w; s[2] = t1.y; s[3] = t1.w;
+  }
 #pragma unroll
   for (int j = 0; j < HP; ++j) {
     float f[8];
@@ -193,10 +202,9 @@ qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     float ss = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+#pragma unroll
+    for (int o = 1; o < GL; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.f / HD) + eps);
     float o[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -205,22 +213,26 @@ qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
       o[2 * i] = a * c[i] - b * s[i];
       o[2 * i + 1] = a * s[i] + b * c[i];
     }
-    if (live) st_stream(y + tok * ldy + (h0 + j) * 64 + sub * 8, ew_pack8(o));
+    if (act) st_stream(y + tok * ldy + (h0 + j) * HD + sub * 8, ew_pack8(o));
   }
 }
 
 // dy is fp32 (the attention dQ accumulator) or bf16.  dn = R^T dy ; dx = rmsnorm_bwd(dn) with weight w.
-template <bool kDyF32, int HP>
+template <bool kDyF32, int HP, int HD>
 __global__ void __launch_bounds__(256)
 qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ cs, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, long tokens,
                        int H, int L, long lddy, long ldx, long lddx, float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  constexpr int GL = HD <= 64 ? 8 : 16;
+  constexpr int GS = GL == 8 ? 3 : 4;
   const int hg = H / HP;
-  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
+  const long g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> GS;
+  const int sub = threadIdx.x & (GL - 1);
+  const bool lane_on = sub * 8 < HD;
   const bool live = g < tokens * hg;
+  const bool act = live && lane_on;
   const long tok = live ? g / hg : 0;
   const int h0 = live ? static_cast<int>(g % hg) * HP : 0;
   uint4 vx[HP];
@@ -230,22 +242,26 @@ qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __rest
     vx[j] = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[j][e] = 0.f;
-    if (live) {
-      vx[j] = ld_stream(x + tok * ldx + (h0 + j) * 64 + sub * 8);
+    if (act) {
+      vx[j] = ld_stream(x + tok * ldx + (h0 + j) * HD + sub * 8);
       if (kDyF32) {
-        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + tok * lddy + (h0 + j) * 64 + sub * 8);
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + tok * lddy + (h0 + j) * HD + sub * 8);
         const float4 a = p[0], b = p[1];
         d[j][0] = a.x; d[j][1] = a.y; d[j][2] = a.z; d[j][3] = a.w; d[j][4] = b.x; d[j][5] = b.y; d[j][6] = b.z; d[j][7] = b.w;
       } else {
-        ew_unpack8(ld_stream(static_cast<const __nv_bfloat16*>(dy_) + tok * lddy + (h0 + j) * 64 + sub * 8), d[j]);
+        ew_unpack8(ld_stream(static_cast<const __nv_bfloat16*>(dy_) + tok * lddy + (h0 + j) * HD + sub * 8), d[j]);
       }
     }
   }
-  float fw[8];
-  ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
-  const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * 32 + sub * 4) * 2);
-  const float4 t0 = t[0], t1 = t[1];
-  const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+  float fw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float c[4] = {0.f, 0.f, 0.f, 0.f}, s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane_on) {
+    ew_unpack8(*reinterpret_cast<const uint4*>(w + sub * 8), fw);
+    const float4* t = reinterpret_cast<const float4*>(cs + (static_cast<long>(tok % L) * (HD / 2) + sub * 4) * 2);
+    const float4 t0 = t[0], t1 = t[1];
+    c[0] = t0.x; c[1] = t0.z; c[2] = t1.x; c[3] = t1.z;
+    s[0] = t0.y; s[1] = t0.w; s[2] = t1.y; s[3] = t1.w;
+  }
   float dwacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < HP; ++j) {
@@ -263,21 +279,21 @@ qknorm_rope_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __rest
       dot += dn[e] * fw[e] * f[e];
     }
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
+    for (int o = 1; o < GL; o <<= 1) {
       ss += __shfl_xor_sync(0xffffffffu, ss, o);
       dot += __shfl_xor_sync(0xffffffffu, dot, o);
     }
-    const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
-    const float coef = dot * rstd * rstd * rstd * (1.f / 64.f);
+    const float rstd = rsqrtf(ss * (1.f / HD) + eps);
+    const float coef = dot * rstd * rstd * rstd * (1.f / HD);
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       o[e] = dn[e] * fw[e] * rstd - f[e] * coef;
       dwacc[e] += dn[e] * f[e] * rstd;
     }
-    if (live) st_stream(dx + tok * lddx + (h0 + j) * 64 + sub * 8, ew_pack8(o));
+    if (act) st_stream(dx + tok * lddx + (h0 + j) * HD + sub * 8, ew_pack8(o));
   }
-  if (live && dw != nullptr) {
+  if (act && dw != nullptr) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) atomicAdd(dw + sub * 8 + e, dwacc[e]);
   }

@@ -235,8 +235,9 @@ class JiTBlockFn(torch.autograd.Function):
         v, t_v = lin(2, h1)
         q = ops.qknorm_rope_fwd_raw(q_pre, qnw, cos_sin, H, L, eps)
         k = ops.qknorm_rope_fwd_raw(k_pre, knw, cos_sin, H, L, eps)
-        as4 = lambda t: t.view(B, L, H, 64).permute(0, 2, 1, 3)
-        o4, lse2 = ops.attn_fwd_raw(as4(q), as4(k), as4(v), seqlens, 0.125)
+        hd = D // H
+        as4 = lambda t: t.view(B, L, H, hd).permute(0, 2, 1, 3)
+        o4, lse2 = ops.attn_fwd_raw(as4(q), as4(k), as4(v), seqlens, hd ** -0.5)
         o2 = o4.permute(0, 2, 1, 3).reshape(M, D)
         x1, t_o = lin(3, o2, x2)
         h2, rstd2 = ops.rmsnorm_fwd_raw(x1, n2w, eps)
@@ -316,8 +317,9 @@ class JiTBlockFn(torch.autograd.Function):
         # attention branch
         do2, dt_o = back(3, dx1)
         lora_grads(3, dx1, t_o, o2, dt_o)
-        as4 = lambda t: t.view(B, L, H, 64).permute(0, 2, 1, 3)
-        dq4, dk4, dv4 = ops.attn_bwd_raw(as4(q), as4(k), as4(v), as4(o2), as4(do2), lse2, ctx.seqlens, 0.125)
+        hd = D // H
+        as4 = lambda t: t.view(B, L, H, hd).permute(0, 2, 1, 3)
+        dq4, dk4, dv4 = ops.attn_bwd_raw(as4(q), as4(k), as4(v), as4(o2), as4(do2), lse2, ctx.seqlens, hd ** -0.5)
         dq_post = dq4.permute(0, 2, 1, 3).reshape(M, D)          # fp32, token-major memory: views, no copies
         dk_post = dk4.permute(0, 2, 1, 3).reshape(M, D)
         dv2 = dv4.permute(0, 2, 1, 3).reshape(M, D)
@@ -360,7 +362,7 @@ class JiTBlock(nn.Module):
 
     def fused_eligible(self, x: torch.Tensor) -> bool:
         norms = [self.norm1, self.norm2, self.attn.q_norm, self.attn.k_norm]
-        return (self.use_fused and x.is_cuda and x.dtype == torch.bfloat16 and self.attn.head_dim == 64
+        return (self.use_fused and x.is_cuda and x.dtype == torch.bfloat16 and self.attn.head_dim in ops.QKNORM_HEAD_DIMS
                 and all(isinstance(n, nn.RMSNorm) and n.weight is not None and not n.weight.requires_grad for n in norms)
                 and all(_linear_ok(l) for l in self._linears())
                 and self.attn.attn_dropout.p == 0 and self.attn.proj_dropout.p == 0 and self.mlp.ffn_dropout.p == 0)

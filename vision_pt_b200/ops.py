@@ -362,6 +362,10 @@ def nf4_lora_linear(x, w, bias=None, lora_down=None, lora_up=None, scale: float 
 
 
 # ------------------------------------------------------------------------------------------------------- attention
+HEAD_DIMS = (64, 32, 80, 96, 128)     # 64 = tcgen05 kernels (JiT-B/L, SDXL); the rest run attention_simple.cuh (JiT-H: 80)
+QKNORM_HEAD_DIMS = (64, 80, 96, 128)
+
+
 def _at(t: torch.Tensor) -> AttnTensorC:
     # logical layout (B, H, L, 64); any strides with a contiguous last dimension
     return AttnTensorC(_p(t), t.stride(0), t.stride(2), t.stride(1))
@@ -370,37 +374,39 @@ def _at(t: torch.Tensor) -> AttnTensorC:
 def _attn_ok(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.bfloat16:
         raise TypeError("attention kernels run in bfloat16")
-    if t.shape[-1] != 64:
-        raise NotImplementedError("the sm_100a attention kernels are built for head_dim 64")
+    if t.shape[-1] not in HEAD_DIMS:
+        raise NotImplementedError(f"attention kernels exist for head_dim {HEAD_DIMS} (64: tcgen05; the others: CUDA cores)")
     if t.stride(3) != 1 or any(s % 8 for s in t.stride()[:3]) or t.data_ptr() % 16:
         t = t.contiguous()
     return t
 
 
 def attn_fwd_raw(q, k, v, seqlens_k, scale: float):
-    """q,k,v: [B,H,L,64] views.  Returns (o [B,H,Lq,64] view over token-major memory, lse2 [B,H,Lq rounded up to 128])."""
-    B, H, Lq, _ = q.shape
+    """q,k,v: [B,H,L,hd] views.  Returns (o [B,H,Lq,hd] view over token-major memory, lse2 [B,H,Lq rounded up to 128])."""
+    B, H, Lq, hd = q.shape
     Lk = k.shape[2]
-    o = torch.empty((B, Lq, H, 64), dtype=torch.bfloat16, device=q.device).permute(0, 2, 1, 3)
+    o = torch.empty((B, Lq, H, hd), dtype=torch.bfloat16, device=q.device).permute(0, 2, 1, 3)
     lse2 = torch.empty((B, H, (Lq + 127) // 128 * 128), dtype=torch.float32, device=q.device)
     tq, tk, tv, to = _at(q), _at(k), _at(v), _at(o)
-    _lib.call("vpt_attn_fwd", C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, _p(seqlens_k),
+    _lib.call("vpt_attn_fwd", C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, hd, _p(seqlens_k),
               float(scale), _p(lse2), _stream())
     return o, lse2
 
 
 def attn_bwd_raw(q, k, v, o, d_o, lse2, seqlens_k, scale: float):
-    """Returns (dq fp32, dk bf16, dv bf16), each a [B,H,L,64] view over token-major memory."""
-    B, H, Lq, _ = q.shape
+    """Returns (dq fp32, dk bf16, dv bf16), each a [B,H,L,hd] view over token-major memory."""
+    B, H, Lq, hd = q.shape
     Lk = k.shape[2]
     dev = q.device
-    dq = torch.zeros((B, Lq, H, 64), dtype=torch.float32, device=dev).permute(0, 2, 1, 3)
-    dk = torch.empty((B, Lk, H, 64), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
-    dv = torch.empty((B, Lk, H, 64), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
+    dq = torch.zeros((B, Lq, H, hd), dtype=torch.float32, device=dev).permute(0, 2, 1, 3)
+    dk = torch.empty((B, Lk, H, hd), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
+    dv = torch.empty((B, Lk, H, hd), dtype=torch.bfloat16, device=dev).permute(0, 2, 1, 3)
     delta = torch.empty((B, H, (Lq + 127) // 128 * 128), dtype=torch.float32, device=dev)
     ts = [_at(t) for t in (q, k, v, o, d_o, dq, dk, dv)]
-    _lib.call("vpt_attn_bwd", *[C.byref(t) for t in ts], B, H, Lq, Lk, _p(seqlens_k), float(scale), _p(lse2), _p(delta),
+    _lib.call("vpt_attn_bwd", *[C.byref(t) for t in ts], B, H, Lq, Lk, hd, _p(seqlens_k), float(scale), _p(lse2), _p(delta),
               _stream())
+    if hd != 64:
+        _lib.add_launches(2)          # delta + dQ + dK + dV kernels on the CUDA-core route
     return dq, dk, dv
 
 
@@ -482,17 +488,19 @@ def rms_norm(x, weight, eps: float = 1e-6):
 
 def qknorm_rope_fwd_raw(x2, w, cos_sin, H: int, L: int, eps: float):
     tokens = x2.shape[0]
-    y = torch.empty((tokens, H * 64), dtype=torch.bfloat16, device=x2.device)
-    _lib.call("vpt_qknorm_rope_fwd", _p(x2), _p(w), _p(cos_sin), _p(y), tokens, H, L,
-              x2.stride(0) if tokens > 1 else H * 64, H * 64, float(eps), _stream())
+    hd = x2.shape[1] // H
+    y = torch.empty((tokens, H * hd), dtype=torch.bfloat16, device=x2.device)
+    _lib.call("vpt_qknorm_rope_fwd", _p(x2), _p(w), _p(cos_sin), _p(y), tokens, H, L, hd,
+              x2.stride(0) if tokens > 1 else H * hd, H * hd, float(eps), _stream())
     return y
 
 
 def qknorm_rope_bwd_raw(dy2, x2, w, cos_sin, H: int, L: int, eps: float, dw=None):
     tokens = x2.shape[0]
-    dx = torch.empty((tokens, H * 64), dtype=torch.bfloat16, device=x2.device)
+    hd = x2.shape[1] // H
+    dx = torch.empty((tokens, H * hd), dtype=torch.bfloat16, device=x2.device)
     _lib.call("vpt_qknorm_rope_bwd", _p(dy2), int(dy2.dtype == torch.float32), _p(x2), _p(w), _p(cos_sin), _p(dx), _p(dw),
-              tokens, H, L, dy2.stride(0) if tokens > 1 else H * 64, x2.stride(0) if tokens > 1 else H * 64, H * 64,
+              tokens, H, L, hd, dy2.stride(0) if tokens > 1 else H * hd, x2.stride(0) if tokens > 1 else H * hd, H * hd,
               float(eps), _stream())
     return dx
 
@@ -518,7 +526,7 @@ class QKNormRopeFn(torch.autograd.Function):
         if dy2.dtype not in (torch.float32, torch.bfloat16):
             dy2 = dy2.to(torch.bfloat16)
         dy2 = dy2.contiguous()
-        dw = torch.zeros(64, dtype=torch.float32, device=x2.device) if wg else None
+        dw = torch.zeros(hd, dtype=torch.float32, device=x2.device) if wg else None
         dx = qknorm_rope_bwd_raw(dy2, x2, wb, cos_sin, H, L, eps, dw)
         return dx.reshape(B, L, H, hd), (dw.to(wb.dtype) if dw is not None else None), None, None
 
