@@ -52,8 +52,9 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
                            int B, int H, int Lq, int Lk, const int* seqlens_k, float scale, const float* lse2,
                            float* delta, cudaStream_t stream) {
   CUtensorMap tq, tk, tv, tdo;
-  if (make_attn_tmap(&tq, q, B, H, Lq) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk) ||
-      make_attn_tmap(&tdo, d_o, B, H, Lq))
+  // Q / dO travel as 64-query sub-tiles (one ring of two slots per sub-tile kind), K / V as 128-key tiles
+  if (make_attn_tmap(&tq, q, B, H, Lq, 64) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk) ||
+      make_attn_tmap(&tdo, d_o, B, H, Lq, 64))
     return 1;
   AttnDeltaParams dp{};
   dp.B = B; dp.H = H; dp.Lq = Lq;
