@@ -25,328 +25,288 @@ struct AttnFwdParams {
 };
 
 struct AttnFwdSmem {
-  static constexpr int kQ = 0;
-  static constexpr int kK = 16384;            // 2 stages
-  static constexpr int kV = kK + 2 * 16384;   // 2 stages
-  static constexpr int kP = kV + 2 * 16384;   // P_A, P_B: [128 queries x 64 keys] bf16 each
-  static constexpr int kStat = kP + 32768;    // (m, l) of both streams per query row, [2 item parities][2 streams][128] float2
-  static constexpr int kBars = kStat + 4096;
-  static constexpr int kNumBars = 15;         // q_full q_empty kv_full[2] kv_empty[2] s_full[2] p_full[2] pv_done[2] o_free s_free[2]
-  static constexpr int kTmemSlot = kBars + kNumBars * 8;
-  static constexpr int kTotal = kTmemSlot + 16;   // no alignment slack: two CTAs must fit in one SM's 228 KB
+  // per stream (X = 0, 1): Q[2] (item double buffer), K[2], V[2] (key-block stages): 6 x 16 KB
+  static constexpr int kStream = 6 * 16384;
+  static constexpr int kQ = 0, kK = 2 * 16384, kV = 4 * 16384;
+  static constexpr int kBars = 2 * kStream;
+  // per stream: q_full[2] q_empty[2] kv_full[2] kv_empty[2] s_full p_full pv_done  (11)
+  static constexpr int kBarsPerStream = 11;
+  static constexpr int kTmemSlot = kBars + 2 * kBarsPerStream * 8;
+  static constexpr int kTotal = kTmemSlot + 16;   // no alignment slack: the dynamic segment starts 1024B-aligned
 };
 
-// Persistent CTAs (one per SM) walk work items (128-query tile, head, sample).  Every 128-key block is split into two
-// 64-key halves A and B, each an independent online-softmax stream with its own warpgroup, running maximum, row sum and O
-// accumulator (S_A, S_B, O_A, O_B: 64 TMEM columns each); the tensor core ping-pongs between the streams, and the two
-// partial results are merged at the end of the item (O = (O_A w_A + O_B w_B) / (l_A w_A + l_B w_B)).  A stream rescales
-// its accumulator only when its maximum grows by more than 2^8 (P stays <= 256: exact in the fp32 sums, safe in bf16).
-// Sequences here are short (330 tokens = 2.6 key blocks per item), so the loop over items matters: the next item's Q / K / V
-// are already in flight while the current one finishes, instead of one CTA launch + pipeline fill per 2.6 blocks.
-// Warps: 0 TMA producer, 1 MMA issuer + TMEM allocator, 2-5 stream A, 6-9 stream B.
-__global__ void __launch_bounds__(320, 1)
+// Persistent CTAs (one per SM) run TWO independent streams, each walking its own work items (128-query tile, head,
+// sample) with its own softmax warpgroup, MMA-issuing warp, TMA producer warp, Q / K / V buffers and TMEM columns:
+//
+//   tensor core    S = Q K_j^T  (128 queries x <=128 keys, fp32, TMEM)
+//   warpgroup      pass 1: row maximum over S;  pass 2: P = exp2(S c - m) -> bf16 written over the S columns it came
+//                  from (A operand of the next MMA, never through shared memory), row sums in registers
+//   tensor core    O += P V_j (A from TMEM), then S of the next key block (or of the stream's next item)
+//   warpgroup      end of item: O / l -> bf16 -> global, lse2
+//
+// The streams never exchange anything, so one stream's exponentials (the MUFU is the binding unit at head_dim 64:
+// 128 x 128 ex2 per key block = 1024 cycles of the SM's 16 ex2 / clock, against 512 tensor cycles) hide the other
+// stream's MMAs, epilogue and item turn-over; two issuing warps because tcgen05.mma issue blocks while the pipe is busy
+// (tools/probes/umma_rate.cu).  The previous form (one item per CTA, key halves as streams, merge at the end) spent 43 % of
+// its time in per-item merge / turn-over at 2.6 key blocks per item (profiles/r1l_attn_fwd_phases.txt).
+// A stream rescales its accumulator only when its maximum grows by more than 2^8 (P stays <= 256: exact in the fp32
+// sums, safe in bf16).
+// Warps: 0 / 2 TMA producers of stream A / B (2 also allocates TMEM), 1 / 3 MMA issuers, 4-7 softmax A, 8-11 softmax B.
+__global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   using S = AttnFwdSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need a 1024B-aligned base
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
-  uint64_t* q_full = bars;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;    // [2]
-  uint64_t* kv_empty = bars + 4;   // [2]
-  uint64_t* s_full = bars + 6;     // [2] A, B
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* pv_done = bars + 10;   // [2]
-  uint64_t* o_free = bars + 12;    // the merge has read O_A / O_B: the next item may overwrite them
-  uint64_t* s_free = bars + 13;    // [2] the stream has S_X in registers: the next S_X may be computed while it works
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
-  float2* s_stat = reinterpret_cast<float2*>(smem + S::kStat);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int X = warp < 4 ? (warp >> 1) : ((warp - 4) >> 2);          // stream of this warp
+  uint8_t* sm = smem + X * S::kStream;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars) + X * S::kBarsPerStream;
+  uint64_t* q_full = bars;          // [2]
+  uint64_t* q_empty = bars + 2;     // [2]
+  uint64_t* kv_full = bars + 4;     // [2]
+  uint64_t* kv_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;      // S_j is complete (and with it every earlier MMA of the stream)
+  uint64_t* p_full = bars + 9;      // P_j is in TMEM
+  uint64_t* pv_done = bars + 10;    // the item's last O += P V is complete
+
   const int nqt = (p.Lq + kAttnTile - 1) / kAttnTile;
   const int num_items = nqt * p.H * p.B;
+  const int first_item = blockIdx.x * 2 + X, item_stride = gridDim.x * 2;
   auto klen_of = [&](int item) {
     if (item >= num_items) return 0;
     if (p.seqlens_k == nullptr) return p.Lk;
     const int kl = __ldg(p.seqlens_k + item / (nqt * p.H));
     return kl < p.Lk ? kl : p.Lk;
   };
-  // keys of block j that stream X covers, rounded up to the UMMA granularity (0 = none)
-  auto sub_n = [](int klen, int j, int X) {
-    const int valid = min(128, klen - j * 128) - X * 64;
-    return valid <= 0 ? 0 : min(64, (valid + 15) & ~15);
-  };
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&pv_done[s], 1);
-      mbar_init(&s_free[s], 128);
+    uint64_t* all = reinterpret_cast<uint64_t*>(smem + S::kBars);
+    for (int x = 0; x < 2; ++x) {
+      uint64_t* bx = all + x * S::kBarsPerStream;
+      for (int i = 0; i < 9; ++i) mbar_init(&bx[i], 1);
+      mbar_init(&bx[9], 128);
+      mbar_init(&bx[10], 1);
     }
-    mbar_init(o_free, 8);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;   // S_A 0, S_B 64, O_A 128, O_B 192
+  const uint32_t tS = tmem_base + X * 256, tO = tS + 128;   // per stream: S / P 0..127, O 128..191
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 2) {
+    // ============================================================ TMA producer of stream X
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      uint32_t jj = 0, itn = 0;
-      int klen = klen_of(blockIdx.x);
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn) {
+      uint32_t it = 0, jj = 0;
+      for (int item = first_item; item < num_items; item += item_stride, ++it) {
         const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
-        const int nblk = (klen + kAttnTile - 1) / kAttnTile;
-        klen = klen_of(item + gridDim.x);
-        mbar_wait(q_empty, (itn & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, 16384);
-        tma_load_4d(&tmQ, q_full, smem + S::kQ, 0, qt * kAttnTile, h, b);
+        const int nblk = (klen_of(item) + kAttnTile - 1) / kAttnTile;
+        const uint32_t qb = it & 1;
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], 16384);
+        tma_load_4d(&tmQ, &q_full[qb], sm + S::kQ + qb * 16384, 0, qt * kAttnTile, h, b);
         for (int j = 0; j < nblk; ++j, ++jj) {
           const uint32_t s = jj & 1;
           mbar_wait(&kv_empty[s], ((jj >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 32768);
-          tma_load_4d(&tmK, &kv_full[s], smem + S::kK + s * 16384, 0, j * kAttnTile, h, b);
-          tma_load_4d(&tmV, &kv_full[s], smem + S::kV + s * 16384, 0, j * kAttnTile, h, b);
+          tma_load_4d(&tmK, &kv_full[s], sm + S::kK + s * 16384, 0, j * kAttnTile, h, b);
+          tma_load_4d(&tmV, &kv_full[s], sm + S::kV + s * 16384, 0, j * kAttnTile, h, b);
         }
       }
     }
-  } else if (warp == 1) {
-    // converged warp, one elected lane issues (operands stay in uniform registers)
-    constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O_X += P_X V_X  (V is MN-major)
-    const uint32_t smem_base = smem_u32(smem);
+    __syncwarp();
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuer of stream X (converged warp, one elected lane)
+    constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O += P V  (V is MN-major)
+    const uint32_t sbase = smem_u32(sm);
     const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
     const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);
-    const uint64_t qd = dK_ + ((smem_base + S::kQ) >> 4);
-    uint32_t jj = 0, itn = 0;
-    uint32_t cnt[2] = {0, 0};                     // P tiles consumed per stream
-    uint32_t s_issued[2] = {0, 0};                // S_X MMAs issued per stream (each is answered by one s_free phase)
-    int klen = klen_of(blockIdx.x);
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn) {
-      const int nblk = (klen + kAttnTile - 1) / kAttnTile;
-      const int kl = klen;
-      klen = klen_of(item + gridDim.x);
-      // S_X = Q K_X^T for block j.  It overwrites the stream's single S buffer, which is free as soon as the stream has
-      // LOADED the previous S_X into registers (s_free) -- long before its exponentials are done -- so the next block's
-      // scores are already waiting when the stream comes back for them.
-      auto issue_s = [&](int j, uint32_t s, uint32_t sp, int X) {
-        const int n = sub_n(kl, j, X);
-        if (n == 0) return;
-        if (s_issued[X] > 0) mbar_wait(&s_free[X], (s_issued[X] - 1) & 1);
-        ++s_issued[X];
-        mbar_wait(&kv_full[s], sp);
+    uint32_t it = 0, jj = 0, pc = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++it) {
+      const int kl = klen_of(item);
+      const int nblk = (kl + kAttnTile - 1) / kAttnTile;
+      const uint32_t qb = it & 1;
+      const uint64_t qd = dK_ + ((sbase + S::kQ + qb * 16384) >> 4);
+      // S = Q K_j^T; the S / P columns are free: the stream's previous O += P V was issued before this (in-order pipe)
+      auto issue_s = [&](int j, uint32_t jn) {
+        const uint32_t s = jn & 1;
+        const int valid = min(128, kl - j * 128);
+        const int n = (valid + 15) & ~15;
+        mbar_wait(&kv_full[s], (jn >> 1) & 1);
         tc_fence_after_sync();
-        const uint64_t kd = dK_ + ((smem_base + S::kK + s * 16384 + X * 8192) >> 4);
+        const uint64_t kd = dK_ + ((sbase + S::kK + s * 16384) >> 4);
         const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
         if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS + X * 64, qd + 2 * k, kd + 2 * k, idesc, k != 0);
-          umma_commit(&s_full[X]);
+          for (int k = 0; k < 4; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, idesc, k != 0);
+          umma_commit(s_full);
         }
         __syncwarp();
       };
-      mbar_wait(q_full, itn & 1);
-      if (nblk > 0) {
-        issue_s(0, jj & 1, (jj >> 1) & 1, 0);
-        issue_s(0, jj & 1, (jj >> 1) & 1, 1);
-      }
-      if (nblk <= 1) {                             // every S MMA of this item is issued: Q may be replaced
-        if (elect_one_sync()) umma_commit(q_empty);
-        __syncwarp();
-      }
-      bool first[2] = {true, true};
+      mbar_wait(&q_full[qb], (it >> 1) & 1);
+      if (nblk > 0) issue_s(0, jj);
       for (int j = 0; j < nblk; ++j, ++jj) {
         const uint32_t s = jj & 1;
-        const uint64_t vd = dMN + ((smem_base + S::kV + s * 16384) >> 4);
-        if (j + 1 < nblk) {
-          issue_s(j + 1, (jj + 1) & 1, ((jj + 1) >> 1) & 1, 0);
-          issue_s(j + 1, (jj + 1) & 1, ((jj + 1) >> 1) & 1, 1);
-          if (j + 2 == nblk) {
-            if (elect_one_sync()) umma_commit(q_empty);
-            __syncwarp();
-          }
-        }
+        const uint64_t vd = dMN + ((sbase + S::kV + s * 16384) >> 4);
+        const int valid = min(128, kl - j * 128);
+        const int n = (valid + 15) & ~15;
+        mbar_wait(p_full, pc & 1);
+        ++pc;
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          if (n == 128) {
 #pragma unroll
-        for (int X = 0; X < 2; ++X) {
-          const int n = sub_n(kl, j, X);
-          if (n > 0) {
-            mbar_wait(&p_full[X], cnt[X] & 1);
-            ++cnt[X];
-            if (first[X] && itn > 0 && X == 0) mbar_wait(o_free, (itn - 1) & 1);   // previous item's merge has read O
-            tc_fence_after_sync();
-            const uint64_t pd = dK_ + ((smem_base + S::kP + X * 16384) >> 4);
-            const uint32_t acc0 = first[X] ? 0u : 1u;
-            first[X] = false;
-            if (elect_one_sync()) {
-              for (int k = 0; k < n / 16; ++k) umma_ss(tO + X * 64, pd + 2 * k, vd + (X * 4 + k) * 128, kIdO, acc0 | (k != 0));
-              umma_commit(&pv_done[X]);
-            }
-            __syncwarp();
+            for (int k = 0; k < 8; ++k) umma_ts(tO, tS + k * 8, vd + k * 128, kIdO, (j | k) != 0);
+          } else {
+            for (int k = 0; k < n / 16; ++k) umma_ts(tO, tS + k * 8, vd + k * 128, kIdO, (j | k) != 0);
           }
-          if (X == 1) {
-            if (elect_one_sync()) umma_commit(&kv_empty[s]);
-            __syncwarp();
-          }
+          umma_commit(&kv_empty[s]);
         }
+        __syncwarp();
+        if (j + 1 < nblk) issue_s(j + 1, jj + 1);
       }
+      if (elect_one_sync()) {
+        umma_commit(pv_done);
+        umma_commit(&q_empty[qb]);     // every S MMA of the item is complete
+      }
+      __syncwarp();
     }
   } else {
-    // ============================================================ softmax streams: A = warps 2-5, B = warps 6-9
-    const int X = (warp - 2) >> 2;
+    // ============================================================ softmax warpgroup of stream X
     const int qd = warp & 3;                      // TMEM lane quarter
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t p_row = smem_u32(smem + S::kP) + X * 16384 + row * 128;
-    const int rin = row & 7;
-    uint32_t cx = 0;
-    int klen_next = klen_of(blockIdx.x), klen_next2 = klen_of(blockIdx.x + gridDim.x);
-    uint32_t itn_s = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itn_s) {
+    uint32_t cx = 0, it = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++it) {
       const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
-      const int klen = klen_next;
-      klen_next = klen_next2;
-      klen_next2 = klen_of(item + 2 * gridDim.x);   // fetched two items ahead of its first use
+      const int klen = klen_of(item);
       const int nblk = (klen + kAttnTile - 1) / kAttnTile;
       float m_ref = -INFINITY, l_run = 0.f;
-      bool first = true;
       for (int j = 0; j < nblk; ++j) {
-        const int n = sub_n(klen, j, X);
-        if (n == 0) continue;
-        mbar_wait(&s_full[X], cx & 1);
+        const int nvalid = min(128, klen - j * 128);          // < 128 only in the last block
+        const int nch = (nvalid + 31) >> 5;                   // 32-column chunks that hold keys
+        mbar_wait(s_full, cx & 1);
+        ++cx;
         tc_fence_after_sync();
-        const int nvalid = min(64, klen - j * 128 - X * 64);     // < n only in the last block
-        uint32_t v[64];
-        tmem_ld32(tS + X * 64 + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        if (n > 32) tmem_ld32(tS + X * 64 + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tmem_wait_ld();
-        tc_fence_before_sync();
-        mbar_arrive(&s_free[X]);                    // the scores are in registers: the tensor core may write the next S_X
-        if (nvalid < 64) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= nvalid) v[i] = 0xff800000u;   // -inf: padded / masked keys
-        }
+        // ---- pass 1: row maximum
         float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + lane_off + c * 32, v);
+          tmem_wait_ld();
+          const int lim = nvalid - c * 32;
+          if (lim < 32) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; ++i)
+              if (i >= lim) v[i] = 0xff800000u;   // -inf: padded / masked keys
+          }
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, __uint_as_float(v[i]));
+            m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        }
         mx *= p.scale_log2;                         // scale > 0: the maximum commutes with the scaling
         // lazy rescale: keep the reference maximum unless the true one outgrew it by 2^8
         const bool grow = mx > m_ref + 8.f;
         const float m_new = grow ? mx : m_ref;
-        if (cx > 0) {
-          // P_X of the previous block (possibly the previous item's) is consumed before it is overwritten, and O_X is
-          // final for it before it is rescaled
-          mbar_wait(&pv_done[X], (cx - 1) & 1);
-          tc_fence_after_sync();
-        }
-        if (!first && __any_sync(0xffffffffu, grow)) {
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          // O is final for block j-1: s_full of block j was committed after that MMA
           const float alpha = grow ? fast_exp2(m_ref - m_new) : 1.f;
           l_run *= alpha;
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld32(tO + X * 64 + lane_off + c * 32, o);
+            tmem_ld32(tO + lane_off + c * 32, o);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + X * 64 + lane_off + c * 32, o);
+            tmem_st32(tO + lane_off + c * 32, o);
           }
-          tmem_wait_st();
         }
-        first = false;
         m_ref = m_new;
         const float neg_m = -m_ref;
-        float psum = 0.f;
+        // ---- pass 2: P = exp2(S c - m) -> bf16 over the S columns (chunk c's 16 P columns lie inside columns already read)
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + lane_off + c * 32, v);
+          tmem_wait_ld();
+          const int lim = nvalid - c * 32;
+          if (lim < 32) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          uint32_t pk[4];
+            for (int i = 0; i < 32; ++i)
+              if (i >= lim) v[i] = 0xff800000u;
+          }
+          uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.scale_log2, neg_m));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.scale_log2, neg_m));
-            psum += p0 + p1;
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * e]), p.scale_log2, neg_m));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * e + 1]), p.scale_log2, neg_m));
+            ps0 += p0;
+            ps1 += p1;
             pk[e] = pack_bf16x2(p0, p1);
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((g ^ rin) * 16)), "r"(pk[0]), "r"(pk[1]),
-                       "r"(pk[2]), "r"(pk[3])
-                       : "memory");
+          tmem_st16(tS + lane_off + c * 16, pk);
         }
-        l_run += psum;
-        ++cx;
-        fence_proxy_async_smem();
+        l_run += ps0 + ps1;
+        tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&p_full[X]);
+        mbar_arrive(p_full);
       }
-      // ---- merge the two streams
-      if (!first) {
-        mbar_wait(&pv_done[X], (cx - 1) & 1);
-        tc_fence_after_sync();
-      }
-      // one barrier per item: the statistics are double-buffered by item parity (a thread is never more than one
-      // item ahead of another, since every item has this exchange)
-      float2* stat = s_stat + (itn_s & 1) * 256;
-      stat[X * 128 + row] = make_float2(m_ref, l_run);
-      named_bar_sync(1, 256);
-      const float2 sa = stat[row], sb = stat[128 + row];
-      const float m = fmaxf(sa.x, sb.x);
-      const float wa = sa.y > 0.f ? fast_exp2(sa.x - m) : 0.f;     // a stream without keys has l = 0
-      const float wb = sb.y > 0.f ? fast_exp2(sb.x - m) : 0.f;
-      const float l = sa.y * wa + sb.y * wb;
-      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      // ---- end of item: O / l -> bf16 -> global
+      mbar_wait(pv_done, it & 1);
+      tc_fence_after_sync();
+      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
       const int q = qt * kAttnTile + row;
-      if (X == 0)   // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
-        p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
-            q < p.Lq ? (l > 0.f ? m + log2f(l) : -INFINITY) : INFINITY;
-      // stream X writes output columns X*32 .. X*32+31, reading that slice of both accumulators
-      const bool has_a = klen > 0, has_b = klen > 64;               // CTA-uniform: the .sync.aligned loads stay convergent
-      uint32_t oa[32], ob[32];
-      if (has_a) tmem_ld32(tO + lane_off + X * 32, oa);
-      if (has_b) tmem_ld32(tO + 64 + lane_off + X * 32, ob);
-      tmem_wait_ld();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-      if (q < p.Lq) {
-        __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh + X * 32;
-        const float fa = wa * inv_l, fb = wb * inv_l;
+      // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
+      p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
+          q < p.Lq ? (l_run > 0.f ? m_ref + log2f(l_run) : -INFINITY) : INFINITY;
+      __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        if (nblk > 0) {                            // CTA-stream-uniform: the .sync.aligned load stays convergent
+          tmem_ld32(tO + lane_off + c * 32, o);
+          tmem_wait_ld();
+        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x0 = 0.f, x1 = 0.f;
-            if (has_a) {
-              x0 = __uint_as_float(oa[g * 8 + 2 * e]) * fa;
-              x1 = __uint_as_float(oa[g * 8 + 2 * e + 1]) * fa;
-            }
-            if (has_b) {
-              x0 = fmaf(__uint_as_float(ob[g * 8 + 2 * e]), fb, x0);
-              x1 = fmaf(__uint_as_float(ob[g * 8 + 2 * e + 1]), fb, x1);
-            }
-            w[e] = pack_bf16x2(x0, x1);
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (q < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w[e] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * e]) * inv_l, __uint_as_float(o[g * 8 + 2 * e + 1]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
-          *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+      // the accumulator is read: order those loads before the stream's next P store / p_full, after which the issuer
+      // overwrites O (accumulate = 0 on the next item's first block)
+      tc_fence_before_sync();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- backward pre-pass

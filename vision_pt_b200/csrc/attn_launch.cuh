@@ -41,8 +41,9 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
     attr = true;
   }
   const int items = ((Lq + kAttnTile - 1) / kAttnTile) * H * B;
+  const int ctas = (items + 1) / 2;              // two streams (items) per CTA
   const int slots = sm_count();
-  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(items < slots ? items : slots), dim3(320), AttnFwdSmem::kTotal, stream, tq, tk, tv, p));
+  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(ctas < slots ? ctas : slots), dim3(384), AttnFwdSmem::kTotal, stream, tq, tk, tv, p));
   return 0;
 }
 
