@@ -14,6 +14,10 @@ namespace vpt {
 
 constexpr int kAttnHD = 64;
 constexpr int kAttnTile = 128;
+#ifndef VPT_ATTN_POLY_EVERY
+#define VPT_ATTN_POLY_EVERY 2
+#endif
+constexpr int kAttnPolyEvery = VPT_ATTN_POLY_EVERY;   // one exponential in 2 * kAttnPolyEvery goes to the FMA pipe
 
 struct AttnFwdParams {
   int B, H, Lq, Lk;
@@ -24,11 +28,25 @@ struct AttnFwdParams {
   float* lse2;                 // [B, H, Lq rounded up to 128]  log2-domain logsumexp of scale*S; +inf in the padding
 };
 
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 polynomial on [-0.5, 0.5], max relative error 7.7e-5: far inside the
+// bf16 rounding of P).  The forward's exponentials are bound by the MUFU (16 ex2 / clock / SM); moving one in four to the
+// FMA / ALU pipes balances the two (x must be <= ~100: here x <= 8 by the lazy-rescale rule).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                // 1.5 * 2^23: rint(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);          // in [-0.5, 0.5]
+  float r = fmaf(f, 0.05508868396282196f, 0.24260404706001282f);
+  r = fmaf(r, f, 0.6932762265205383f);
+  r = fmaf(r, f, 0.9999289512634277f);
+  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));   // * 2^rint(x)
+}
+
 struct AttnFwdSmem {
   // per stream (X = 0, 1): Q[2] (item double buffer), K[2], V[2] (key-block stages): 6 x 16 KB
   static constexpr int kStream = 6 * 16384;
   static constexpr int kQ = 0, kK = 2 * 16384, kV = 4 * 16384;
-  static constexpr int kBars = 2 * kStream;
+  static constexpr int kOut = 2 * kStream;        // 8 softmax warps x one slab of [32 rows x 128 B] (output tile -> TMA store)
+  static constexpr int kBars = kOut + 8 * 4096;
   // per stream: q_full[2] q_empty[2] kv_full[2] kv_empty[2] s_full p_full pv_done  (11)
   static constexpr int kBarsPerStream = 11;
   static constexpr int kTmemSlot = kBars + 2 * kBarsPerStream * 8;
@@ -42,7 +60,7 @@ struct AttnFwdSmem {
 //   warpgroup      pass 1: row maximum over S;  pass 2: P = exp2(S c - m) -> bf16 written over the S columns it came
 //                  from (A operand of the next MMA, never through shared memory), row sums in registers
 //   tensor core    O += P V_j (A from TMEM), then S of the next key block (or of the stream's next item)
-//   warpgroup      end of item: O / l -> bf16 -> global, lse2
+//   warpgroup      end of item: O / l -> bf16 -> 128B-swizzled slab -> TMA store (tmO: box {64, 32}), lse2
 //
 // The streams never exchange anything, so one stream's exponentials (the MUFU is the binding unit at head_dim 64:
 // 128 x 128 ex2 per key block = 1024 cycles of the SM's 16 ex2 / clock, against 512 tensor cycles) hide the other
@@ -54,7 +72,7 @@ struct AttnFwdSmem {
 // Warps: 0 / 2 TMA producers of stream A / B (2 also allocates TMEM), 1 / 3 MMA issuers, 4-7 softmax A, 8-11 softmax B.
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnFwdParams p) {
   using S = AttnFwdSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -133,6 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
     const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);
     uint32_t it = 0, jj = 0, pc = 0;
+    PROF_DECL(8)
     for (int item = first_item; item < num_items; item += item_stride, ++it) {
       const int kl = klen_of(item);
       const int nblk = (kl + kAttnTile - 1) / kAttnTile;
@@ -143,7 +162,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t s = jn & 1;
         const int valid = min(128, kl - j * 128);
         const int n = (valid + 15) & ~15;
+        PROF(0)
         mbar_wait(&kv_full[s], (jn >> 1) & 1);
+        PROF(1)
         tc_fence_after_sync();
         const uint64_t kd = dK_ + ((sbase + S::kK + s * 16384) >> 4);
         const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
@@ -153,15 +174,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(s_full);
         }
         __syncwarp();
+        PROF(2)
       };
+      PROF(0)
       mbar_wait(&q_full[qb], (it >> 1) & 1);
+      PROF(3)
       if (nblk > 0) issue_s(0, jj);
       for (int j = 0; j < nblk; ++j, ++jj) {
         const uint32_t s = jj & 1;
         const uint64_t vd = dMN + ((sbase + S::kV + s * 16384) >> 4);
         const int valid = min(128, kl - j * 128);
         const int n = (valid + 15) & ~15;
+        PROF(0)
         mbar_wait(p_full, pc & 1);
+        PROF(4)
         ++pc;
         tc_fence_after_sync();
         if (elect_one_sync()) {
@@ -174,6 +200,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(&kv_empty[s]);
         }
         __syncwarp();
+        PROF(5)
         if (j + 1 < nblk) issue_s(j + 1, jj + 1);
       }
       if (elect_one_sync()) {
@@ -182,12 +209,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       __syncwarp();
     }
+#ifdef VPT_BWD_PROF
+    PROF(0)
+    if (blockIdx.x == 0 && lane == 0)
+      printf("fwd mma%d: other %lld kv_full %lld S issue %lld q_full %lld p_full %lld PV issue %lld\n", X, prof_[0], prof_[1], prof_[2],
+             prof_[3], prof_[4], prof_[5]);
+#endif
   } else {
     // ============================================================ softmax warpgroup of stream X
     const int qd = warp & 3;                      // TMEM lane quarter
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    uint8_t* out_slab = smem + S::kOut + (warp - 4) * 4096;
+    const uint32_t out_row = smem_u32(out_slab) + lane * 128;
+    if (lane == 0) tma_prefetch_desc(&tmO);
     uint32_t cx = 0, it = 0;
+    PROF_DECL(8)
     for (int item = first_item; item < num_items; item += item_stride, ++it) {
       const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
       const int klen = klen_of(item);
@@ -196,10 +233,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < nblk; ++j) {
         const int nvalid = min(128, klen - j * 128);          // < 128 only in the last block
         const int nch = (nvalid + 31) >> 5;                   // 32-column chunks that hold keys
+        PROF(0)
         mbar_wait(s_full, cx & 1);
+        PROF(1)
         ++cx;
         tc_fence_after_sync();
-        // ---- pass 1: row maximum
+        // ---- pass 1: row maximum.  (Prefetching the next chunk's TMEM load while reducing this one needs the loop
+        // unrolled over two register buffers and measured slower: 68 vs 61 us.)
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
@@ -207,7 +247,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_ld32(tS + lane_off + c * 32, v);
           tmem_wait_ld();
           const int lim = nvalid - c * 32;
-          if (lim < 32) {
+          if (lim < 32) {                            // only the item's last chunk
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i >= lim) v[i] = 0xff800000u;   // -inf: padded / masked keys
@@ -220,6 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           mx = fmaxf(mx, fmaxf(m0, m1));
         }
+        PROF(2)
         mx *= p.scale_log2;                         // scale > 0: the maximum commutes with the scaling
         // lazy rescale: keep the reference maximum unless the true one outgrew it by 2^8
         const bool grow = mx > m_ref + 8.f;
@@ -238,6 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st32(tO + lane_off + c * 32, o);
           }
         }
+        PROF(3)
         m_ref = m_new;
         const float neg_m = -m_ref;
         // ---- pass 2: P = exp2(S c - m) -> bf16 over the S columns (chunk c's 16 P columns lie inside columns already read)
@@ -251,58 +293,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (lim < 32) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (i >= lim) v[i] = 0xff800000u;
+              if (i >= lim) v[i] = 0xff800000u;   // exp2(-inf) = 0 on both paths
           }
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * e]), p.scale_log2, neg_m));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * e + 1]), p.scale_log2, neg_m));
+            const float x0 = fmaf(__uint_as_float(v[2 * e]), p.scale_log2, neg_m);
+            const float x1 = fmaf(__uint_as_float(v[2 * e + 1]), p.scale_log2, neg_m);
+            const float p0 = fast_exp2(x0);
+            const float p1 = (e % kAttnPolyEvery == kAttnPolyEvery - 1) ? poly_exp2(x1) : fast_exp2(x1);
             ps0 += p0;
             ps1 += p1;
             pk[e] = pack_bf16x2(p0, p1);
           }
+          // chunk c's 16 P columns lie inside S columns [0, 32 c + 16): all read already
           tmem_st16(tS + lane_off + c * 16, pk);
         }
         l_run += ps0 + ps1;
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(p_full);
+        PROF(4)
       }
       // ---- end of item: O / l -> bf16 -> global
+      PROF(0)
       mbar_wait(pv_done, it & 1);
+      PROF(5)
       tc_fence_after_sync();
       const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
       const int q = qt * kAttnTile + row;
       // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
       p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
           q < p.Lq ? (l_run > 0.f ? m_ref + log2f(l_run) : -INFINITY) : INFINITY;
-      __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh;
+      if (lane == 0) tma_store_wait_read<0>();     // the previous item's store has read the slab
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
-        if (nblk > 0) {                            // CTA-stream-uniform: the .sync.aligned load stays convergent
+        if (nblk > 0) {                            // stream-uniform: the .sync.aligned load stays convergent
           tmem_ld32(tO + lane_off + c * 32, o);
           tmem_wait_ld();
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
-        if (q < p.Lq) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              w[e] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * e]) * inv_l, __uint_as_float(o[g * 8 + 2 * e + 1]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + (((c * 4 + g) ^ (lane & 7)) * 16)),
+                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l)),
+                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l)),
+                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l)),
+                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l))
+                       : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (qt * kAttnTile + qd * 32 < p.Lq)       // rows past Lq inside the box are clipped by the TMA unit
+          tma_store_4d(&tmO, out_slab, 0, qt * kAttnTile + qd * 32, h, b);
+        tma_store_commit();
       }
       // the accumulator is read: order those loads before the stream's next P store / p_full, after which the issuer
       // overwrites O (accumulate = 0 on the next item's first block)
       tc_fence_before_sync();
+      PROF(6)
     }
+#ifdef VPT_BWD_PROF
+    PROF(0)
+    if (blockIdx.x == 0 && lane == 0 && qd == 0)
+      printf("fwd wg%d : other %lld s_full %lld pass1 %lld rescale %lld pass2 %lld pv_done %lld epilogue %lld\n", X, prof_[0], prof_[1],
+             prof_[2], prof_[3], prof_[4], prof_[5], prof_[6]);
+#endif
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before_sync();
   __syncthreads();

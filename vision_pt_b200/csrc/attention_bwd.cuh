@@ -27,22 +27,9 @@
 // S^T / dP^T, 3 issues dV / dK / dQ, 4-7 warpgroup A, 8-11 warpgroup B, 12-15 drain (dQ per tile, dV / dK per item).
 // The last query tile is trimmed to a multiple of 16 queries (UMMA N / K granularity).
 #pragma once
-#ifdef VPT_BWD_PROF
-#include <cstdio>
-#endif
 #include "sm100.cuh"
 
 namespace vpt {
-
-// clock64 phase accounting of one thread per role (CTA 0), printed at the end of the kernel; a build with -DVPT_BWD_PROF
-// is for reading waits only (every probe costs ~100-200 cycles of its own)
-#ifdef VPT_BWD_PROF
-#define PROF_DECL(n) long long prof_[n] = {}; long long prof_t_ = clock64();
-#define PROF(k) { const long long t_ = clock64(); prof_[k] += t_ - prof_t_; prof_t_ = t_; }
-#else
-#define PROF_DECL(n)
-#define PROF(k)
-#endif
 
 struct AttnBwd2Params {
   int B, H, Lq, Lk;

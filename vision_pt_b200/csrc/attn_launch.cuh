@@ -24,10 +24,11 @@ inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int
 inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,
                            int H, int Lq, int Lk, const int* seqlens_k, float scale, float* lse2,
                            cudaStream_t stream) {
-  CUtensorMap tq, tk, tv;
-  if (make_attn_tmap(&tq, q, B, H, Lq) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk))
-    return 1;
   if ((o.sl | o.sh | o.sb) & 7) return fail("attention output strides must be multiples of 8 elements");
+  CUtensorMap tq, tk, tv, to;
+  if (make_attn_tmap(&tq, q, B, H, Lq) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk) ||
+      make_attn_tmap(&to, o, B, H, Lq, 32))
+    return 1;
   AttnFwdParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.seqlens_k = seqlens_k;
@@ -43,7 +44,7 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   const int items = ((Lq + kAttnTile - 1) / kAttnTile) * H * B;
   const int ctas = (items + 1) / 2;              // two streams (items) per CTA
   const int slots = sm_count();
-  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(ctas < slots ? ctas : slots), dim3(384), AttnFwdSmem::kTotal, stream, tq, tk, tv, p));
+  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(ctas < slots ? ctas : slots), dim3(384), AttnFwdSmem::kTotal, stream, tq, tk, tv, to, p));
   return 0;
 }
 

@@ -2,10 +2,23 @@
 // tcgen05 (UMMA issue / commit / TMEM alloc / TMEM load) and the shared-memory + instruction descriptors.
 // Everything is inline PTX; there is no CUTLASS dependency.
 #pragma once
+#ifdef VPT_BWD_PROF
+#include <cstdio>
+#endif
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+// clock64 phase accounting of one thread per role (CTA 0), printed at the end of the attention kernels; a build with
+// -DVPT_BWD_PROF is for reading waits only (every probe costs ~100-200 cycles of its own)
+#ifdef VPT_BWD_PROF
+#define PROF_DECL(n) long long prof_[n] = {}; long long prof_t_ = clock64();
+#define PROF(k) { const long long t_ = clock64(); prof_[k] += t_ - prof_t_; prof_t_ = t_; }
+#else
+#define PROF_DECL(n)
+#define PROF(k)
+#endif
 
 namespace vpt {
 
