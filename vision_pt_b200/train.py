@@ -137,22 +137,13 @@ class TrainHParams:
     ts_mean: float = -0.8
 
 
-class JiTQLoRATrainStep:
-    """One optimisation step of JiT NF4-QLoRA class-to-image training; `run()` replays a captured CUDA graph.
+class TrainState:
+    """What persists across steps and is shared by every (H, W) bucket of a run: the flat LoRA parameter / gradient
+    buffers, the AdamW moments and step counter, the frozen class-label table, and the CUDA-graph memory pool (only one
+    bucket's graph runs at a time, so all of them replay out of the same pool)."""
 
-    Inputs of a step (static device buffers the caller fills, e.g. by an async copy from pinned host memory):
-      image [B,3,H,W] fp16 (the dataset emits fp16, src/dataset/text_to_image.py:152), class_ids [B,T] int64,
-      attention_mask [B,T] int64 (leading ones).  Output: `loss` (fp32 device scalar of the last step)."""
-
-    def __init__(self, model: Denoiser, batch: int, height: int, width: int, num_classes: int = 1000,
-                 max_token_length: int = 64, hp: TrainHParams | None = None, process_group=None, use_graph: bool = True,
-                 seed: int = 0):
-        self.model = model
-        self.hp = hp or TrainHParams()
-        self.group = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    def __init__(self, model: Denoiser, num_classes: int = 1000):
         dev = next(model.parameters()).device
-        self.device = dev
         cfg = model.config
         gen = torch.Generator(device="cpu").manual_seed(1234)   # same class table on every rank (replicated, frozen)
         self.class_encoder = ClassEncoder(num_classes, cfg.context_dim)
@@ -166,6 +157,34 @@ class JiTQLoRATrainStep:
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.pool = None
+
+    def tensors(self) -> tuple[torch.Tensor, ...]:
+        return (self.flat.param, self.exp_avg, self.exp_avg_sq, self.step_t)
+
+
+class JiTQLoRATrainStep:
+    """One optimisation step of JiT NF4-QLoRA class-to-image training; `run()` replays a captured CUDA graph.
+
+    Inputs of a step (static device buffers the caller fills, e.g. by an async copy from pinned host memory):
+      image [B,3,H,W] fp16 (the dataset emits fp16, src/dataset/text_to_image.py:152), class_ids [B,T] int64,
+      attention_mask [B,T] int64 (leading ones).  Output: `loss` (fp32 device scalar of the last step)."""
+
+    def __init__(self, model: Denoiser, batch: int, height: int, width: int, num_classes: int = 1000,
+                 max_token_length: int = 64, hp: TrainHParams | None = None, process_group=None, use_graph: bool = True,
+                 seed: int | None = 0, state: TrainState | None = None):
+        self.model = model
+        self.hp = hp or TrainHParams()
+        self.group = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        dev = next(model.parameters()).device
+        self.device = dev
+        cfg = model.config
+        self.state = state if state is not None else TrainState(model, num_classes)
+        self.class_encoder = self.state.class_encoder
+        self.flat = self.state.flat
+        self.exp_avg, self.exp_avg_sq = self.state.exp_avg, self.state.exp_avg_sq
+        self.step_t, self.sumsq = self.state.step_t, self.state.sumsq
         self.image = torch.zeros((batch, cfg.in_channels, height, width), dtype=torch.float16, device=dev)
         self.class_ids = torch.full((batch, max_token_length), num_classes, dtype=torch.int64, device=dev)
         self.attention_mask = torch.zeros((batch, max_token_length), dtype=torch.int64, device=dev)
@@ -176,7 +195,8 @@ class JiTQLoRATrainStep:
         self.graph: torch.cuda.CUDAGraph | None = None
         self.graph_update: torch.cuda.CUDAGraph | None = None
         self.kernel_launches = 0
-        torch.manual_seed(seed)
+        if seed is not None:
+            torch.manual_seed(seed)
         model.train()
 
     # ------------------------------------------------------------------ the step itself (eager or under capture)
@@ -224,6 +244,8 @@ class JiTQLoRATrainStep:
         """Eager warm-up on a side stream (one-time kernel attribute setup, allocator growth, NCCL init), then capture.
         One graph at world size 1.  With data parallelism the step is two graphs (compute | update) with the NCCL
         all-reduce launched between them on the same stream: three launches per step, and no collective inside a capture."""
+        snap = [t.clone() for t in self.state.tensors()]         # the warm-up steps must not train: a new (H, W) bucket
+        rng = torch.cuda.get_rng_state(self.device)              # may be captured in the middle of a run (nor draw noise)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -233,16 +255,23 @@ class JiTQLoRATrainStep:
         torch.cuda.synchronize()
         before = ops._lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
+        pool = {} if self.state.pool is None else {"pool": self.state.pool}
         if self.world == 1:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, **pool):
                 self._step()
         else:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, **pool):
                 self._compute()
             self.graph_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
                 self._update(1.0 / self.world)
+        self.state.pool = self.graph.pool()
         self.kernel_launches = ops._lib.launch_count() - before
+        for t, t0 in zip(self.state.tensors(), snap):
+            t.copy_(t0)
+        self.flat.grad.zero_()
+        torch.cuda.set_rng_state(rng, self.device)
+        torch.cuda.synchronize()
 
     def run(self) -> torch.Tensor:
         if self.use_graph:
@@ -257,6 +286,106 @@ class JiTQLoRATrainStep:
             self._step()
             self.kernel_launches = ops._lib.launch_count() - before
         return self.loss
+
+
+class JiTQLoRATrainer:
+    """The caller-facing loop body for aspect-ratio-bucketed training (BASELINE.json configs[3]: (H, W) differs per step
+    and per rank; reference: src/dataset/aspect_ratio_bucket.py:20-60 feeding train/jit/class_to_image.py:166-243).
+
+    One `JiTQLoRATrainStep` (= one CUDA graph) per (batch, H, W) bucket, created on first use; all of them share the
+    LoRA parameters, gradients, AdamW state and graph memory pool of one `TrainState`.  `train_step` takes the host
+    batch exactly as the reference's dataloader yields it (image fp16 [B,3,H,W], class ids, mask), copies it to the
+    bucket's static buffers asynchronously and replays the graph; the returned loss is a device scalar (no sync).
+
+    Checkpoints: the adapter as safetensors with the reference's key names (`get_adapter_parameters`,
+    src/modules/peft/functional.py:114-125: `<path>.lora_down.weight`, `<path>.lora_up.weight`, `<path>.alpha`) and the
+    optimiser state (moments by the same names + the step counter) beside it, so a run resumes bit-exactly."""
+
+    def __init__(self, model: Denoiser, num_classes: int = 1000, max_token_length: int = 64,
+                 hp: TrainHParams | None = None, process_group=None, use_graph: bool = True, seed: int = 0):
+        self.model = model
+        self.num_classes, self.max_token_length = num_classes, max_token_length
+        self.hp = hp or TrainHParams()
+        self.group = process_group
+        self.use_graph = use_graph
+        self.state = TrainState(model, num_classes)
+        self.buckets: dict[tuple[int, int, int], JiTQLoRATrainStep] = {}
+        torch.manual_seed(seed)
+
+    def bucket(self, batch: int, height: int, width: int) -> JiTQLoRATrainStep:
+        key = (batch, height, width)
+        step = self.buckets.get(key)
+        if step is None:
+            step = JiTQLoRATrainStep(self.model, batch, height, width, self.num_classes, self.max_token_length, self.hp,
+                                     self.group, self.use_graph, seed=None, state=self.state)
+            self.buckets[key] = step
+        return step
+
+    def train_step(self, image: torch.Tensor, class_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        B, _, H, W = image.shape
+        step = self.bucket(B, H, W)
+        if step.use_graph and step.graph is None:
+            step.capture()                       # before the copies: warm-up must not consume this batch's buffers
+        step.image.copy_(image, non_blocking=True)
+        step.class_ids.copy_(class_ids, non_blocking=True)
+        step.attention_mask.copy_(attention_mask, non_blocking=True)
+        return step.run()
+
+    @property
+    def global_step(self) -> int:
+        return int(self.state.step_t.item())
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def _named_slices(self):
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        for p, off in zip(self.state.flat.params, self.state.flat.offsets):
+            yield names[id(p)], off, p
+
+    def adapter_state_dict(self) -> dict[str, torch.Tensor]:
+        from .modules.peft import get_adapter_parameters
+        return {k: v.detach().cpu().contiguous() for k, v in get_adapter_parameters(self.model).items()}
+
+    def save_checkpoint(self, directory: str) -> None:
+        import os
+
+        from safetensors.torch import save_file
+        os.makedirs(directory, exist_ok=True)
+        save_file(self.adapter_state_dict(), os.path.join(directory, "adapter.safetensors"),
+                  metadata={"format": "pt", "peft": "lora"})
+        opt = {"step": self.state.step_t.detach().cpu().clone()}
+        for name, off, p in self._named_slices():
+            n = p.numel()
+            opt[f"{name}.exp_avg"] = self.state.exp_avg[off:off + n].view_as(p).cpu().clone()
+            opt[f"{name}.exp_avg_sq"] = self.state.exp_avg_sq[off:off + n].view_as(p).cpu().clone()
+        save_file(opt, os.path.join(directory, "optimizer.safetensors"))
+        torch.save({"rng_cpu": torch.random.get_rng_state(), "rng_cuda": torch.cuda.get_rng_state(), "hp": vars(self.hp)},
+                   os.path.join(directory, "trainer_state.pt"))
+
+    def load_checkpoint(self, directory: str, strict: bool = True) -> None:
+        import os
+
+        from safetensors.torch import load_file
+        adapter = load_file(os.path.join(directory, "adapter.safetensors"))
+        opt_path = os.path.join(directory, "optimizer.safetensors")
+        opt = load_file(opt_path) if os.path.exists(opt_path) else None
+        with torch.no_grad():
+            for name, off, p in self._named_slices():
+                if name not in adapter:
+                    if strict:
+                        raise KeyError(f"adapter checkpoint has no '{name}'")
+                    continue
+                p.copy_(adapter[name].to(p.device, p.dtype))          # in place: the parameter is a view of the flat buffer
+                if opt is not None:
+                    n = p.numel()
+                    self.state.exp_avg[off:off + n].copy_(opt[f"{name}.exp_avg"].reshape(-1))
+                    self.state.exp_avg_sq[off:off + n].copy_(opt[f"{name}.exp_avg_sq"].reshape(-1))
+            if opt is not None:
+                self.state.step_t.copy_(opt["step"])
+        ts = os.path.join(directory, "trainer_state.pt")
+        if os.path.exists(ts):
+            st = torch.load(ts, weights_only=False)
+            torch.random.set_rng_state(st["rng_cpu"])
+            torch.cuda.set_rng_state(st["rng_cuda"])
 
 
 def synthetic_batch(batch: int, height: int, width: int, num_classes: int = 1000, max_token_length: int = 64,
