@@ -77,7 +77,7 @@ def attention_explicit(q, k, v, key_len=None, scale=None):
     scale = hd ** -0.5 if scale is None else scale
     s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
     if key_len is not None:
-        idx = torch.arange(k.shape[2]).view(1, 1, 1, -1)
+        idx = torch.arange(k.shape[2], device=s.device).view(1, 1, 1, -1)
         s = s.masked_fill(idx >= key_len.view(B, 1, 1, 1), float("-inf"))
     return torch.matmul(torch.softmax(s, dim=-1), v.float())
 

@@ -12,7 +12,10 @@ pytestmark = pytest.mark.gpu
                                            (2, 1, 200, 77, [77, 40]), (1, 2, 1100, 1100, [1093]),
                                            # SDXL TransformerBlock at D=1280 (20 heads of 64): self-attention over ~1024 latent
                                            # tokens and cross-attention to 77 / 231 text tokens (src/models/sdxl/denoiser.py:32-172)
-                                           (1, 20, 1056, 1056, None), (2, 20, 1024, 231, None), (1, 10, 2112, 77, None)])
+                                           (1, 20, 1056, 1056, None), (2, 20, 1024, 231, None), (1, 10, 2112, 77, None),
+                                           # edges: fewer queries than one sub-tile, a single valid key, ragged tails
+                                           (1, 1, 40, 24, None), (2, 2, 17, 330, [330, 1]), (3, 1, 129, 129, [129, 65, 16]),
+                                           (1, 3, 64, 640, [577])])
 @pytest.mark.parametrize("layout", ["bhld", "blhd"])
 def test_attention_fwd_bwd(B, H, Lq, Lk, lens, layout):
     from vision_pt_b200 import ops
@@ -79,3 +82,26 @@ def test_attention_other_head_dims(B, H, Lq, Lk, lens, hd):
         for b, n in enumerate(lens):
             if n < Lk:
                 assert kg.grad[b, :, n:].abs().max() == 0 and vg.grad[b, :, n:].abs().max() == 0
+
+
+def test_attention_full_size_jit_b():
+    """BASELINE.json configs[1] shape (B=64, H=12, L=330, per-sample valid key lengths as the class-label context gives
+    them) against the oracle evaluated in fp32 on the same device."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(7)
+    B, H, L = 64, 12, 330
+    mk = lambda: torch.randn(B, L, H, 64, device="cuda").to(torch.bfloat16).permute(0, 2, 1, 3)
+    q, k, v, d_o = mk() * 1.5, mk() * 1.5, mk(), mk()
+    seq = torch.randint(L - 56, L + 1, (B,), device="cuda", dtype=torch.int32)
+    qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+    o = ops.attention(qg, kg, vg, seq)
+    o.backward(d_o)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    orf = oj.attention_explicit(qr, kr, vr, seq.long())
+    orf.backward(d_o.float())
+    assert rel_err(o, orf) <= 2e-2
+    assert rel_err(qg.grad, qr.grad) <= 2e-2 and rel_err(kg.grad, kr.grad) <= 2e-2 and rel_err(vg.grad, vr.grad) <= 2e-2
+    for b in range(0, B, 7):
+        n = int(seq[b])
+        if n < L:
+            assert kg.grad[b, :, n:].abs().max() == 0 and vg.grad[b, :, n:].abs().max() == 0
