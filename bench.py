@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--rank", type=int, default=16)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--checkpointing", action="store_true", help="gradient checkpointing per block (the reference's shipped YAML sets it)")
+    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "radam_schedulefree"],
+                    help="update rule of the timed step (the shipped YAMLs name schedulefree.RAdamScheduleFree)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -255,8 +257,9 @@ def run_ours(args) -> None:
     model_name = args.model
     net = T.build_jit_qlora(model_name, rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
     net.set_gradient_checkpointing(args.checkpointing)
+    hp = T.TrainHParams(optimizer=args.optimizer)
     step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
-                               seed=42 + rank)
+                               seed=42 + rank, hp=hp)
     host = T.synthetic_batch(args.batch, args.res, args.res, seed=1000 + rank)
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
@@ -340,7 +343,7 @@ def run_ours(args) -> None:
         torch.cuda.empty_cache()
         net = T.build_jit_qlora("JiT-L/16", rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
         step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
-                                   seed=42 + rank)
+                                   seed=42 + rank, hp=hp)
         load_batch_l = lambda: (step.image.copy_(host[0], non_blocking=True), step.class_ids.copy_(host[1], non_blocking=True),
                                 step.attention_mask.copy_(host[2], non_blocking=True))
         load_batch_l()
@@ -375,7 +378,8 @@ def run_ours(args) -> None:
                        "global_batch": world * args.batch, "parallelism": f"dp{world}",
                        "cuda_graph": not args.no_graph, "gradient_checkpointing": bool(args.checkpointing),
                        "l2": "no flush: one step streams far more than the 126 MB L2 (saved activations of every block)",
-                       "optimizer": "AdamW over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target},
+                       "optimizer": ("AdamW" if args.optimizer == "adamw" else "schedulefree.RAdamScheduleFree")
+                                    + " over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,

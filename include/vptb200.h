@@ -200,6 +200,18 @@ int vpt_grad_sumsq(const float* g, int64_t n, float scale, float* out, vpt_strea
 int vpt_adamw_step(void* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float grad_scale, const float* sumsq, float max_norm,
                    const float* step, int32_t zero_grad, vpt_stream_t stream);
+/* schedulefree.RAdamScheduleFree.step (the optimiser the shipped YAMLs name: configs/jit/x-loss/config.yml:75;
+ * schedulefree 1.4.1 -- absent from this image, restated from the published algorithm) over the same flat buffers, with
+ * the same clipping rule as vpt_adamw_step.  param = the y sequence (bf16), z = base sequence (fp32, initialised to
+ * the parameters), exp_avg_sq fp32; sched = double[4] {steps done, lr_max, weight_sum, scheduled_lr} (zero-initialised,
+ * advanced on the device in double precision, as the package's Python scalars are, so that a captured graph replays),
+ * coef = float[8] scratch.  Two launches.
+ * vpt_radam_schedulefree_swap: optimizer.eval() (to_eval != 0: p.lerp_(z, 1 - 1/beta1)) / optimizer.train(). */
+int vpt_radam_schedulefree_step(void* param, float* grad, float* z, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                                double beta2, float eps, float weight_decay, double r, double weight_lr_power,
+                                int32_t silent_sgd_phase, float grad_scale, const float* sumsq, float max_norm,
+                                double* sched, float* coef, int32_t zero_grad, vpt_stream_t stream);
+int vpt_radam_schedulefree_swap(void* param, const float* z, int64_t n, float beta1, int32_t to_eval, vpt_stream_t stream);
 /* treat_loss, model_pred "image" (train/jit/class_to_image.py:106-139): mode 0 = MSE(pred, clean), mode 1 = MSE of
  * the velocities (image_to_velocity, src/models/jit/pipeline.py:253-260) with timestep [batch] fp32.  pred bf16,
  * clean/noisy of in_dtype (VPT_BF16/F16/F32); loss_out[0] += mean (zero on entry); dpred (bf16, may be NULL) = dloss/dpred. */

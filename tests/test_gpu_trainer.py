@@ -139,3 +139,84 @@ def test_quantize_model_tool_roundtrip(tmp_path):
     ref = x.float() @ w.t() + fresh.attn["to_q"].bias.float()
     assert (y.float() - ref).abs().max() <= 2e-2 * ref.abs().max()
     assert (w.cpu() - net.attn["to_q"].weight.float()).abs().max() <= 0.15 * net.attn["to_q"].weight.float().abs().max()
+
+
+def test_radam_schedulefree_kernel_matches_oracle():
+    """vpt_radam_schedulefree_step (device-side schedule scalars, bf16 y / fp32 z) against oracle/optim.py with y rounded
+    to bf16 after every step, 40 steps with gradient clipping, through the silent phase into the Adam phase."""
+    from oracle import optim as oo
+    from vision_pt_b200 import ops
+    torch.manual_seed(3)
+    n, lr, wd, max_norm = 4096 + 8, 5e-3, 0.01, 1.0
+    y = (torch.randn(n) * 0.1).to(torch.bfloat16)
+    dev_y = y.clone().cuda()
+    z = dev_y.float()
+    v = torch.zeros(n, device="cuda")
+    g32 = torch.zeros(n, device="cuda")
+    sched = torch.zeros(4, dtype=torch.float64, device="cuda")
+    coef = torch.zeros(8, device="cuda")
+    sumsq = torch.zeros(1, device="cuda")
+    gr = oo.RAdamSFGroup(lr=lr, weight_decay=wd)
+    ry = [y.double()]
+    for step in range(40):
+        g = torch.randn(n) * (3.0 if step % 7 == 0 else 0.01)       # sometimes clipped, sometimes not
+        g32.copy_(g)
+        sumsq.zero_()
+        ops.grad_sumsq(g32, 1.0, sumsq)
+        ops.radam_schedulefree_step(dev_y, g32, z, v, sched, coef, lr, weight_decay=wd, sumsq=sumsq, max_norm=max_norm)
+        clip = min(1.0, max_norm / (float(g.double().norm()) + 1e-6))
+        oo.radam_schedulefree_step(gr, ry, [g.double() * clip])
+        ry[0].copy_(ry[0].float().to(torch.bfloat16).double())
+        assert float(g32.abs().max()) == 0.0
+    assert abs(float(sched[0]) - 40) == 0 and abs(float(sched[3]) - gr.scheduled_lr) <= 1e-9 * lr
+    assert abs(float(sched[2]) - gr.weight_sum) <= 1e-6 * gr.weight_sum
+    zr = gr.state[0]["z"]
+    assert (z.cpu().double() - zr).abs().max() <= 2e-3 * zr.abs().max()
+    # y is stored in bf16 on both sides: allow one rounding step of disagreement
+    assert (dev_y.cpu().double() - ry[0]).abs().max() <= 2 ** -7 * ry[0].abs().max()
+    # eval() / train(): the averaged iterate and back (bf16 storage: within rounding)
+    before = dev_y.clone()
+    ops.radam_schedulefree_swap(dev_y, z, 0.9, True)
+    x_ref = ry[0] + (1 - 1 / 0.9) * (zr - ry[0])
+    assert (dev_y.cpu().double() - x_ref).abs().max() <= 2 ** -6 * x_ref.abs().max()
+    ops.radam_schedulefree_swap(dev_y, z, 0.9, False)
+    assert (dev_y.float() - before.float()).abs().max() <= 2 ** -6 * before.float().abs().max()
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_trainer_with_radam_schedulefree(tmp_path, use_graph):
+    from vision_pt_b200 import train as T
+    net = T.build_jit_qlora(_small_cfg(), rank=16, alpha=16.0, device="cuda", seed=11, lora_up_std=0.02)
+    hp = T.TrainHParams(lr=2e-3, clip_grad_norm=1.0, optimizer="radam_schedulefree", weight_decay=0.0)
+    tr = T.JiTQLoRATrainer(net, num_classes=10, max_token_length=16, hp=hp, use_graph=use_graph, seed=5)
+    a = T.synthetic_batch(8, 64, 64, num_classes=10, max_token_length=16, seed=1)
+    b = T.synthetic_batch(8, 64, 128, num_classes=10, max_token_length=16, seed=2)
+    p0 = tr.state.flat.param.clone()
+    lrs, losses = [], []
+    for it in range(12):
+        losses.append(float(tr.train_step(*(a if it % 2 == 0 else b))))
+        lrs.append(tr.scheduled_lr)
+        if it < 4:
+            assert torch.equal(tr.state.flat.param, p0)       # RAdam's silent phase: scheduled lr = 0
+    assert tr.global_step == 12 and lrs[3] == 0.0 and lrs[4] > 0.0 and lrs[-1] > lrs[4]
+    assert all(torch.isfinite(torch.tensor(losses))) and not torch.equal(tr.state.flat.param, p0)
+    tr.save_checkpoint(str(tmp_path))
+    for batch in (a, b):
+        tr.train_step(*batch)
+    torch.cuda.synchronize()
+    want = (tr.state.flat.param.clone(), tr.state.z.clone(), tr.state.sched.clone())
+    net2 = T.build_jit_qlora(_small_cfg(), rank=16, alpha=16.0, device="cuda", seed=11, lora_up_std=0.02)
+    tr2 = T.JiTQLoRATrainer(net2, num_classes=10, max_token_length=16, hp=hp, use_graph=use_graph, seed=77)
+    tr2.load_checkpoint(str(tmp_path))
+    for batch in (a, b):
+        tr2.train_step(*batch)
+    torch.cuda.synchronize()
+    assert torch.equal(tr2.state.flat.param, want[0]) and torch.equal(tr2.state.z, want[1]) and torch.equal(tr2.state.sched, want[2])
+    # eval(): parameters become the averaged iterate; training refuses to run until train()
+    y = tr2.state.flat.param.clone()
+    tr2.eval()
+    assert not torch.equal(tr2.state.flat.param, y)
+    with pytest.raises(RuntimeError):
+        tr2.train_step(*a)
+    tr2.train()
+    assert (tr2.state.flat.param.float() - y.float()).abs().max() <= 2 ** -6 * y.float().abs().max()

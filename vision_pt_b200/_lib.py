@@ -42,7 +42,7 @@ class AttnTensorC(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sl", C.c_int64), ("sh", C.c_int64)]
 
 
-_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _AT = C.POINTER(AttnTensorC)
 
 # name -> argtypes (the stream is always last); every function returns int
@@ -70,6 +70,8 @@ SIGNATURES: dict[str, list] = {
     "vpt_unpatchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     "vpt_grad_sumsq": [_P, _I64, _F, _P, _P],
     "vpt_adamw_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _F, _P, _I32, _P],
+    "vpt_radam_schedulefree_step": [_P, _P, _P, _P, _I64, _D, _D, _D, _F, _F, _D, _D, _I32, _F, _P, _F, _P, _P, _I32, _P],
+    "vpt_radam_schedulefree_swap": [_P, _P, _I64, _F, _I32, _P],
     "vpt_flow_loss": [_P, _P, _P, C.c_int, _P, _I64, _I64, _I32, _F, _P, _P, _P],
 }
 
@@ -100,7 +102,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per C-ABI call (vpt_attn_bwd = delta pre-pass + main kernel); used for the bench's gpu_launches
-_KERNELS_PER_CALL = {"vpt_attn_bwd": 2, "vpt_nf4_quantize": 3}
+_KERNELS_PER_CALL = {"vpt_attn_bwd": 2, "vpt_nf4_quantize": 3, "vpt_radam_schedulefree_step": 2}
 CALLS: dict[str, int] = {}
 _launches = 0
 

@@ -22,7 +22,7 @@ static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
 }
 
 extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
-extern "C" int vpt_abi_version(void) { return 3; }
+extern "C" int vpt_abi_version(void) { return 4; }
 
 // ---------------------------------------------------------------------------------------------------- NF4
 extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
@@ -416,6 +416,28 @@ extern "C" int vpt_adamw_step(void* param, float* grad, float* exp_avg, float* e
   AdamWParams a{BFM(param), grad, exp_avg, exp_avg_sq, static_cast<long>(n), lr, beta1, beta2, eps, weight_decay,
                 grad_scale, sumsq, max_norm, step, zero_grad};
   adamw_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(a);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_radam_schedulefree_step(void* param, float* grad, float* z, float* exp_avg_sq, int64_t n, double lr,
+                                           double beta1, double beta2, float eps, float weight_decay, double r,
+                                           double weight_lr_power, int32_t silent_sgd_phase, float grad_scale,
+                                           const float* sumsq, float max_norm, double* sched, float* coef,
+                                           int32_t zero_grad, vpt_stream_t stream) {
+  VPT_REQUIRE(param && grad && z && exp_avg_sq && sched && coef && n > 0, "vpt_radam_schedulefree_step: bad arguments");
+  radam_sf_advance_kernel<<<1, 32, 0, S(stream)>>>(sched, coef, lr, beta1, beta2, r, weight_lr_power, silent_sgd_phase);
+  VPT_CUDA_OK(cudaGetLastError());
+  RAdamSFParams a{BFM(param), grad, z, exp_avg_sq, static_cast<long>(n), static_cast<float>(beta2), eps, weight_decay, grad_scale, sumsq, max_norm,
+                  coef, zero_grad};
+  radam_sf_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(a);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_radam_schedulefree_swap(void* param, const float* z, int64_t n, float beta1, int32_t to_eval,
+                                           vpt_stream_t stream) {
+  VPT_REQUIRE(param && z && n > 0 && beta1 > 0.f, "vpt_radam_schedulefree_swap: bad arguments");
+  const float w = to_eval ? 1.f - 1.f / beta1 : 1.f - beta1;
+  radam_sf_swap_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(BFM(param), z, static_cast<long>(n), w);
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }

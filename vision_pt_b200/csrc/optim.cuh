@@ -82,6 +82,85 @@ adamw_kernel(const AdamWParams a) {
   }
 }
 
+// ---- schedulefree.RAdamScheduleFree (the optimiser of the shipped YAMLs: configs/jit/x-loss/config.yml:75; package
+// schedulefree 1.4.1, uv.lock:3428 -- not in this image, so the update below restates the published algorithm of
+// radam_schedulefree.py and is checked against this repo's CPU restatement of it only: parity unpinned).
+// The parameters are the "y" sequence (what the model trains with), z is the base sequence (fp32 here; the package
+// keeps it in the parameter dtype), exp_avg_sq the second moment.  Per step, on the device so that a graph replays:
+//   sched = {k, lr_max, weight_sum, scheduled_lr}  ->  coef = {lr_t, ckp1, adaptive_y_lr, bias_correction2, adam}
+__global__ void radam_sf_advance_kernel(double* sched, float* coef, double lr, double beta1, double beta2, double r,
+                                        double weight_lr_power, int silent_sgd_phase) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double step = sched[0] + 1.0;
+  const double beta2_t = pow(beta2, step);
+  const double bc2 = 1.0 - beta2_t;
+  const double rho_inf = 2.0 / (1.0 - beta2) - 1.0;
+  const double rho_t = rho_inf - 2.0 * step * beta2_t / bc2;
+  const bool adam = rho_t > 4.0;
+  const double rect = adam ? sqrt((rho_t - 4.0) * (rho_t - 2.0) * rho_inf / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t))
+                           : (silent_sgd_phase ? 0.0 : 1.0);
+  const double lr_t = lr * rect;
+  const double lr_max = fmax(lr_t, sched[1]);
+  const double weight = pow(step, r) * pow(lr_max, weight_lr_power);
+  const double weight_sum = sched[2] + weight;
+  const double ckp1 = weight_sum > 0.0 ? weight / weight_sum : 0.0;
+  sched[0] = step;
+  sched[1] = lr_max;
+  sched[2] = weight_sum;
+  sched[3] = lr_t;                                   // param_group["scheduled_lr"] (logged by src/trainer/common.py:499-506)
+  coef[0] = static_cast<float>(lr_t);
+  coef[1] = static_cast<float>(ckp1);
+  coef[2] = static_cast<float>(lr_t * (beta1 * (1.0 - ckp1) - 1.0));
+  coef[3] = static_cast<float>(bc2);
+  coef[4] = adam ? 1.f : 0.f;
+}
+
+struct RAdamSFParams {
+  __nv_bfloat16* y;        // [n] parameters (the y sequence), updated in place
+  float* g;                // [n] gradients; zeroed after use when zero_grad != 0
+  float* z;                // [n] base sequence
+  float* v;                // [n] second moment
+  long n;
+  float beta2, eps, weight_decay;
+  float grad_scale;
+  const float* sumsq;
+  float max_norm;
+  const float* coef;       // written by radam_sf_advance_kernel just before
+  int zero_grad;
+};
+
+__global__ void __launch_bounds__(256)
+radam_sf_kernel(const RAdamSFParams a) {
+  float clip = a.grad_scale;
+  if (a.sumsq != nullptr) clip *= fminf(1.f, a.max_norm / (sqrtf(__ldg(a.sumsq)) + 1e-6f));
+  const float lr_t = __ldg(a.coef), ckp1 = __ldg(a.coef + 1), y_lr = __ldg(a.coef + 2), bc2 = __ldg(a.coef + 3);
+  const bool adam = __ldg(a.coef + 4) != 0.f;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float g = a.g[i] * clip;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.v[i] = v;
+    float y = __bfloat162float(a.y[i]);
+    float gn = adam ? g / (sqrtf(v / bc2) + a.eps) : g;
+    gn += a.weight_decay * y;                       // weight decay is evaluated at y
+    const float z = a.z[i];
+    y = y + ckp1 * (z - y);                         // y.lerp_(z, ckp1)
+    y += y_lr * gn;
+    a.y[i] = __float2bfloat16_rn(y);
+    a.z[i] = z - lr_t * gn;
+    if (a.zero_grad) a.g[i] = 0.f;
+  }
+}
+
+// optimizer.eval() / .train() of the package: parameters y <-> x = the averaged iterate (what is evaluated and saved)
+//   to_eval != 0: p.lerp_(z, 1 - 1/beta1);  else: p.lerp_(z, 1 - beta1)
+__global__ void __launch_bounds__(256)
+radam_sf_swap_kernel(__nv_bfloat16* p, const float* z, long n, float weight) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float y = __bfloat162float(p[i]);
+    p[i] = __float2bfloat16_rn(y + weight * (z[i] - y));
+  }
+}
+
 }  // namespace vpt
 
 // ------------------------------------------------------------------------------------------- flow-matching loss

@@ -740,3 +740,21 @@ def adamw_step(param, grad32, exp_avg, exp_avg_sq, step_t, lr, betas, eps, weigh
     _lib.call("vpt_adamw_step", _p(param), _p(grad32), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr), float(betas[0]),
               float(betas[1]), float(eps), float(weight_decay), float(grad_scale), _p(sumsq), float(max_norm), _p(step_t),
               int(zero_grad), _stream())
+
+
+def radam_schedulefree_step(param, grad32, z, exp_avg_sq, sched, coef, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                            r=0.0, weight_lr_power=2.0, silent_sgd_phase=True, grad_scale=1.0, sumsq=None, max_norm=0.0,
+                            zero_grad=True) -> None:
+    """schedulefree.RAdamScheduleFree.step over the flat buffers (include/vptb200.h).  `sched` float64[4] zeros at the
+    start of a run (steps done, lr_max, weight_sum, scheduled_lr), `coef` float32[8] scratch, `z` fp32 clone of `param`."""
+    if param.dtype != torch.bfloat16 or grad32.dtype != torch.float32 or z.dtype != torch.float32 or sched.dtype != torch.float64:
+        raise TypeError("radam_schedulefree_step: bf16 parameters, fp32 gradients / z, float64 schedule state")
+    _lib.call("vpt_radam_schedulefree_step", _p(param), _p(grad32), _p(z), _p(exp_avg_sq), param.numel(), float(lr),
+              float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(r), float(weight_lr_power),
+              int(silent_sgd_phase), float(grad_scale), _p(sumsq), float(max_norm), _p(sched), _p(coef), int(zero_grad),
+              _stream())
+
+
+def radam_schedulefree_swap(param, z, beta1: float, to_eval: bool) -> None:
+    """optimizer.eval() / optimizer.train() of the package: y -> x (the averaged iterate) and back."""
+    _lib.call("vpt_radam_schedulefree_swap", _p(param), _p(z), param.numel(), float(beta1), int(to_eval), _stream())

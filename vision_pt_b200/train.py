@@ -135,6 +135,12 @@ class TrainHParams:
     noise_scale: float = 1.0
     ts_std: float = 0.8               # scale_shift_sigmoid timestep sampling (src/modules/timestep/sampling.py:259-272)
     ts_mean: float = -0.8
+    # "adamw" (torch.optim.AdamW semantics) or "radam_schedulefree" (schedulefree.RAdamScheduleFree, the optimiser of
+    # the shipped YAMLs, configs/jit/x-loss/config.yml:75 with lr 1e-4; package defaults otherwise: no weight decay)
+    optimizer: str = "adamw"
+    sf_r: float = 0.0
+    sf_weight_lr_power: float = 2.0
+    sf_silent_sgd_phase: bool = True
 
 
 class TrainState:
@@ -157,10 +163,29 @@ class TrainState:
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        # schedule-free optimiser state (allocated on first use): base sequence z, schedule scalars, coefficient scratch
+        self.z: torch.Tensor | None = None
+        self.sched = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.coef = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.eval_mode = False
         self.pool = None
 
     def tensors(self) -> tuple[torch.Tensor, ...]:
-        return (self.flat.param, self.exp_avg, self.exp_avg_sq, self.step_t)
+        extra = () if self.z is None else (self.z,)
+        return (self.flat.param, self.exp_avg, self.exp_avg_sq, self.step_t, self.sched) + extra
+
+    def ensure_z(self) -> torch.Tensor:
+        if self.z is None:
+            self.z = self.flat.param.float()
+        return self.z
+
+    def set_eval(self, eval_mode: bool, beta1: float) -> None:
+        """optimizer.eval() / optimizer.train() of a schedule-free optimiser: the parameters become the averaged iterate x
+        (what is evaluated and saved) or go back to the training sequence y.  No-op for AdamW (z is None)."""
+        if self.z is None or eval_mode == self.eval_mode:
+            return
+        ops.radam_schedulefree_swap(self.flat.param, self.z, beta1, eval_mode)
+        self.eval_mode = eval_mode
 
 
 class JiTQLoRATrainStep:
@@ -233,6 +258,14 @@ class JiTQLoRATrainStep:
             ops.grad_sumsq(self.flat.grad, scale, self.sumsq)
             sumsq = self.sumsq
         self.step_t += 1
+        if hp.optimizer == "radam_schedulefree":
+            ops.radam_schedulefree_step(self.flat.param, self.flat.grad, self.state.ensure_z(), self.exp_avg_sq, self.state.sched,
+                                        self.state.coef, hp.lr, hp.betas, hp.eps, hp.weight_decay, hp.sf_r, hp.sf_weight_lr_power,
+                                        hp.sf_silent_sgd_phase, grad_scale=scale, sumsq=sumsq,
+                                        max_norm=hp.clip_grad_norm or 0.0, zero_grad=True)
+            return
+        if hp.optimizer != "adamw":
+            raise ValueError(f"unknown optimizer '{hp.optimizer}'")
         ops.adamw_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.step_t, hp.lr, hp.betas, hp.eps,
                        hp.weight_decay, grad_scale=scale, sumsq=sumsq, max_norm=hp.clip_grad_norm or 0.0, zero_grad=True)
 
@@ -244,6 +277,8 @@ class JiTQLoRATrainStep:
         """Eager warm-up on a side stream (one-time kernel attribute setup, allocator growth, NCCL init), then capture.
         One graph at world size 1.  With data parallelism the step is two graphs (compute | update) with the NCCL
         all-reduce launched between them on the same stream: three launches per step, and no collective inside a capture."""
+        if self.hp.optimizer == "radam_schedulefree":
+            self.state.ensure_z()
         snap = [t.clone() for t in self.state.tensors()]         # the warm-up steps must not train: a new (H, W) bucket
         rng = torch.cuda.get_rng_state(self.device)              # may be captured in the middle of a run (nor draw noise)
         s = torch.cuda.Stream()
@@ -323,6 +358,8 @@ class JiTQLoRATrainer:
 
     def train_step(self, image: torch.Tensor, class_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
         B, _, H, W = image.shape
+        if self.state.eval_mode:
+            raise RuntimeError("train_step in eval mode: call trainer.train() first (schedule-free optimiser)")
         step = self.bucket(B, H, W)
         if step.use_graph and step.graph is None:
             step.capture()                       # before the copies: warm-up must not consume this batch's buffers
@@ -334,6 +371,18 @@ class JiTQLoRATrainer:
     @property
     def global_step(self) -> int:
         return int(self.state.step_t.item())
+
+    @property
+    def scheduled_lr(self) -> float:
+        """param_group["scheduled_lr"] of a schedule-free optimiser (what src/trainer/common.py:499-506 logs)."""
+        return float(self.state.sched[3].item()) if self.hp.optimizer == "radam_schedulefree" else self.hp.lr
+
+    def eval(self) -> None:
+        """Before validation / saving with a schedule-free optimiser (optimizer.eval()): parameters -> averaged iterate."""
+        self.state.set_eval(True, self.hp.betas[0])
+
+    def train(self) -> None:
+        self.state.set_eval(False, self.hp.betas[0])
 
     # ------------------------------------------------------------------ checkpoint / resume
     def _named_slices(self):
@@ -352,11 +401,13 @@ class JiTQLoRATrainer:
         os.makedirs(directory, exist_ok=True)
         save_file(self.adapter_state_dict(), os.path.join(directory, "adapter.safetensors"),
                   metadata={"format": "pt", "peft": "lora"})
-        opt = {"step": self.state.step_t.detach().cpu().clone()}
+        opt = {"step": self.state.step_t.detach().cpu().clone(), "sched": self.state.sched.detach().cpu().clone()}
         for name, off, p in self._named_slices():
             n = p.numel()
             opt[f"{name}.exp_avg"] = self.state.exp_avg[off:off + n].view_as(p).cpu().clone()
             opt[f"{name}.exp_avg_sq"] = self.state.exp_avg_sq[off:off + n].view_as(p).cpu().clone()
+            if self.state.z is not None:
+                opt[f"{name}.z"] = self.state.z[off:off + n].view_as(p).cpu().clone()
         save_file(opt, os.path.join(directory, "optimizer.safetensors"))
         torch.save({"rng_cpu": torch.random.get_rng_state(), "rng_cuda": torch.cuda.get_rng_state(), "hp": vars(self.hp)},
                    os.path.join(directory, "trainer_state.pt"))
@@ -379,8 +430,12 @@ class JiTQLoRATrainer:
                     n = p.numel()
                     self.state.exp_avg[off:off + n].copy_(opt[f"{name}.exp_avg"].reshape(-1))
                     self.state.exp_avg_sq[off:off + n].copy_(opt[f"{name}.exp_avg_sq"].reshape(-1))
+                    if f"{name}.z" in opt:
+                        self.state.ensure_z()[off:off + n].copy_(opt[f"{name}.z"].reshape(-1))
             if opt is not None:
                 self.state.step_t.copy_(opt["step"])
+                if "sched" in opt:
+                    self.state.sched.copy_(opt["sched"])
         ts = os.path.join(directory, "trainer_state.pt")
         if os.path.exists(ts):
             st = torch.load(ts, weights_only=False)
