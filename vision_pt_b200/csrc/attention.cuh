@@ -46,8 +46,9 @@ struct AttnFwdSmem {
   static constexpr int kStream = 6 * 16384;
   static constexpr int kQ = 0, kK = 2 * 16384, kV = 4 * 16384;
   static constexpr int kOut = 2 * kStream;        // 8 softmax warps x one slab of [32 rows x 128 B] (output tile -> TMA store)
-  static constexpr int kBars = kOut + 8 * 4096;
-  // per stream: q_full[2] q_empty[2] kv_full[2] kv_empty[2] s_full p_full pv_done  (11)
+  static constexpr int kXchg = kOut + 8 * 4096;   // per stream: 2 block parities x 2 column halves x 128 rows, bf16 row maxima
+  static constexpr int kBars = kXchg + 2 * 1024;
+  // per stream: q_full[2] q_empty[2] kv_full[2] kv_empty[2] s_full p_full (256 arrivals) pv_done  (11)
   static constexpr int kBarsPerStream = 11;
   static constexpr int kTmemSlot = kBars + 2 * kBarsPerStream * 8;
   static constexpr int kTotal = kTmemSlot + 16;   // no alignment slack: the dynamic segment starts 1024B-aligned
@@ -57,8 +58,9 @@ struct AttnFwdSmem {
 // sample) with its own softmax warpgroup, MMA-issuing warp, TMA producer warp, Q / K / V buffers and TMEM columns:
 //
 //   tensor core    S = Q K_j^T  (128 queries x <=128 keys, fp32, TMEM)
-//   warpgroup      pass 1: row maximum over S;  pass 2: P = exp2(S c - m) -> bf16 written over the S columns it came
-//                  from (A operand of the next MMA, never through shared memory), row sums in registers
+//   2 warpgroups   each takes one half of the block's key columns: pass 1 row maximum (exchanged between the halves
+//                  through shared memory), pass 2 P = exp2(S c - m) -> bf16 into the stream's P columns of TMEM (A operand
+//                  of the next MMA, never through shared memory), partial row sums in registers
 //   tensor core    O += P V_j (A from TMEM), then S of the next key block (or of the stream's next item)
 //   warpgroup      end of item: O / l -> bf16 -> 128B-swizzled slab -> TMA store (tmO: box {64, 32}), lse2
 //
@@ -69,8 +71,10 @@ struct AttnFwdSmem {
 // its time in per-item merge / turn-over at 2.6 key blocks per item (profiles/r1l_attn_fwd_phases.txt).
 // A stream rescales its accumulator only when its maximum grows by more than 2^8 (P stays <= 256: exact in the fp32
 // sums, safe in bf16).
-// Warps: 0 / 2 TMA producers of stream A / B (2 also allocates TMEM), 1 / 3 MMA issuers, 4-7 softmax A, 8-11 softmax B.
-__global__ void __launch_bounds__(384, 1)
+// Eight softmax warps per stream (two per TMEM lane quarter): with four, a scheduler held two softmax warps and the
+// tcgen05.ld -> ex2 -> tcgen05.st chains were latency-bound (MUFU 30 % busy, profiles/r1o_attn_fwd_ncu.txt).
+// Warps: 0 / 2 TMA producers of stream A / B (2 also allocates TMEM), 1 / 3 MMA issuers, 4-11 softmax A, 12-19 softmax B.
+__global__ void __launch_bounds__(640, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnFwdParams p) {
   using S = AttnFwdSmem;
@@ -80,7 +84,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int X = warp < 4 ? (warp >> 1) : ((warp - 4) >> 2);          // stream of this warp
+  const int X = warp < 4 ? (warp >> 1) : ((warp - 4) >> 3);          // stream of this warp
   uint8_t* sm = smem + X * S::kStream;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars) + X * S::kBarsPerStream;
   uint64_t* q_full = bars;          // [2]
@@ -106,7 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int x = 0; x < 2; ++x) {
       uint64_t* bx = all + x * S::kBarsPerStream;
       for (int i = 0; i < 9; ++i) mbar_init(&bx[i], 1);
-      mbar_init(&bx[9], 128);
+      mbar_init(&bx[9], 256);
       mbar_init(&bx[10], 1);
     }
     fence_mbar_init();
@@ -116,7 +120,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base + X * 256, tO = tS + 128;   // per stream: S / P 0..127, O 128..191
+  const uint32_t tS = tmem_base + X * 256, tO = tS + 128, tP = tS + 192;   // per stream: S 0..127, O 128..191, P 192..255
   pdl_launch_dependents();
   pdl_wait();
 
@@ -157,7 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int nblk = (kl + kAttnTile - 1) / kAttnTile;
       const uint32_t qb = it & 1;
       const uint64_t qd = dK_ + ((sbase + S::kQ + qb * 16384) >> 4);
-      // S = Q K_j^T; the S / P columns are free: the stream's previous O += P V was issued before this (in-order pipe)
+      // S = Q K_j^T (the softmax halves have read the previous S: p_full)
       auto issue_s = [&](int j, uint32_t jn) {
         const uint32_t s = jn & 1;
         const int valid = min(128, kl - j * 128);
@@ -193,9 +197,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (elect_one_sync()) {
           if (n == 128) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_ts(tO, tS + k * 8, vd + k * 128, kIdO, (j | k) != 0);
+            for (int k = 0; k < 8; ++k) umma_ts(tO, tP + k * 8, vd + k * 128, kIdO, (j | k) != 0);
           } else {
-            for (int k = 0; k < n / 16; ++k) umma_ts(tO, tS + k * 8, vd + k * 128, kIdO, (j | k) != 0);
+            for (int k = 0; k < n / 16; ++k) umma_ts(tO, tP + k * 8, vd + k * 128, kIdO, (j | k) != 0);
           }
           umma_commit(&kv_empty[s]);
         }
@@ -216,33 +220,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
              prof_[3], prof_[4], prof_[5]);
 #endif
   } else {
-    // ============================================================ softmax warpgroup of stream X
+    // ============================================================ softmax warps of stream X (two column halves)
+    const int half = ((warp - 4) >> 2) & 1;       // key columns 64 half .. 64 half + 63 of every block
     const int qd = warp & 3;                      // TMEM lane quarter
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    uint8_t* out_slab = smem + S::kOut + (warp - 4) * 4096;
+    uint8_t* out_slab = smem + S::kOut + (X * 4 + qd) * 4096;       // used by half 0 (the epilogue half)
     const uint32_t out_row = smem_u32(out_slab) + lane * 128;
-    if (lane == 0) tma_prefetch_desc(&tmO);
+    __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem + S::kXchg + X * 1024);   // [parity][half][128]
+    if (lane == 0 && half == 0) tma_prefetch_desc(&tmO);
     uint32_t cx = 0, it = 0;
     PROF_DECL(8)
     for (int item = first_item; item < num_items; item += item_stride, ++it) {
       const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
       const int klen = klen_of(item);
       const int nblk = (klen + kAttnTile - 1) / kAttnTile;
-      float m_ref = -INFINITY, l_run = 0.f;
+      float m_ref = -INFINITY, l_run = 0.f;       // l_run: this half's part of the row sum
       for (int j = 0; j < nblk; ++j) {
         const int nvalid = min(128, klen - j * 128);          // < 128 only in the last block
         const int nch = (nvalid + 31) >> 5;                   // 32-column chunks that hold keys
+        const int c_begin = 2 * half, c_end = min(nch, 2 * half + 2);
+        __nv_bfloat16* xb = xchg + (cx & 1) * 256;
         PROF(0)
         mbar_wait(s_full, cx & 1);
         PROF(1)
         ++cx;
         tc_fence_after_sync();
-        // ---- pass 1: row maximum.  (Prefetching the next chunk's TMEM load while reducing this one needs the loop
-        // unrolled over two register buffers and measured slower: 68 vs 61 us.)
+        // ---- pass 1: row maximum over this half's columns
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           uint32_t v[32];
           tmem_ld32(tS + lane_off + c * 32, v);
           tmem_wait_ld();
@@ -260,32 +267,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           mx = fmaxf(mx, fmaxf(m0, m1));
         }
+        // the halves agree on ONE reference maximum: both take max(bf16(own), bf16(other)).  bf16 is enough -- the
+        // reference only has to be within 2^8 of the true maximum (lazy-rescale rule below), not equal to it.
+        const __nv_bfloat16 mine = __float2bfloat16_rn(mx * p.scale_log2);   // scale > 0: max commutes with the scaling
+        xb[half * 128 + row] = mine;
+        named_bar_sync(1 + X, 256);
+        mx = fmaxf(__bfloat162float(mine), __bfloat162float(xb[(half ^ 1) * 128 + row]));
         PROF(2)
-        mx *= p.scale_log2;                         // scale > 0: the maximum commutes with the scaling
         // lazy rescale: keep the reference maximum unless the true one outgrew it by 2^8
         const bool grow = mx > m_ref + 8.f;
         const float m_new = grow ? mx : m_ref;
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          // O is final for block j-1: s_full of block j was committed after that MMA
           const float alpha = grow ? fast_exp2(m_ref - m_new) : 1.f;
           l_run *= alpha;
+          if (half == 0) {
+            // O is final for block j-1: s_full of block j was committed after that MMA.  One half rescales it; the other's
+            // P store and this one's are both behind p_full (256 arrivals) before the next accumulation.
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO + lane_off + c * 32, o);
-            tmem_wait_ld();
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + lane_off + c * 32, o);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + lane_off + c * 32, o);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + lane_off + c * 32, o);
+            }
           }
         }
         PROF(3)
         m_ref = m_new;
         const float neg_m = -m_ref;
-        // ---- pass 2: P = exp2(S c - m) -> bf16 over the S columns (chunk c's 16 P columns lie inside columns already read)
+        // ---- pass 2: P = exp2(S c - m) -> bf16 into the P columns
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           uint32_t v[32];
           tmem_ld32(tS + lane_off + c * 32, v);
           tmem_wait_ld();
@@ -306,65 +321,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ps1 += p1;
             pk[e] = pack_bf16x2(p0, p1);
           }
-          // chunk c's 16 P columns lie inside S columns [0, 32 c + 16): all read already
-          tmem_st16(tS + lane_off + c * 16, pk);
+          tmem_st16(tP + lane_off + c * 16, pk);
         }
         l_run += ps0 + ps1;
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(p_full);
+        mbar_arrive(p_full);                        // also: this half has read its S columns (the next S may be issued)
         PROF(4)
       }
-      // ---- end of item: O / l -> bf16 -> global
+      // ---- end of item: the halves add their row sums; half 0 writes O / l -> bf16 -> slab -> TMA store
       PROF(0)
       mbar_wait(pv_done, it & 1);
       PROF(5)
       tc_fence_after_sync();
-      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
-      const int q = qt * kAttnTile + row;
-      // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
-      p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
-          q < p.Lq ? (l_run > 0.f ? m_ref + log2f(l_run) : -INFINITY) : INFINITY;
-      if (lane == 0) tma_store_wait_read<0>();     // the previous item's store has read the slab
-      __syncwarp();
+      if (nblk > 0) {
+        // the exchange buffer of the item's last block is free again: every read of it precedes that half's p_full arrival,
+        // and pv_done follows both
+        float* lx = reinterpret_cast<float*>(xchg + ((cx - 1) & 1) * 256);
+        if (half == 1) lx[row] = l_run;
+        named_bar_sync(1 + X, 256);
+        if (half == 0) l_run += lx[row];
+      }
+      if (half == 0) {
+        const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+        const int q = qt * kAttnTile + row;
+        // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
+        p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
+            q < p.Lq ? (l_run > 0.f ? m_ref + log2f(l_run) : -INFINITY) : INFINITY;
+        if (lane == 0) tma_store_wait_read<0>();     // the previous item's store has read the slab
+        __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        if (nblk > 0) {                            // stream-uniform: the .sync.aligned load stays convergent
-          tmem_ld32(tO + lane_off + c * 32, o);
-          tmem_wait_ld();
-        } else {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          if (nblk > 0) {                            // stream-uniform: the .sync.aligned load stays convergent
+            tmem_ld32(tO + lane_off + c * 32, o);
+            tmem_wait_ld();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0u;
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + (((c * 4 + g) ^ (lane & 7)) * 16)),
+                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l)),
+                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l)),
+                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l)),
+                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l))
+                         : "memory");
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + (((c * 4 + g) ^ (lane & 7)) * 16)),
-                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l)),
-                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l)),
-                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l)),
-                       "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l))
-                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (qt * kAttnTile + qd * 32 < p.Lq)       // rows past Lq inside the box are clipped by the TMA unit
+            tma_store_4d(&tmO, out_slab, 0, qt * kAttnTile + qd * 32, h, b);
+          tma_store_commit();
+        }
+        // the accumulator is read: order those loads before this half's next p_full arrival, after which the issuer
+        // overwrites O (accumulate = 0 on the next item's first block)
+        tc_fence_before_sync();
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (qt * kAttnTile + qd * 32 < p.Lq)       // rows past Lq inside the box are clipped by the TMA unit
-          tma_store_4d(&tmO, out_slab, 0, qt * kAttnTile + qd * 32, h, b);
-        tma_store_commit();
-      }
-      // the accumulator is read: order those loads before the stream's next P store / p_full, after which the issuer
-      // overwrites O (accumulate = 0 on the next item's first block)
-      tc_fence_before_sync();
       PROF(6)
     }
 #ifdef VPT_BWD_PROF
     PROF(0)
     if (blockIdx.x == 0 && lane == 0 && qd == 0)
-      printf("fwd wg%d : other %lld s_full %lld pass1 %lld rescale %lld pass2 %lld pv_done %lld epilogue %lld\n", X, prof_[0], prof_[1],
+      printf("fwd wg%d.%d: other %lld s_full %lld pass1 %lld rescale %lld pass2 %lld pv_done %lld epilogue %lld\n", X, half, prof_[0], prof_[1],
              prof_[2], prof_[3], prof_[4], prof_[5], prof_[6]);
 #endif
-    if (lane == 0) tma_store_wait_all<0>();
+    if (lane == 0 && half == 0) tma_store_wait_all<0>();
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -44,7 +44,7 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   const int items = ((Lq + kAttnTile - 1) / kAttnTile) * H * B;
   const int ctas = (items + 1) / 2;              // two streams (items) per CTA
   const int slots = sm_count();
-  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(ctas < slots ? ctas : slots), dim3(384), AttnFwdSmem::kTotal, stream, tq, tk, tv, to, p));
+  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(ctas < slots ? ctas : slots), dim3(640), AttnFwdSmem::kTotal, stream, tq, tk, tv, to, p));
   return 0;
 }
 
