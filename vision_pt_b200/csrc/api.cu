@@ -447,7 +447,7 @@ extern "C" int vpt_flow_loss(const void* pred, const void* clean, const void* no
   VPT_REQUIRE(pred && clean && loss_out && batch > 0 && per_sample > 0 && (mode == 0 || (mode == 1 && noisy && timestep)) &&
                   in_dtype >= 0 && in_dtype <= 2, "vpt_flow_loss: bad arguments");
   const long total = static_cast<long>(batch) * per_sample;
-  flow_loss_kernel<<<blocks_for(total, 256 * 8, 148 * 16), 256, 0, S(stream)>>>(BF(pred), clean, noisy, in_dtype, timestep, per_sample, total, mode,
+  flow_loss_kernel<<<blocks_for(total / 8 + 1, 256, 148 * 8), 256, 0, S(stream)>>>(BF(pred), clean, noisy, in_dtype, timestep, per_sample, total, mode,
                                                                        clamp_eps, loss_out, BFM(dpred));
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
