@@ -11,7 +11,7 @@ from vision_pt_b200 import ops  # noqa: E402
 from vision_pt_b200.modules.quant import nested_code_table  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--model", default="B")
+ap.add_argument("--model", default="B", help="B | L | H (JiT block linears) | sdxl640 | sdxl1280 (SDXL TransformerBlock linears, SURVEY 8a12)")
 ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--M", type=int, default=21120)
 ap.add_argument("--iters", type=int, default=20)
@@ -20,8 +20,13 @@ ap.add_argument("--no-flush", action="store_true")
 ap.add_argument("--no-res", action="store_true")
 ap.add_argument("--only", type=int, default=-1)
 args = ap.parse_args()
-D, F = {"B": (768, 2048), "L": (1024, 2730), "H": (1280, 3413)}[args.model]
-shapes = [(D, D), (D, F), (F, D)]           # (K, N)
+if args.model.startswith("sdxl"):
+    D = int(args.model[4:])
+    # attn1/attn2 to_q/k/v/out [D,D], attn2.to_k/v [D,2048] (ctx), ff.net.0.proj D->8D (GeGLU), ff.net.2 4D->D
+    shapes = [(D, D), (2048, D), (D, 8 * D), (4 * D, D)]
+else:
+    D, F = {"B": (768, 2048), "L": (1024, 2730), "H": (1280, 3413)}[args.model]
+    shapes = [(D, D), (D, F), (F, D)]           # (K, N)
 dev = torch.device("cuda")
 torch.manual_seed(0)
 code = torch.tensor([-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635,

@@ -1,7 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_block.py -x -q 2>&1 | tail -2
-timeout 120 python tools/probes/small_kernels.py && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"delta" --csv python tools/probes/small_kernels.py 2>/dev/null | grep -v "^==" | python -c "
-import csv,sys
-rows=list(csv.reader(sys.stdin))
-for r in rows[1:]:
-    if len(r)>14: print(r[4][:40], r[12], r[14])"
-timeout 200 python tools/bench_attn.py 2>&1 | tail -1
+echo "== SDXL D=640 (L=4096, B=4): linears"; timeout 300 python tools/bench_linear.py --model sdxl640 --M 16384 --no-res 2>&1 | tail -9 | cut -c1-110
+echo "== SDXL D=1280 (L=1024, B=4): linears"; timeout 300 python tools/bench_linear.py --model sdxl1280 --M 4096 --no-res 2>&1 | tail -9 | cut -c1-110
+echo "== attention"; timeout 200 python tools/bench_attn.py --B 4 --H 10 --L 4096 2>&1 | tail -2
+timeout 200 python tools/bench_attn.py --B 4 --H 10 --L 4096 --Lk 231 2>&1 | tail -2
+timeout 200 python tools/bench_attn.py --B 4 --H 20 --L 1024 2>&1 | tail -2
+timeout 200 python tools/bench_attn.py --B 4 --H 20 --L 1024 --Lk 231 2>&1 | tail -2
