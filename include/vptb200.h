@@ -190,6 +190,13 @@ int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t C, int32_t
                    int32_t order, vpt_stream_t stream);
 
 
+/* JiT.forward's per-block context-token refresh (src/models/jit/denoiser.py:1092-1113: the original context tokens are
+ * re-appended in front of every block >= context_start_block and the block's outputs for them dropped) with the slots kept
+ * in the token buffer: dst[r, 0:row_bytes] = src[r, 0:row_bytes] for rows a pitch apart; src NULL = zero fill (their
+ * gradient).  Everything a multiple of 16 bytes. */
+int vpt_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t rows, int64_t row_bytes,
+                  vpt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ optimiser / loss
  * accelerator.clip_grad_norm_ + optimizer.step + zero_grad (src/models/for_training.py:98-109,
  * src/trainer/common.py:382-388) over the flat LoRA buffers: param bf16 [n], grad / exp_avg / exp_avg_sq fp32 [n].

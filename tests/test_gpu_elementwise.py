@@ -153,3 +153,22 @@ def test_qknorm_rope_head_dim_80(B, L, H):
     xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
     oj.apply_rope(oj.rms_norm_fp32(xr.permute(0, 2, 1, 3), wr), f).permute(0, 2, 1, 3).backward(dy.float())
     assert rel_err(xg.grad, xr.grad) <= 2e-2 and rel_err(wg.grad, wr.grad) <= 2e-2
+
+
+@pytest.mark.parametrize("B,L,D,start", [(64, 330, 768, 266), (3, 50, 128, 10), (2, 9, 24, 4), (2, 7, 12, 3)])
+def test_copy_token_slots(B, L, D, start):
+    """The per-block context-slot refresh (reference denoiser.py:1092-1113) and its gradient zeroing: bit-exact against
+    the torch slice assignment, including shapes that take the unaligned fallback."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(0)
+    buf = torch.randn(B, L, D, device="cuda").to(torch.bfloat16)
+    tail = torch.randn(B, L - start, D, device="cuda").to(torch.bfloat16)
+    want = buf.clone()
+    want[:, start:] = tail
+    got = buf.clone()
+    ops.copy_token_slots(got, start, tail)
+    assert torch.equal(got, want)
+    want[:, start:] = 0
+    ops.copy_token_slots(got, start, None)
+    assert torch.equal(got, want)
+    assert torch.equal(got[:, :start], buf[:, :start])

@@ -1,6 +1,3 @@
-echo "== SDXL D=640 (L=4096, B=4): linears"; timeout 300 python tools/bench_linear.py --model sdxl640 --M 16384 --no-res 2>&1 | tail -9 | cut -c1-110
-echo "== SDXL D=1280 (L=1024, B=4): linears"; timeout 300 python tools/bench_linear.py --model sdxl1280 --M 4096 --no-res 2>&1 | tail -9 | cut -c1-110
-echo "== attention"; timeout 200 python tools/bench_attn.py --B 4 --H 10 --L 4096 2>&1 | tail -2
-timeout 200 python tools/bench_attn.py --B 4 --H 10 --L 4096 --Lk 231 2>&1 | tail -2
-timeout 200 python tools/bench_attn.py --B 4 --H 20 --L 1024 2>&1 | tail -2
-timeout 200 python tools/bench_attn.py --B 4 --H 20 --L 1024 --Lk 231 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_elementwise.py tests/test_gpu_block.py tests/test_gpu_train.py -x -q 2>&1 | tail -2
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches_per_step')}, d['clocks'])"

@@ -402,6 +402,19 @@ extern "C" int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t
   return patch_common(patches, img, B, C, H, W, p, order, false, S(stream));
 }
 
+extern "C" int vpt_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t rows, int64_t row_bytes,
+                             vpt_stream_t stream) {
+  VPT_REQUIRE(dst && rows > 0 && row_bytes > 0, "vpt_copy_rows: bad arguments");
+  VPT_REQUIRE(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(dst_pitch) |
+                static_cast<uintptr_t>(src_pitch) | static_cast<uintptr_t>(row_bytes)) & 15) == 0,
+              "vpt_copy_rows: pointers, pitches and the row length must be multiples of 16 bytes");
+  const long vec = row_bytes / 16;
+  VPT_CUDA_OK(launch_pdl(copy_rows_kernel, dim3(blocks_for(rows * vec, 256, 148 * 8)), dim3(256), 0, S(stream),
+                         static_cast<uint8_t*>(dst), static_cast<long>(dst_pitch), static_cast<const uint8_t*>(src),
+                         static_cast<long>(src_pitch), static_cast<long>(rows), vec));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ optimiser / loss
 extern "C" int vpt_grad_sumsq(const float* g, int64_t n, float scale, float* out, vpt_stream_t stream) {
   VPT_REQUIRE(g && out && n > 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "vpt_grad_sumsq: bad arguments");

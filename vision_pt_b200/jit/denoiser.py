@@ -255,7 +255,7 @@ class JiTBlockFn(torch.autograd.Function):
             # JiT re-appends the ORIGINAL context tokens in front of every block >= context_start_block and strips the
             # block's outputs for them (reference denoiser.py:1092-1113): with the slots kept in the buffer that is one small
             # strided copy here (and zeroing their gradient in backward) instead of a torch.cat of all tokens per block
-            y3[:, n_keep:].copy_(tail)
+            ops.copy_token_slots(y3, n_keep, tail)
         return y3
 
     @staticmethod
@@ -339,7 +339,7 @@ class JiTBlockFn(torch.autograd.Function):
             if fresh_in:
                 # this block's input had its context slots REPLACED by the previous block's epilogue: no gradient flows
                 # through them into that block (the reference strips those rows, denoiser.py:1111-1113)
-                dx[:, n_keep:].zero_()
+                ops.copy_token_slots(dx, n_keep, None)
         return (dx, None, None, None, *grads)
 
 

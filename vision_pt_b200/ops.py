@@ -758,3 +758,27 @@ def radam_schedulefree_step(param, grad32, z, exp_avg_sq, sched, coef, lr, betas
 def radam_schedulefree_swap(param, z, beta1: float, to_eval: bool) -> None:
     """optimizer.eval() / optimizer.train() of the package: y -> x (the averaged iterate) and back."""
     _lib.call("vpt_radam_schedulefree_swap", _p(param), _p(z), param.numel(), float(beta1), int(to_eval), _stream())
+
+
+def copy_token_slots(dst3: torch.Tensor, start: int, src3: torch.Tensor | None) -> None:
+    """dst3[:, start:] = src3 (or 0 when src3 is None) for a [B, L, D] token buffer: the per-block context-slot refresh of
+    JiT (reference denoiser.py:1092-1113) as one 16-byte-vectorised launch; falls back to torch for odd alignments."""
+    B, L, D = dst3.shape
+    n = L - start
+    if n <= 0:
+        return
+    view = dst3[:, start:]
+    es = dst3.element_size()
+    ok = (dst3.is_cuda and dst3.stride(2) == 1 and dst3.stride(1) == D and (n * D * es) % 16 == 0
+          and (dst3.stride(0) * es) % 16 == 0 and view.data_ptr() % 16 == 0)
+    if src3 is not None:
+        ok = ok and src3.dtype == dst3.dtype and tuple(src3.shape) == (B, n, D) and src3.stride(2) == 1 and src3.stride(1) == D \
+            and (src3.stride(0) * es) % 16 == 0 and src3.data_ptr() % 16 == 0
+    if not ok:
+        if src3 is None:
+            view.zero_()
+        else:
+            view.copy_(src3)
+        return
+    _lib.call("vpt_copy_rows", _p(view), dst3.stride(0) * es, _p(src3), 0 if src3 is None else src3.stride(0) * es, B,
+              n * D * es, _stream())
