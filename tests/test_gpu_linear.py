@@ -164,3 +164,33 @@ def test_sdxl_transformer_block_linears(K, N, bias, rank):
     assert rel_err(xg.grad, xr.grad) <= TOL
     assert rel_err(layer.lora_down.weight.grad, down.grad) <= TOL
     assert rel_err(layer.lora_up.weight.grad, up.grad) <= TOL
+
+
+@pytest.mark.parametrize("K,N", [(768, 768), (768, 2048), (2048, 768)])
+def test_full_size_jit_b_linear(K, N):
+    """BASELINE.json configs[1] size: M = 64 x 330 = 21120 rows (the CTA-pair route, several waves of tiles, a ragged last
+    row tile) -- forward, dX and the LoRA gradients against the oracle's formula evaluated in fp32 on the same device, plus
+    the size-independent properties: zero-initialised lora_up leaves the base output untouched, and rows are independent
+    (any row slice of the big call equals the same rows computed alone)."""
+    M = 21120
+    layer, w_ref, x = _make(M, K, N, 16, True, bias=True, seed=K + N)
+    xg = x.cuda().requires_grad_(True)
+    y = layer(xg)
+    dy = torch.randn(M, N).to(torch.bfloat16).cuda()
+    y.backward(dy)
+    wd = oj.dense_weight(w_ref).float().cuda()
+    xr = x.cuda().float().requires_grad_(True)
+    down = layer.lora_down.weight.detach().float().requires_grad_(True)
+    up = layer.lora_up.weight.detach().float().requires_grad_(True)
+    yr = oj.lora_linear(xr, wd, layer.linear.bias.detach().float(), down, up, alpha=2.0)
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= TOL and rel_err(xg.grad, xr.grad) <= TOL
+    assert rel_err(layer.lora_down.weight.grad, down.grad) <= TOL and rel_err(layer.lora_up.weight.grad, up.grad) <= TOL
+    with torch.no_grad():
+        rows = slice(20991, 21120)                         # the ragged tail of the last 256-row tile
+        y_tail = layer(x[rows].cuda())
+        assert rel_err(y_tail, y[rows]) <= 1e-6 + 2 ** -7   # same arithmetic, possibly another route (prologue vs pair)
+        layer.lora_up.weight.zero_()
+        y0 = layer(x.cuda())
+        yb = layer.linear(x.cuda())
+        assert torch.equal(y0, yb)
