@@ -14,15 +14,17 @@ ap.add_argument("--H", type=int, default=12)
 ap.add_argument("--L", type=int, default=330)
 ap.add_argument("--Lk", type=int, default=0, help="key length (0 = L): cross-attention")
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--hd", type=int, default=64)
 args = ap.parse_args()
 B, H, L = args.B, args.H, args.L
 Lk = args.Lk or L
 dev = torch.device("cuda")
 torch.manual_seed(0)
-mk = lambda n=L: torch.randn(B, n, H, 64, device=dev).to(torch.bfloat16).permute(0, 2, 1, 3)
+HD = args.hd
+mk = lambda n=L: torch.randn(B, n, H, HD, device=dev).to(torch.bfloat16).permute(0, 2, 1, 3)
 sets = [(mk(), mk(Lk), mk(Lk), mk()) for _ in range(4)]
 seq = torch.randint(max(1, Lk - 56), Lk + 1, (B,), device=dev, dtype=torch.int32)
-fl_f = 4.0 * B * H * L * Lk * 64
+fl_f = 4.0 * B * H * L * Lk * HD
 
 
 def timed(fn):
@@ -44,10 +46,10 @@ def timed(fn):
     return 1e3 * best / args.iters
 
 
-fw = lambda i: ops.attn_fwd_raw(sets[i % 4][0], sets[i % 4][1], sets[i % 4][2], seq, 0.125)
+fw = lambda i: ops.attn_fwd_raw(sets[i % 4][0], sets[i % 4][1], sets[i % 4][2], seq, HD ** -0.5)
 us = timed(fw)
 print(f"fwd  B={B} H={H} L={L}x{Lk}: {us:8.1f} us  {fl_f / us / 1e6:7.1f} TF (full LxL)")
-outs = [ops.attn_fwd_raw(s[0], s[1], s[2], seq, 0.125) for s in sets]
-bw = lambda i: ops.attn_bwd_raw(sets[i % 4][0], sets[i % 4][1], sets[i % 4][2], outs[i % 4][0], sets[i % 4][3], outs[i % 4][1], seq, 0.125)
+outs = [ops.attn_fwd_raw(s[0], s[1], s[2], seq, HD ** -0.5) for s in sets]
+bw = lambda i: ops.attn_bwd_raw(sets[i % 4][0], sets[i % 4][1], sets[i % 4][2], outs[i % 4][0], sets[i % 4][3], outs[i % 4][1], seq, HD ** -0.5)
 us = timed(bw)
 print(f"bwd  B={B} H={H} L={L}x{Lk}: {us:8.1f} us  {2.5 * fl_f / us / 1e6:7.1f} TF (incl. dq zero-fill + delta pre-pass)")

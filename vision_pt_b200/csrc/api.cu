@@ -243,6 +243,10 @@ extern "C" int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, 
                             const int32_t* seqlens_k, float scale, float* lse2, vpt_stream_t stream) {
   VPT_REQUIRE(q && k && v && o && lse2 && B > 0 && H > 0 && Lq > 0 && Lk > 0, "vpt_attn_fwd: bad arguments");
   if (head_dim == 64) return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream));
+  // head_dim 80 (JiT-H): forward on the tensor cores; VPT_ATTN80_SIMPLE=1 keeps the CUDA-core kernel (same lse2 layout)
+  static const bool simple80 = getenv("VPT_ATTN80_SIMPLE") != nullptr;
+  if (head_dim == 80 && !simple80)
+    return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream), 80);
   return launch_attn_simple_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, head_dim, seqlens_k, scale, lse2, S(stream));
 }
 extern "C" int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, const vpt_attn_tensor* v,

@@ -41,18 +41,24 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));   // * 2^rint(x)
 }
 
-struct AttnFwdSmem {
-  // per stream (X = 0, 1): Q[2] (item double buffer), K[2], V[2] (key-block stages): 6 x 16 KB
-  static constexpr int kStream = 6 * 16384;
-  static constexpr int kQ = 0, kK = 2 * 16384, kV = 4 * 16384;
-  static constexpr int kOut = 2 * kStream;        // 8 softmax warps x one slab of [32 rows x 128 B] (output tile -> TMA store)
+template <int HD>
+struct AttnFwdSmemT {
+  static constexpr int kBlk = (HD + 63) / 64;          // 64-column (128-byte, swizzled) blocks per row: 80 -> 2, the second
+  static constexpr int kTile = kBlk * 16384;           // zero-filled past the head dimension by the TMA unit
+  static constexpr int kStreams = HD == 64 ? 2 : 1;    // 6 tiles per stream: two streams only fit at head_dim 64
+  // per stream (X = 0, 1): Q[2] (item double buffer), K[2], V[2] (key-block stages)
+  static constexpr int kStream = 6 * kTile;
+  static constexpr int kQ = 0, kK = 2 * kTile, kV = 4 * kTile;
+  static constexpr int kOut = kStreams * kStream;   // 8 softmax warps x one slab of [32 rows x 128 B] (output tile -> TMA store)
   static constexpr int kXchg = kOut + 8 * 4096;   // per stream: 2 block parities x 2 column halves x 128 rows, bf16 row maxima
   static constexpr int kBars = kXchg + 2 * 1024;
   // per stream: q_full[2] q_empty[2] kv_full[2] kv_empty[2] s_full p_full (256 arrivals) pv_done  (11)
   static constexpr int kBarsPerStream = 11;
   static constexpr int kTmemSlot = kBars + 2 * kBarsPerStream * 8;
   static constexpr int kTotal = kTmemSlot + 16;   // no alignment slack: the dynamic segment starts 1024B-aligned
+  static_assert(kTotal <= 232448, "shared memory");
 };
+using AttnFwdSmem = AttnFwdSmemT<64>;
 
 // Persistent CTAs (one per SM) run TWO independent streams, each walking its own work items (128-query tile, head,
 // sample) with its own softmax warpgroup, MMA-issuing warp, TMA producer warp, Q / K / V buffers and TMEM columns:
@@ -74,10 +80,16 @@ struct AttnFwdSmem {
 // Eight softmax warps per stream (two per TMEM lane quarter): with four, a scheduler held two softmax warps and the
 // tcgen05.ld -> ex2 -> tcgen05.st chains were latency-bound (MUFU 30 % busy, profiles/r1o_attn_fwd_ncu.txt).
 // Warps: 0 / 2 TMA producers of stream A / B (2 also allocates TMEM), 1 / 3 MMA issuers, 4-11 softmax A, 12-19 softmax B.
+// head_dim 80 (JiT-H): the same kernel on two-block tiles -- QK^T runs a fifth k-step over the second block, O += P V uses
+// N = 80 across both blocks (MN-major operand, leading-block stride = one 16 KB block) -- with ONE stream per CTA (six
+// 32 KB tiles fill the shared memory; the second stream's warps retire at once) and the output written straight from
+// registers.
+template <int HD>
 __global__ void __launch_bounds__(640, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnFwdParams p) {
-  using S = AttnFwdSmem;
+  using S = AttnFwdSmemT<HD>;
+  constexpr int kTile = S::kTile;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need a 1024B-aligned base
@@ -85,7 +97,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int X = warp < 4 ? (warp >> 1) : ((warp - 4) >> 3);          // stream of this warp
-  uint8_t* sm = smem + X * S::kStream;
+  uint8_t* sm = smem + (X < S::kStreams ? X : 0) * S::kStream;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars) + X * S::kBarsPerStream;
   uint64_t* q_full = bars;          // [2]
   uint64_t* q_empty = bars + 2;     // [2]
@@ -97,7 +109,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int nqt = (p.Lq + kAttnTile - 1) / kAttnTile;
   const int num_items = nqt * p.H * p.B;
-  const int first_item = blockIdx.x * 2 + X, item_stride = gridDim.x * 2;
+  const int first_item = blockIdx.x * S::kStreams + X, item_stride = gridDim.x * S::kStreams;
+  const bool idle = X >= S::kStreams;             // head_dim 80: no second stream
   auto klen_of = [&](int item) {
     if (item >= num_items) return 0;
     if (p.seqlens_k == nullptr) return p.Lk;
@@ -120,11 +133,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base + X * 256, tO = tS + 128, tP = tS + 192;   // per stream: S 0..127, O 128..191, P 192..255
+  // per stream: S 0..127, O 128..128+HD-1, P (64 columns of bf16 pairs) behind it; stream 1 starts at column 256
+  const uint32_t tS = tmem_base + X * 256, tO = tS + 128, tP = tO + (HD == 64 ? 64 : 80);
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == 0 || warp == 2) {
+  if (idle) {
+    // nothing: joins the final barrier below
+  } else if (warp == 0 || warp == 2) {
     // ============================================================ TMA producer of stream X
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
@@ -136,31 +152,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int nblk = (klen_of(item) + kAttnTile - 1) / kAttnTile;
         const uint32_t qb = it & 1;
         mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qb], 16384);
-        tma_load_4d(&tmQ, &q_full[qb], sm + S::kQ + qb * 16384, 0, qt * kAttnTile, h, b);
+        mbar_arrive_expect_tx(&q_full[qb], kTile);
+#pragma unroll
+        for (int blk = 0; blk < S::kBlk; ++blk)
+          tma_load_4d(&tmQ, &q_full[qb], sm + S::kQ + qb * kTile + blk * 16384, blk * 64, qt * kAttnTile, h, b);
         for (int j = 0; j < nblk; ++j, ++jj) {
           const uint32_t s = jj & 1;
           mbar_wait(&kv_empty[s], ((jj >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 32768);
-          tma_load_4d(&tmK, &kv_full[s], sm + S::kK + s * 16384, 0, j * kAttnTile, h, b);
-          tma_load_4d(&tmV, &kv_full[s], sm + S::kV + s * 16384, 0, j * kAttnTile, h, b);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * kTile);
+#pragma unroll
+          for (int blk = 0; blk < S::kBlk; ++blk) {
+            tma_load_4d(&tmK, &kv_full[s], sm + S::kK + s * kTile + blk * 16384, blk * 64, j * kAttnTile, h, b);
+            tma_load_4d(&tmV, &kv_full[s], sm + S::kV + s * kTile + blk * 16384, blk * 64, j * kAttnTile, h, b);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuer of stream X (converged warp, one elected lane)
-    constexpr uint32_t kIdO = umma_idesc_bf16(128, 64, 0, 1);    // O += P V  (V is MN-major)
+    constexpr uint32_t kIdO = umma_idesc_bf16(128, HD, 0, 1);    // O += P V  (V is MN-major)
     const uint32_t sbase = smem_u32(sm);
     const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
-    const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);
+    const uint64_t dMN = umma_smem_desc(0, 16384, 1024, kLayoutSW128);   // MN-major: 64-column blocks 16 KB apart
     uint32_t it = 0, jj = 0, pc = 0;
     PROF_DECL(8)
     for (int item = first_item; item < num_items; item += item_stride, ++it) {
       const int kl = klen_of(item);
       const int nblk = (kl + kAttnTile - 1) / kAttnTile;
       const uint32_t qb = it & 1;
-      const uint64_t qd = dK_ + ((sbase + S::kQ + qb * 16384) >> 4);
+      const uint64_t qd = dK_ + ((sbase + S::kQ + qb * kTile) >> 4);
       // S = Q K_j^T (the softmax halves have read the previous S: p_full)
       auto issue_s = [&](int j, uint32_t jn) {
         const uint32_t s = jn & 1;
@@ -170,11 +191,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&kv_full[s], (jn >> 1) & 1);
         PROF(1)
         tc_fence_after_sync();
-        const uint64_t kd = dK_ + ((sbase + S::kK + s * 16384) >> 4);
+        const uint64_t kd = dK_ + ((sbase + S::kK + s * kTile) >> 4);
         const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, idesc, k != 0);
+#pragma unroll
+          for (int k = 0; k < (HD - 64) / 16; ++k)        // head-dim columns 64.. : the tiles' second block (+16 KB)
+            umma_ss(tS, qd + 1024 + 2 * k, kd + 1024 + 2 * k, idesc, 1);
           umma_commit(s_full);
         }
         __syncwarp();
@@ -186,7 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (nblk > 0) issue_s(0, jj);
       for (int j = 0; j < nblk; ++j, ++jj) {
         const uint32_t s = jj & 1;
-        const uint64_t vd = dMN + ((sbase + S::kV + s * 16384) >> 4);
+        const uint64_t vd = dMN + ((sbase + S::kV + s * kTile) >> 4);
         const int valid = min(128, kl - j * 128);
         const int n = (valid + 15) & ~15;
         PROF(0)
@@ -292,6 +316,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
               tmem_st32(tO + lane_off + c * 32, o);
             }
+            if (HD > 64) {
+              uint32_t o[16];
+              tmem_ld16(tO + lane_off + 64, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + lane_off + 64, o);
+            }
           }
         }
         PROF(3)
@@ -348,33 +380,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // row pitch = Lq rounded up to 128 (one bulk copy per tile in the backward); +inf for padded queries
         p.lse2[(static_cast<long>(b) * p.H + h) * (static_cast<long>(nqt) * kAttnTile) + q] =
             q < p.Lq ? (l_run > 0.f ? m_ref + log2f(l_run) : -INFINITY) : INFINITY;
-        if (lane == 0) tma_store_wait_read<0>();     // the previous item's store has read the slab
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          if (nblk > 0) {                            // stream-uniform: the .sync.aligned load stays convergent
-            tmem_ld32(tO + lane_off + c * 32, o);
-            tmem_wait_ld();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0u;
+        if constexpr (HD == 64) {
+          if (lane == 0) tma_store_wait_read<0>();     // the previous item's store has read the slab
+          __syncwarp();
+  #pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            if (nblk > 0) {                            // stream-uniform: the .sync.aligned load stays convergent
+              tmem_ld32(tO + lane_off + c * 32, o);
+              tmem_wait_ld();
+            } else {
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
+  #pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + (((c * 4 + g) ^ (lane & 7)) * 16)),
+                           "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l)),
+                           "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l)),
+                           "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l)),
+                           "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l))
+                           : "memory");
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (qt * kAttnTile + qd * 32 < p.Lq)       // rows past Lq inside the box are clipped by the TMA unit
+              tma_store_4d(&tmO, out_slab, 0, qt * kAttnTile + qd * 32, h, b);
+            tma_store_commit();
+          }
+        } else {
+          // head_dim 80: 160-byte rows straight from registers (no room for a slab beside six 32 KB tiles)
+          __nv_bfloat16* orow = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + (((c * 4 + g) ^ (lane & 7)) * 16)),
-                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l)),
-                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l)),
-                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l)),
-                         "r"(pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l))
-                         : "memory");
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (qt * kAttnTile + qd * 32 < p.Lq)       // rows past Lq inside the box are clipped by the TMA unit
-            tma_store_4d(&tmO, out_slab, 0, qt * kAttnTile + qd * 32, h, b);
-          tma_store_commit();
+          for (int c = 0; c < 3; ++c) {
+            uint32_t o[32];
+            if (nblk > 0) {
+              if (c < 2) {
+                tmem_ld32(tO + lane_off + c * 32, o);
+              } else {
+                tmem_ld16(tO + lane_off + 64, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+              }
+              tmem_wait_ld();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
+            if (q < p.Lq) {
+#pragma unroll
+              for (int g = 0; g < (c < 2 ? 4 : 2); ++g) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  w[e] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * e]) * inv_l, __uint_as_float(o[g * 8 + 2 * e + 1]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
         }
         // the accumulator is read: order those loads before this half's next p_full arrival, after which the issuer
         // overwrites O (accumulate = 0 on the next item's first block)

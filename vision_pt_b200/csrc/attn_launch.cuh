@@ -12,8 +12,9 @@ struct AttnTensor {
   long sb, sl, sh;   // element strides of (batch, token, head); head_dim is contiguous
 };
 
-inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int L, int box_rows = kAttnTile) {
-  const uint64_t dims[4] = {static_cast<uint64_t>(kAttnHD), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
+inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int L, int box_rows = kAttnTile, int hd = kAttnHD) {
+  // head_dim 80: the 64-column box at column 64 is zero-filled past column 80
+  const uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
                             static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(t.sl) * 2, static_cast<uint64_t>(t.sh) * 2,
                                static_cast<uint64_t>(t.sb) * 2};
@@ -21,13 +22,14 @@ inline int make_attn_tmap(CUtensorMap* m, const AttnTensor& t, int B, int H, int
   return make_tmap_bf16_4d(m, t.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,
-                           int H, int Lq, int Lk, const int* seqlens_k, float scale, float* lse2,
-                           cudaStream_t stream) {
+template <int HD>
+inline int launch_attn_fwd_t(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,
+                             int H, int Lq, int Lk, const int* seqlens_k, float scale, float* lse2, cudaStream_t stream) {
+  using Smem = AttnFwdSmemT<HD>;
   if ((o.sl | o.sh | o.sb) & 7) return fail("attention output strides must be multiples of 8 elements");
   CUtensorMap tq, tk, tv, to;
-  if (make_attn_tmap(&tq, q, B, H, Lq) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk) ||
-      make_attn_tmap(&to, o, B, H, Lq, 32))
+  if (make_attn_tmap(&tq, q, B, H, Lq, kAttnTile, HD) || make_attn_tmap(&tk, k, B, H, Lk, kAttnTile, HD) ||
+      make_attn_tmap(&tv, v, B, H, Lk, kAttnTile, HD) || make_attn_tmap(&to, o, B, H, Lq, 32, HD))
     return 1;
   AttnFwdParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
@@ -38,14 +40,20 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   p.lse2 = lse2;
   static bool attr = false;
   if (!attr) {
-    VPT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
+    VPT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal));
     attr = true;
   }
   const int items = ((Lq + kAttnTile - 1) / kAttnTile) * H * B;
-  const int ctas = (items + 1) / 2;              // two streams (items) per CTA
+  const int ctas = (items + Smem::kStreams - 1) / Smem::kStreams;   // one item stream per CTA at head_dim 80, two at 64
   const int slots = sm_count();
-  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3(ctas < slots ? ctas : slots), dim3(640), AttnFwdSmem::kTotal, stream, tq, tk, tv, to, p));
+  VPT_CUDA_OK(launch_pdl(attn_fwd_kernel<HD>, dim3(ctas < slots ? ctas : slots), dim3(640), Smem::kTotal, stream, tq, tk, tv, to, p));
   return 0;
+}
+inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,
+                           int H, int Lq, int Lk, const int* seqlens_k, float scale, float* lse2,
+                           cudaStream_t stream, int head_dim = 64) {
+  if (head_dim == 80) return launch_attn_fwd_t<80>(q, k, v, o, B, H, Lq, Lk, seqlens_k, scale, lse2, stream);
+  return launch_attn_fwd_t<64>(q, k, v, o, B, H, Lq, Lk, seqlens_k, scale, lse2, stream);
 }
 
 // dq_f32 must be zero on entry (fp32, same (b, l, h) element strides as given); delta is a [B,H,Lq] fp32 workspace.
