@@ -492,4 +492,30 @@ __global__ void attn_bwd_delta_kernel(const AttnDeltaParams p) {
   if (gid < total && sub == 0) p.delta[gid] = acc * p.scale;
 }
 
+// the same for any head_dim that is a multiple of 8: one thread per (b, h, q) row
+template <int HD>
+__global__ void __launch_bounds__(256) attn_bwd_delta_row_kernel(const AttnDeltaParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(p.B) * p.H * p.Lq_pad;
+  if (gid >= total) return;
+  const int q = gid % p.Lq_pad;
+  const int h = (gid / p.Lq_pad) % p.H;
+  const int b = gid / (static_cast<long>(p.Lq_pad) * p.H);
+  float acc = 0.f;
+  if (q < p.Lq) {
+    const __nv_bfloat16* o = p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh;
+    const __nv_bfloat16* g = p.d_o + b * p.do_sb + static_cast<long>(q) * p.do_sl + h * p.do_sh;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + c * 8)), w = __ldg(reinterpret_cast<const uint4*>(g + c * 8));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc += bf16lo(aw[i]) * bf16lo(gw[i]) + bf16hi(aw[i]) * bf16hi(gw[i]);
+    }
+  }
+  p.delta[gid] = acc * p.scale;
+}
+
 }  // namespace vpt

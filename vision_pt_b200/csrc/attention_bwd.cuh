@@ -42,31 +42,44 @@ struct AttnBwd2Params {
   int nk, nq, num_items;       // key tiles, query tiles, B * H * nk
 };
 
-struct AttnBwd2Smem {
-  static constexpr int kSlots = 5;                   // Q / dO ring: sub-tile slots of [64 queries x 64] bf16 each
-  static constexpr int kK = 0;                       // 2 buffers x 16 KB
-  static constexpr int kV = 32768;                   // 2 buffers x 16 KB
-  static constexpr int kQ = 65536;
-  static constexpr int kDO = kQ + kSlots * 8192;
-  static constexpr int kDST = kDO + kSlots * 8192;   // 2 buffers x [128 keys x 128 queries] bf16 = 2 K-atoms (A, B) each
-  static constexpr int kDQ = kDST + 2 * 32768;       // 4 drain warps x one slab of [32 x 128 B], 128B-swizzled
-  static constexpr int kStats = kDQ + 4 * 4096;      // per slot: lse2[64], delta*scale[64] fp32
+// head_dim 64: the layout described above.  head_dim 80 (JiT-H): every operand tile is two 128-byte-swizzled 64-column
+// blocks (the second zero-filled past column 80 by the TMA unit), which doubles K / V / Q / dO in shared memory -- so K / V
+// are single-buffered, the Q / dO ring has 3 slots, dS^T one buffer, and (TMEM: 2 * 64 + 2 * 64 + 3 * 80 = 496 columns) P^T is
+// written over the S^T columns it came from, which ties the next S^T_X to the dV MMA of the current one.
+template <int HD>
+struct AttnBwd2SmemT {
+  static constexpr int kBlk = (HD + 63) / 64;         // 64-column blocks per operand row
+  static constexpr int kSlots = HD == 64 ? 5 : 3;     // Q / dO ring: sub-tile slots of [64 queries x HD] bf16 each
+  static constexpr int kKVBufs = HD == 64 ? 2 : 1;
+  static constexpr int kDSTBufs = HD == 64 ? 2 : 1;
+  static constexpr bool kPInPlace = HD != 64;         // P^T_X over S^T_X columns [0, 32)
+  static constexpr int kSub = kBlk * 8192;            // one Q or dO sub-tile
+  static constexpr int kKVTile = kBlk * 16384;        // one K or V tile
+  static constexpr int kK = 0;
+  static constexpr int kV = kKVBufs * kKVTile;
+  static constexpr int kQ = 2 * kKVBufs * kKVTile;
+  static constexpr int kDO = kQ + kSlots * kSub;
+  static constexpr int kDST = kDO + kSlots * kSub;    // kDSTBufs x [128 keys x 128 queries] bf16 = 2 K-atoms (A, B) each
+  static constexpr int kDQ = kDST + kDSTBufs * 32768; // 4 drain warps x one slab of [32 x 128 B], 128B-swizzled
+  static constexpr int kStats = kDQ + 4 * 4096;       // per slot: lse2[64], delta*scale[64] fp32
   static constexpr int kBars = kStats + kSlots * 512;
   // kv_full[2] kv_empty[2] s_full[2] p_full[2] mma2_done[2] st_free[2] dvdk_done[2] dq_free dkv_free
   // qdo_full[kSlots] qdo_empty[kSlots]
   static constexpr int kNumBars = 16 + 2 * kSlots;
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
-  static constexpr int kTotal = kTmemSlot + 16;      // no alignment slack: the dynamic segment starts 1024B-aligned
+  static constexpr int kTotal = kTmemSlot + 16;       // no alignment slack: the dynamic segment starts 1024B-aligned
   static_assert(kTotal <= 232448, "shared memory");
 };
+using AttnBwd2Smem = AttnBwd2SmemT<64>;
 
 __device__ __forceinline__ int attn_round16(int x) { return (x + 15) & ~15; }
 
 // Position in the Q / dO ring; every role steps it once per PRESENT sub-tile, in the order A(i), B(i), A(i+1), ...
-struct AttnRing {
+template <int kSlots>
+struct AttnRingT {
   uint32_t slot = 0, phase = 0;
   __device__ __forceinline__ void next() {
-    if (++slot == AttnBwd2Smem::kSlots) {
+    if (++slot == kSlots) {
       slot = 0;
       phase ^= 1;
     }
@@ -76,12 +89,14 @@ struct AttnRing {
 // tmQ / tmDO: 4-D bf16 maps (hd, L, H, B), box {64, 64, 1, 1}; tmK / tmV: box {64, 128, 1, 1}; all SWIZZLE_128B
 // tmDQ: 4-D fp32 map (hd, Lq, H, B) of the dQ accumulator, box {32, 32, 1, 1}, SWIZZLE_128B
 // tmDK / tmDV: 4-D bf16 maps (hd, Lk, H, B) of the outputs, box {64, 32, 1, 1}, SWIZZLE_128B
+template <int HD>
 __global__ void __launch_bounds__(512, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                  const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
                  const __grid_constant__ CUtensorMap tmDV, const AttnBwd2Params p) {
-  using S = AttnBwd2Smem;
+  using S = AttnBwd2SmemT<HD>;
+  using AttnRing = AttnRingT<S::kSlots>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need a 1024B-aligned base
@@ -128,9 +143,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  // columns: S^T_A 0, S^T_B 64, dP^T_A 128, dP^T_B 192, dV 256, dK 320, dQ 384, P^T_A 448, P^T_B 480 (bf16 pairs)
-  const uint32_t tST = tmem_base, tDPT = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
-                 tDQ = tmem_base + 384, tPT = tmem_base + 448;
+  // columns (head_dim 64): S^T_A 0, S^T_B 64, dP^T_A 128, dP^T_B 192, dV 256, dK 320, dQ 384, P^T_A 448, P^T_B 480 (bf16
+  // pairs); head_dim 80: dV 256, dK 336, dQ 416 and P^T_X over S^T_X
+  const uint32_t tST = tmem_base, tDPT = tmem_base + 128, tDV = tmem_base + 256, tDK = tDV + HD, tDQ = tDK + HD;
+  auto tPT_of = [&](int X) { return S::kPInPlace ? tST + X * 64 : tmem_base + 448 + X * 32; };
 
   // queries of tile i that sub-tile X covers, rounded up to the UMMA granularity (0 = sub-tile absent)
   auto sub_n = [&](int i, int X) {
@@ -153,9 +169,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (sub_n(i, X) == 0) continue;
             mbar_wait(&qdo_empty[r.slot], r.phase ^ 1);
             uint64_t* full = &qdo_full[r.slot];
-            mbar_arrive_expect_tx(full, 16384 + 512);
-            tma_load_4d(&tmQ, full, smem + S::kQ + r.slot * 8192, 0, i * 128 + X * 64, h, b);
-            tma_load_4d(&tmDO, full, smem + S::kDO + r.slot * 8192, 0, i * 128 + X * 64, h, b);
+            mbar_arrive_expect_tx(full, 2 * S::kSub + 512);
+#pragma unroll
+            for (int blk = 0; blk < S::kBlk; ++blk) {
+              tma_load_4d(&tmQ, full, smem + S::kQ + r.slot * S::kSub + blk * 8192, blk * 64, i * 128 + X * 64, h, b);
+              tma_load_4d(&tmDO, full, smem + S::kDO + r.slot * S::kSub + blk * 8192, blk * 64, i * 128 + X * 64, h, b);
+            }
             const long srow = stat_row + i * 128 + X * 64;
             bulk_load_1d(smem + S::kStats + r.slot * 512, p.lse2 + srow, 256, full);
             bulk_load_1d(smem + S::kStats + r.slot * 512 + 256, p.delta + srow, 256, full);
@@ -174,21 +193,25 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t n = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
         const int kt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
-        const uint32_t kb = n & 1;
-        mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[kb], 32768);
-        tma_load_4d(&tmK, &kv_full[kb], smem + S::kK + kb * 16384, 0, kt * 128, h, b);
-        tma_load_4d(&tmV, &kv_full[kb], smem + S::kV + kb * 16384, 0, kt * 128, h, b);
+        const uint32_t kb = n % S::kKVBufs;
+        mbar_wait(&kv_empty[kb], ((n / S::kKVBufs) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[kb], 2 * S::kKVTile);
+#pragma unroll
+        for (int blk = 0; blk < S::kBlk; ++blk) {
+          tma_load_4d(&tmK, &kv_full[kb], smem + S::kK + kb * S::kKVTile + blk * 16384, blk * 64, kt * 128, h, b);
+          tma_load_4d(&tmV, &kv_full[kb], smem + S::kV + kb * S::kKVTile + blk * 16384, blk * 64, kt * 128, h, b);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuers (converged warps, one elected lane issues)
-    constexpr uint32_t kIdKM64 = umma_idesc_bf16(128, 64, 0, 1);   // dV += P^T dO, dK += dS^T Q (B MN-major)
-    constexpr uint32_t kIdMM = umma_idesc_bf16(128, 64, 1, 1);     // dQ = dS K (A = dS^T viewed MN-major, B MN-major)
+    constexpr uint32_t kIdKM64 = umma_idesc_bf16(128, HD, 0, 1);   // dV += P^T dO, dK += dS^T Q (B MN-major, N = head_dim)
+    constexpr uint32_t kIdMM = umma_idesc_bf16(128, HD, 1, 1);     // dQ = dS K (A = dS^T viewed MN-major, B MN-major)
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);       // K-major operand, + (addr >> 4)
-    const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);     // MN-major, one 64-wide block
+    const uint64_t dMN = umma_smem_desc(0, 8192, 1024, kLayoutSW128);     // MN-major Q / dO sub-tile: 64-column blocks 8 KB apart
+    const uint64_t dMNkv = umma_smem_desc(0, 16384, 1024, kLayoutSW128);  // MN-major K tile: 64-column blocks 16 KB apart
     const uint64_t dMNq = umma_smem_desc(0, 16384, 1024, kLayoutSW128);   // dS^T viewed MN-major (query atoms 16 KB apart)
     const uint64_t aDST0 = dK_ + ((smem_base + S::kDST) >> 4);     // + db * 2048 (32 KB buffers) + X * 1024 + 2 k
     const uint64_t aDSTq0 = dMNq + ((smem_base + S::kDST) >> 4);
@@ -203,30 +226,38 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t itn = 0;
       int i = 0;
       for (uint32_t g = 0; g < total; ++g) {
-        const uint32_t kb = itn & 1;
-        const uint64_t kd = dK_ + ((smem_base + S::kK + kb * 16384) >> 4), vd = dK_ + ((smem_base + S::kV + kb * 16384) >> 4);
+        const uint32_t kb = itn % S::kKVBufs;
+        const uint64_t kd = dK_ + ((smem_base + S::kK + kb * S::kKVTile) >> 4), vd = dK_ + ((smem_base + S::kV + kb * S::kKVTile) >> 4);
         PROF(0)
-        if (i == 0) mbar_wait(&kv_full[kb], (itn >> 1) & 1);
+        if (i == 0) mbar_wait(&kv_full[kb], (itn / S::kKVBufs) & 1);
         PROF(4)
 #pragma unroll 1
         for (int X = 0; X < 2; ++X) {
           const int n = i == nq - 1 ? n_last[X] : 64;
           if (n == 0) continue;
           PROF(0)
-          if (issued[X] > 0) mbar_wait(&st_free[X], (issued[X] - 1) & 1);   // S^T_X / dP^T_X are single-buffered
+          // S^T_X / dP^T_X are single-buffered: free once warpgroup X has them in registers -- or, with P^T_X written over
+          // S^T_X, once the dV MMA that reads it is done
+          if (issued[X] > 0) mbar_wait(S::kPInPlace ? &dvdk_done[X] : &st_free[X], (issued[X] - 1) & 1);
           ++issued[X];
           PROF(1)
           mbar_wait(&qdo_full[r.slot], r.phase);
           PROF(2)
           tc_fence_after_sync();
-          const uint64_t qd_ = dK_ + ((smem_base + S::kQ + r.slot * 8192) >> 4);
-          const uint64_t dod = dK_ + ((smem_base + S::kDO + r.slot * 8192) >> 4);
+          const uint64_t qd_ = dK_ + ((smem_base + S::kQ + r.slot * S::kSub) >> 4);
+          const uint64_t dod = dK_ + ((smem_base + S::kDO + r.slot * S::kSub) >> 4);
           const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_ss(tST + X * 64, kd + 2 * k, qd_ + 2 * k, idesc, k != 0);
 #pragma unroll
+            for (int k = 0; k < (HD - 64) / 16; ++k)      // head-dim columns 64..: second blocks (+16 KB of K / V, +8 KB of Q / dO)
+              umma_ss(tST + X * 64, kd + 1024 + 2 * k, qd_ + 512 + 2 * k, idesc, 1);
+#pragma unroll
             for (int k = 0; k < 4; ++k) umma_ss(tDPT + X * 64, vd + 2 * k, dod + 2 * k, idesc, k != 0);
+#pragma unroll
+            for (int k = 0; k < (HD - 64) / 16; ++k)
+              umma_ss(tDPT + X * 64, vd + 1024 + 2 * k, dod + 512 + 2 * k, idesc, 1);
             umma_commit(&s_full[X]);
           }
           __syncwarp();
@@ -250,11 +281,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t itn = 0;
       int i = 0;
       for (uint32_t g = 0; g < total; ++g) {
-        const uint32_t kb = itn & 1;
-        const uint64_t kmn = dMN + ((smem_base + S::kK + kb * 16384) >> 4);
-        const uint32_t db = g & 1;                    // dS^T buffer of this tile
+        const uint32_t kb = itn % S::kKVBufs;
+        const uint64_t kmn = dMNkv + ((smem_base + S::kK + kb * S::kKVTile) >> 4);
+        const uint32_t db = g % S::kDSTBufs;          // dS^T buffer of this tile
         PROF(0)
-        if (i == 0) mbar_wait(&kv_full[kb], (itn >> 1) & 1);   // long complete (the scores came from it): acquires K for dQ
+        if (i == 0) mbar_wait(&kv_full[kb], (itn / S::kKVBufs) & 1);   // long complete (the scores came from it): acquires K for dQ
         PROF(6)
 #pragma unroll 1
         for (int X = 0; X < 2; ++X) {
@@ -267,19 +298,20 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (i == 0 && X == 0 && itn > 0) mbar_wait(dkv_free, (itn - 1) & 1);   // previous item's dV / dK are out
             PROF(2)
             tc_fence_after_sync();
-            const uint64_t qmn = dMN + ((smem_base + S::kQ + r.slot * 8192) >> 4), domn = dMN + ((smem_base + S::kDO + r.slot * 8192) >> 4);
+            const uint64_t qmn = dMN + ((smem_base + S::kQ + r.slot * S::kSub) >> 4), domn = dMN + ((smem_base + S::kDO + r.slot * S::kSub) >> 4);
+            const uint32_t tPT = tPT_of(X);
             if (elect_one_sync()) {
               if (n == 64) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {          // reduction over this sub-tile's queries
                   const uint32_t acc = (i | X | k) != 0;
-                  umma_ts(tDV, tPT + X * 32 + k * 8, domn + k * 128, kIdKM64, acc);      // A = P^T_X in TMEM
+                  umma_ts(tDV, tPT + k * 8, domn + k * 128, kIdKM64, acc);      // A = P^T_X in TMEM
                   umma_ss(tDK, aDST0 + db * 2048 + X * 1024 + 2 * k, qmn + k * 128, kIdKM64, acc);
                 }
               } else {
                 for (int k = 0; k < n / 16; ++k) {
                   const uint32_t acc = (i | X | k) != 0;
-                  umma_ts(tDV, tPT + X * 32 + k * 8, domn + k * 128, kIdKM64, acc);
+                  umma_ts(tDV, tPT + k * 8, domn + k * 128, kIdKM64, acc);
                   umma_ss(tDK, aDST0 + db * 2048 + X * 1024 + 2 * k, qmn + k * 128, kIdKM64, acc);
                 }
               }
@@ -345,12 +377,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const bool key_ok = key < klen;
       for (int i = 0; i < nq; ++i, ++f) {
         const int n = sub_n(i, X);
-        const uint32_t db = f & 1;
+        const uint32_t db = f % S::kDSTBufs, dst_use = f / S::kDSTBufs;     // buffer and how often it has been used before
         if (X == 1) r.next();                        // sub-tile A of this tile (always present) sits before ours in the ring
         if (n == 0) {
           // absent sub-tile: still observe this buffer's mma2_done phase (a parity wait is only unambiguous for a waiter
           // that is at most one phase behind)
-          if (f >= 2) mbar_wait(&mma2_done[db], ((f >> 1) - 1) & 1);
+          if (dst_use >= 1) mbar_wait(&mma2_done[db], (dst_use - 1) & 1);
           continue;
         }
         const float* st = s_stats + r.slot * 128;
@@ -397,11 +429,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               // dK / dQ MMAs of the tile two back.  Neither wait involves the other warpgroup's current tile.  (Holding
               // both chunks' P^T in registers to store them last did not pay: the wait moved into a slower schedule.)
               if (cx > 0) mbar_wait(&dvdk_done[X], (cx - 1) & 1);
-              if (f >= 2) mbar_wait(&mma2_done[db], ((f >> 1) - 1) & 1);
+              if (dst_use >= 1) mbar_wait(&mma2_done[db], (dst_use - 1) & 1);
               tc_fence_after_sync();
               PROF(4)
             }
-            tmem_st16(tPT + X * 32 + lane_off + c * 16, pk);   // 32 queries = 16 columns of bf16 pairs
+            // 32 queries = 16 columns of bf16 pairs (in place at head_dim 80: inside S^T columns that are already read)
+            tmem_st16(tPT_of(X) + lane_off + c * 16, pk);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint32_t chunk = static_cast<uint32_t>((c * 4 + g) ^ rin) * 16;
@@ -445,50 +478,66 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
       for (int i = 0; i < nq; ++i, ++f) {
-        mbar_wait(&mma2_done[f & 1], (f >> 1) & 1);
+        mbar_wait(&mma2_done[f % S::kDSTBufs], (f / S::kDSTBufs) & 1);
         tc_fence_after_sync();
         if (i == nq - 1) {
           // item finished (the wait above covered its last MMAs).  dV / dK go first: the first MMA of the next item waits
-          // for these accumulators, its dQ MMA only comes a whole tile later.  bf16 slab -> TMA store.
+          // for these accumulators, its dQ MMA only comes a whole tile later.  bf16 slab -> TMA store, 64 columns at a time
+          // (head_dim 80: the second piece holds 16 columns; the store's box is clipped at the tensor's edge).
           const int kt = item % p.nk;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            uint32_t va[32], vb[32];
-            tmem_ld32((t == 0 ? tDV : tDK) + lane_off, va);
-            tmem_ld32((t == 0 ? tDV : tDK) + lane_off + 32, vb);
-            tmem_wait_ld();
-            if (t == 1) {
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(dkv_free);  // the accumulators are read: the next item may overwrite them
-            }
-            if (lane == 0) tma_store_wait_read<0>();   // the slab's previous TMA read is done
-            __syncwarp();
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint32_t* v = g < 4 ? &va[g * 8] : &vb[(g - 4) * 8];
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ (lane & 7)) * 16)),
-                           "r"(pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]))),
-                           "r"(pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]))),
-                           "r"(pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]))),
-                           "r"(pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7])))
-                           : "memory");
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (kt * 128 + qd * 32 < p.Lk)           // rows past Lk inside the box are clipped by the TMA unit
-                tma_store_4d(t == 0 ? &tmDV : &tmDK, slab, 0, kt * 128 + qd * 32, h, b);
-              tma_store_commit();
+            for (int pc = 0; pc < S::kBlk; ++pc) {
+              uint32_t va[32], vb[32];
+              const uint32_t tacc = (t == 0 ? tDV : tDK) + lane_off + pc * 64;
+              if (pc == 0) {
+                tmem_ld32(tacc, va);
+                tmem_ld32(tacc + 32, vb);
+              } else {
+                tmem_ld16(tacc, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
+              }
+              tmem_wait_ld();
+              if (t == 1 && pc == S::kBlk - 1) {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dkv_free);  // the accumulators are read: the next item may overwrite them
+              }
+              if (lane == 0) tma_store_wait_read<0>();   // the slab's previous TMA read is done
+              __syncwarp();
+#pragma unroll
+              for (int g = 0; g < (pc == 0 ? 8 : 2); ++g) {
+                const uint32_t* v = g < 4 ? &va[g * 8] : &vb[(g - 4) * 8];
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ (lane & 7)) * 16)),
+                             "r"(pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]))),
+                             "r"(pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]))),
+                             "r"(pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]))),
+                             "r"(pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7])))
+                             : "memory");
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (kt * 128 + qd * 32 < p.Lk)           // rows past Lk inside the box are clipped by the TMA unit
+                  tma_store_4d(t == 0 ? &tmDV : &tmDK, slab, pc * 64, kt * 128 + qd * 32, h, b);
+                tma_store_commit();
+              }
             }
           }
         }
+        constexpr int kPieces = (HD + 31) / 32;      // dQ leaves in 32-column fp32 pieces (head_dim 80: the last holds 16)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kPieces; ++c) {
           uint32_t v[32];
-          tmem_ld32(tDQ + lane_off + c * 32, v);
+          if (c * 32 + 32 <= HD) {
+            tmem_ld32(tDQ + lane_off + c * 32, v);
+          } else {
+            tmem_ld16(tDQ + lane_off + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+#pragma unroll
+            for (int e = 16; e < 32; ++e) v[e] = 0u;
+          }
           tmem_wait_ld();
-          if (c == 1) {
+          if (c == kPieces - 1) {
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(dq_free);     // TMEM is read: the next dQ MMA may overwrite it
@@ -503,7 +552,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (i * 128 + qd * 32 < p.Lq)              // rows past Lq inside the box are clipped by the TMA unit
+            if (i * 128 + qd * 32 < p.Lq)              // rows past Lq (and columns past head_dim) are clipped by the TMA unit
               tma_reduce_add_4d(&tmDQ, slab, c * 32, i * 128 + qd * 32, h, b);
             tma_store_commit();
           }

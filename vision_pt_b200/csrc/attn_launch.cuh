@@ -57,14 +57,16 @@ inline int launch_attn_fwd(const AttnTensor& q, const AttnTensor& k, const AttnT
 }
 
 // dq_f32 must be zero on entry (fp32, same (b, l, h) element strides as given); delta is a [B,H,Lq] fp32 workspace.
-inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o,
-                           const AttnTensor& d_o, const AttnTensor& dq_f32, const AttnTensor& dk, const AttnTensor& dv,
-                           int B, int H, int Lq, int Lk, const int* seqlens_k, float scale, const float* lse2,
-                           float* delta, cudaStream_t stream) {
+template <int HD>
+inline int launch_attn_bwd_t(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o,
+                             const AttnTensor& d_o, const AttnTensor& dq_f32, const AttnTensor& dk, const AttnTensor& dv,
+                             int B, int H, int Lq, int Lk, const int* seqlens_k, float scale, const float* lse2,
+                             float* delta, cudaStream_t stream) {
+  using Smem = AttnBwd2SmemT<HD>;
   CUtensorMap tq, tk, tv, tdo;
-  // Q / dO travel as 64-query sub-tiles (one ring of two slots per sub-tile kind), K / V as 128-key tiles
-  if (make_attn_tmap(&tq, q, B, H, Lq, 64) || make_attn_tmap(&tk, k, B, H, Lk) || make_attn_tmap(&tv, v, B, H, Lk) ||
-      make_attn_tmap(&tdo, d_o, B, H, Lq, 64))
+  // Q / dO travel as 64-query sub-tiles (a ring of sub-tile slots), K / V as 128-key tiles
+  if (make_attn_tmap(&tq, q, B, H, Lq, 64, HD) || make_attn_tmap(&tk, k, B, H, Lk, kAttnTile, HD) ||
+      make_attn_tmap(&tv, v, B, H, Lk, kAttnTile, HD) || make_attn_tmap(&tdo, d_o, B, H, Lq, 64, HD))
     return 1;
   AttnDeltaParams dp{};
   dp.B = B; dp.H = H; dp.Lq = Lq;
@@ -76,11 +78,15 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   dp.Lq_pad = (Lq + kAttnTile - 1) / kAttnTile * kAttnTile;
   dp.scale = scale;
   const long groups = static_cast<long>(B) * H * dp.Lq_pad;
-  VPT_CUDA_OK(launch_pdl(attn_bwd_delta_kernel, dim3(static_cast<unsigned>((groups * 8 + 255) / 256)), dim3(256), 0, stream, dp));
+  if (HD == 64) {
+    VPT_CUDA_OK(launch_pdl(attn_bwd_delta_kernel, dim3(static_cast<unsigned>((groups * 8 + 255) / 256)), dim3(256), 0, stream, dp));
+  } else {
+    VPT_CUDA_OK(launch_pdl(attn_bwd_delta_row_kernel<HD>, dim3(static_cast<unsigned>((groups + 255) / 256)), dim3(256), 0, stream, dp));
+  }
 
   CUtensorMap tdq;
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(kAttnHD), static_cast<uint64_t>(Lq), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    const uint64_t dims[4] = {static_cast<uint64_t>(HD), static_cast<uint64_t>(Lq), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
     const uint64_t strides[3] = {static_cast<uint64_t>(dq_f32.sl) * 4, static_cast<uint64_t>(dq_f32.sh) * 4, static_cast<uint64_t>(dq_f32.sb) * 4};
     const uint32_t box[4] = {32, 32, 1, 1};
     if (make_tmap_f32_4d(&tdq, dq_f32.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
@@ -95,18 +101,26 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   p.dq = static_cast<float*>(const_cast<void*>(dq_f32.ptr));
   p.dq_sb = dq_f32.sb; p.dq_sl = dq_f32.sl; p.dq_sh = dq_f32.sh;
   CUtensorMap tdk, tdv;
-  if (make_attn_tmap(&tdk, dk, B, H, Lk, 32) || make_attn_tmap(&tdv, dv, B, H, Lk, 32)) return 1;
+  if (make_attn_tmap(&tdk, dk, B, H, Lk, 32, HD) || make_attn_tmap(&tdv, dv, B, H, Lk, 32, HD)) return 1;
   p.nk = (Lk + kAttnTile - 1) / kAttnTile;
   p.nq = (Lq + kAttnTile - 1) / kAttnTile;
   p.num_items = B * H * p.nk;
   static bool attr = false;
   if (!attr) {
-    VPT_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwd2Smem::kTotal));
+    VPT_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal));
     attr = true;
   }
   const int ctas = p.num_items < sm_count() ? p.num_items : sm_count();
-  VPT_CUDA_OK(launch_pdl(attn_bwd2_kernel, dim3(ctas), dim3(512), AttnBwd2Smem::kTotal, stream, tq, tk, tv, tdo, tdq, tdk, tdv, p));
+  VPT_CUDA_OK(launch_pdl(attn_bwd2_kernel<HD>, dim3(ctas), dim3(512), Smem::kTotal, stream, tq, tk, tv, tdo, tdq, tdk, tdv, p));
   return 0;
+}
+inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o,
+                           const AttnTensor& d_o, const AttnTensor& dq_f32, const AttnTensor& dk, const AttnTensor& dv,
+                           int B, int H, int Lq, int Lk, const int* seqlens_k, float scale, const float* lse2,
+                           float* delta, cudaStream_t stream, int head_dim = 64) {
+  if (head_dim == 80)
+    return launch_attn_bwd_t<80>(q, k, v, o, d_o, dq_f32, dk, dv, B, H, Lq, Lk, seqlens_k, scale, lse2, delta, stream);
+  return launch_attn_bwd_t<64>(q, k, v, o, d_o, dq_f32, dk, dv, B, H, Lq, Lk, seqlens_k, scale, lse2, delta, stream);
 }
 
 // ---- head_dim != 64: CUDA-core kernels (attention_simple.cuh)
