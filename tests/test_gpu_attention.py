@@ -60,10 +60,13 @@ def test_reference_sdpa_vector(golden):
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk,lens,hd", [(2, 3, 300, 300, [300, 251], 80), (1, 2, 1100, 1100, [1093], 80),
-                                              (2, 2, 200, 77, [77, 40], 80), (1, 2, 130, 130, None, 128), (1, 1, 64, 40, None, 32)])
+                                              (2, 2, 200, 77, [77, 40], 80), (1, 2, 130, 130, None, 128), (1, 1, 64, 40, None, 32),
+                                              # head_dim 80 runs the tcgen05 kernels on two-block tiles: the same edges as head_dim 64
+                                              (1, 1, 40, 24, None, 80), (2, 2, 17, 330, [330, 1], 80), (3, 1, 129, 129, [129, 65, 16], 80),
+                                              (1, 3, 64, 640, [577], 80), (16, 16, 1098, 1098, None, 80)])
 def test_attention_other_head_dims(B, H, Lq, Lk, lens, hd):
-    """head_dim != 64 (JiT-H: 80, BASELINE.json configs[3]) runs the CUDA-core kernels of attention_simple.cuh: same
-    contract and the same tolerance as the tcgen05 path."""
+    """head_dim 80 (JiT-H, BASELINE.json configs[3]; the last row is its full size) runs the tcgen05 kernels templated on
+    head_dim; 32 / 128 run the CUDA-core kernels of attention_simple.cuh: same contract and tolerance everywhere."""
     from vision_pt_b200 import ops
     torch.manual_seed(B * 100 + Lq + hd)
     mk = lambda L: torch.randn(B, H, L, hd).to(torch.bfloat16)
@@ -73,9 +76,11 @@ def test_attention_other_head_dims(B, H, Lq, Lk, lens, hd):
     qg, kg, vg = dev(q), dev(k), dev(v)
     o = ops.attention(qg, kg, vg, None if seq is None else seq.cuda())
     o.backward(d_o.cuda())
-    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
-    orf = oj.attention_explicit(qr, kr, vr, None if seq is None else seq.long())
-    orf.backward(d_o.float())
+    big = B * H * Lq * Lk > 1 << 24               # the full-size row: evaluate the oracle on the GPU
+    put = (lambda t: t.cuda()) if big else (lambda t: t)
+    qr, kr, vr = (put(t).float().requires_grad_(True) for t in (q, k, v))
+    orf = oj.attention_explicit(qr, kr, vr, None if seq is None else put(seq).long())
+    orf.backward(put(d_o).float())
     assert rel_err(o, orf) <= 2e-2
     assert rel_err(qg.grad, qr.grad) <= 2e-2 and rel_err(kg.grad, kr.grad) <= 2e-2 and rel_err(vg.grad, vr.grad) <= 2e-2
     if seq is not None:

@@ -50,7 +50,7 @@ struct AttnFwdSmemT {
   static constexpr int kStream = 6 * kTile;
   static constexpr int kQ = 0, kK = 2 * kTile, kV = 4 * kTile;
   static constexpr int kOut = kStreams * kStream;   // 8 softmax warps x one slab of [32 rows x 128 B] (output tile -> TMA store)
-  static constexpr int kXchg = kOut + 8 * 4096;   // per stream: 2 block parities x 2 column halves x 128 rows, bf16 row maxima
+  static constexpr int kXchg = kOut + 8 * 4096;   // per stream: 2 column halves x 128 rows, fp32 row maxima (row sums at item end)
   static constexpr int kBars = kXchg + 2 * 1024;
   // per stream: q_full[2] q_empty[2] kv_full[2] kv_empty[2] s_full p_full (256 arrivals) pv_done  (11)
   static constexpr int kBarsPerStream = 11;
@@ -251,7 +251,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     uint8_t* out_slab = smem + S::kOut + (X * 4 + qd) * 4096;       // used by half 0 (the epilogue half)
     const uint32_t out_row = smem_u32(out_slab) + lane * 128;
-    __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem + S::kXchg + X * 1024);   // [parity][half][128]
+    float* xchg = reinterpret_cast<float*>(smem + S::kXchg + X * 1024);   // [half][128]
     if (lane == 0 && half == 0) tma_prefetch_desc(&tmO);
     uint32_t cx = 0, it = 0;
     PROF_DECL(8)
@@ -264,7 +264,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int nvalid = min(128, klen - j * 128);          // < 128 only in the last block
         const int nch = (nvalid + 31) >> 5;                   // 32-column chunks that hold keys
         const int c_begin = 2 * half, c_end = min(nch, 2 * half + 2);
-        __nv_bfloat16* xb = xchg + (cx & 1) * 256;
         PROF(0)
         mbar_wait(s_full, cx & 1);
         PROF(1)
@@ -291,12 +290,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           mx = fmaxf(mx, fmaxf(m0, m1));
         }
-        // the halves agree on ONE reference maximum: both take max(bf16(own), bf16(other)).  bf16 is enough -- the
-        // reference only has to be within 2^8 of the true maximum (lazy-rescale rule below), not equal to it.
-        const __nv_bfloat16 mine = __float2bfloat16_rn(mx * p.scale_log2);   // scale > 0: max commutes with the scaling
-        xb[half * 128 + row] = mine;
+        // the halves agree on ONE reference maximum through shared memory.  One buffer is enough: this half's next write to
+        // its slot comes after s_full of the next block, which the issuer commits only after p_full of this block, which
+        // the other half arrives on after it has read the slot.
+        mx *= p.scale_log2;                         // scale > 0: the maximum commutes with the scaling
+        xchg[half * 128 + row] = mx;
         named_bar_sync(1 + X, 256);
-        mx = fmaxf(__bfloat162float(mine), __bfloat162float(xb[(half ^ 1) * 128 + row]));
+        mx = fmaxf(mx, xchg[(half ^ 1) * 128 + row]);
         PROF(2)
         // lazy rescale: keep the reference maximum unless the true one outgrew it by 2^8
         const bool grow = mx > m_ref + 8.f;
@@ -367,12 +367,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       PROF(5)
       tc_fence_after_sync();
       if (nblk > 0) {
-        // the exchange buffer of the item's last block is free again: every read of it precedes that half's p_full arrival,
-        // and pv_done follows both
-        float* lx = reinterpret_cast<float*>(xchg + ((cx - 1) & 1) * 256);
-        if (half == 1) lx[row] = l_run;
+        // half 1 hands its row sum over in half 0's slot: half 1 read that slot before its own last pass 2, half 0 writes
+        // it again only after this read (program order), and half 1 reads it again only after the next block's barrier
+        if (half == 1) xchg[row] = l_run;
         named_bar_sync(1 + X, 256);
-        if (half == 0) l_run += lx[row];
+        if (half == 0) l_run += xchg[row];
       }
       if (half == 0) {
         const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
