@@ -127,3 +127,20 @@ def test_jit_config_and_model_structure():
     assert (b.hidden_size, b.depth, b.num_heads, b.context_start_block) == (768, 12, 12, 4)
     with pytest.raises(AssertionError):
         Denoiser(DenoiserConfig(hidden_size=128, num_heads=4, depth=1))   # rope dims must sum to head_dim
+
+
+def test_aspect_ratio_buckets_follow_the_reference_rule():
+    """tools/bench_arb.py restates generate_buckets (src/dataset/aspect_ratio_bucket.py:20-60): base 512 / step 64 / min 256
+    gives the 9 buckets BASELINE.json configs[3] trains on; the reference's defaults (1024 / 64 / 384) give 21."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bench_arb.py")
+    spec = importlib.util.spec_from_file_location("bench_arb", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.buckets(512, 64, 256)
+    assert sorted(got) == sorted([(512, 512), (448, 576), (576, 448), (384, 704), (704, 384), (320, 832), (832, 320),
+                                  (256, 1024), (1024, 256)])
+    big = mod.buckets(1024, 64, 384)
+    assert (1024, 1024) in big and (384, 2752) in big and (2752, 384) in big and all(h % 64 == 0 and w % 64 == 0 for h, w in big)
+    assert len(big) == len(set(big)) == 21

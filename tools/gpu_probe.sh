@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_attention.py tests/test_gpu_block.py -x -q 2>&1 | tail -3
-timeout 200 python tools/bench_attn.py 2>&1 | tail -2 | head -1
+timeout 900 python tools/bench_arb.py --steps 36 2>&1 | tail -1 > gpurun_out/r1q_arb.json; cat gpurun_out/r1q_arb.json | cut -c1-1500
