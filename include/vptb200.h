@@ -88,7 +88,7 @@ typedef struct {
    * CTA re-dequantising its weight tile per 128-row block of x.  This is the large-M (training) path; NULL selects
    * the per-stage prologue dequantiser (small M). */
   void* w_scratch;
-  int64_t ld_scratch;          /* unused since ABI 2 (kept for layout compatibility) */
+  int64_t ld_scratch;          /* ABI 4: row pitch of w_bf16 in elements (0 = in_features); must be a multiple of 8 */
   int64_t scratch_bytes;       /* capacity of w_scratch */
   int64_t ld_side;             /* row pitch of `side` in elements */
   int32_t reuse_scratch;       /* non-zero: w_scratch already holds this weight in this direction's layout (the previous

@@ -194,3 +194,25 @@ def test_full_size_jit_b_linear(K, N):
         y0 = layer(x.cuda())
         yb = layer.linear(x.cuda())
         assert torch.equal(y0, yb)
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 3413, 1280), (17568, 3413, 1280), (21120, 2730, 1024), (130, 341, 128)])
+def test_frozen_bf16_linear_with_ragged_in_features(M, K, N):
+    """The final layer's SwiGLU w_3 of JiT-H / JiT-L (frozen bf16, in_features 3413 / 2730: not a multiple of 8) runs the
+    tcgen05 kernels through a row-padded view of the weight (ops.padded_weight) in both directions, small and large M."""
+    from vision_pt_b200 import ops
+    from vision_pt_b200.jit.denoiser import _kernel_linear
+    torch.manual_seed(K)
+    w = (torch.randn(N, K) * 0.03).to(torch.bfloat16).cuda()
+    b = (torch.randn(N) * 0.2).to(torch.bfloat16).cuda()
+    x = torch.randn(M, K).to(torch.bfloat16).cuda().requires_grad_(True)
+    y = _kernel_linear(x, w, b)
+    assert y is not None and y.shape == (M, N)
+    dy = torch.randn(M, N).to(torch.bfloat16).cuda()
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = xr @ w.float().t() + b.float()
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= TOL and rel_err(x.grad, xr.grad) <= TOL
+    pw = ops.padded_weight(w)
+    assert pw.shape == (N, K) and pw.stride(0) % 8 == 0 and torch.equal(pw, w) and ops.padded_weight(w) is pw   # cached

@@ -123,10 +123,14 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
   VPT_REQUIRE(a->ld_in % 8 == 0 && a->ld_out % 8 == 0, "vpt_nf4lora_linear: leading dimensions must be multiples of 8");
   VPT_REQUIRE(a->side == nullptr || (a->ld_side >= a->M && a->ld_side % 8 == 0), "vpt_nf4lora_linear: side needs ld_side >= M, a multiple of 8");
   const bool via_scratch = a->w_bf16 == nullptr && a->w_scratch != nullptr;
+  // row pitch of a bf16 weight (ld_scratch doubles as that since ABI 4): a ragged in_features (3413, 2730) is served
+  // from a copy whose rows are padded to a multiple of 8 elements -- TMA zero-fills past K
+  const long ld_wb = (a->w_bf16 != nullptr && a->ld_scratch > 0) ? a->ld_scratch : K;
+  if (a->w_bf16 != nullptr) VPT_REQUIRE(ld_wb >= K && ld_wb % 8 == 0, "vpt_nf4lora_linear: a bf16 weight needs a row pitch (ld_scratch, 0 = in_features) that is a multiple of 8");
   const bool lora = a->lora_down != nullptr;
   if (lora) VPT_REQUIRE(a->lora_up != nullptr && a->ld_lora_down % 8 == 0 && a->ld_lora_down >= K, "vpt_nf4lora_linear: bad LoRA arguments");
   static const bool use_pairs = getenv("VPT_NO_PAIR") == nullptr;   // A/B switch for profiling the 1-CTA kernel
-  if (use_pairs && (via_scratch || (a->w_bf16 != nullptr && !bwd && K % 8 == 0))) {
+  if (use_pairs && (via_scratch || (a->w_bf16 != nullptr && !bwd))) {
     // Large-M route: CTA-pair kernel over a K-major bf16 weight.  An NF4 weight is dequantised once per call into the
     // caller's L2-resident workspace -- as [N, K] for the forward, TRANSPOSED [K, N] (plus the two transposed LoRA
     // matrices) for the backward, so that both directions run the same kernel.
@@ -170,14 +174,14 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
       }
       VPT_CUDA_OK(cudaGetLastError());
     } else {
-      g.w = a->w_bf16; g.ldw = K;
+      g.w = a->w_bf16; g.ldw = ld_wb;
       g.p_rows = a->lora_down; g.ldp = a->ld_lora_down;
       g.p.q_rows = static_cast<const __nv_bfloat16*>(a->lora_up);
     }
     return launch_pair(g, stream);
   }
   const void* w_dense = a->w_bf16;
-  long ldw = 0;
+  long ldw = a->w_bf16 != nullptr ? ld_wb : 0;
   if (via_scratch) {
     const long n = static_cast<long>(N) * K;
     ldw = (K + 7) / 8 * 8;
@@ -197,8 +201,6 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
       VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax, "vpt_nf4lora_linear: NF4 tensors missing");
       VPT_REQUIRE(K % 64 == 0, "vpt_nf4lora_linear: in_features must be a multiple of 64 (repack ragged weights with vpt_nf4_repack)");
     }
-  } else {
-    VPT_REQUIRE(K % 8 == 0, "vpt_nf4lora_linear: a bf16 weight needs in_features % 8 == 0");
   }
   GemmLaunch g{};
   g.bwd = bwd; g.nf4 = nf4; g.lora = lora; g.bn = a->tile_n;

@@ -34,6 +34,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn encode_tiled_fn() {
+  // cuTensorMapEncodeTiled is a driver call and wants a current context: on a thread whose first CUDA call this is
+  // (autograd's backward thread running one of these ops first) the runtime has not bound the primary context yet and
+  // the encode fails with CUDA_ERROR_INVALID_CONTEXT -- bind it once per thread.
+  static thread_local bool bound = (cudaFree(nullptr), true);
+  (void)bound;
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;

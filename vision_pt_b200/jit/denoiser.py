@@ -41,8 +41,10 @@ def _kernel_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | N
     """x W^T + b through the tcgen05 kernel for a FROZEN bf16 weight (patch embed, final layer, context embedder);
     None when the layer does not qualify (trainable, other dtype, CPU) and the caller falls back to torch."""
     if (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and not weight.requires_grad
-            and weight.shape[-1] % 8 == 0 and (bias is None or not bias.requires_grad)):
-        return ops.nf4_lora_linear(x, weight, bias)
+            and (bias is None or not bias.requires_grad)):
+        # a ragged in_features (the final layer's 3413- / 2730-wide SwiGLU) goes through a row-padded copy of the weight:
+        # torch's matmul falls to an unaligned legacy kernel there (1.2 ms per call at JiT-H sizes)
+        return ops.nf4_lora_linear(x, ops.padded_weight(weight), bias)
     return None
 
 

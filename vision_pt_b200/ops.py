@@ -102,6 +102,26 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     return buf[:, :d]
 
 
+_PADDED_WEIGHTS: dict = {}
+
+
+def padded_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] view of a frozen bf16 weight whose rows start on 16-byte boundaries (pitch = K rounded up to 8): what the
+    tensor-map needs when in_features is ragged (3413 = JiT-H's SwiGLU width, 2730 = JiT-L's).  The padded copy is made
+    once per weight (keyed by storage and version) and zero-filled past K."""
+    N, K = w.shape
+    if K % 8 == 0 and w.is_contiguous() and w.data_ptr() % 16 == 0:
+        return w
+    key = (w.data_ptr(), w._version, N, K, w.device)
+    hit = _PADDED_WEIGHTS.get(key)
+    if hit is None:
+        buf = torch.zeros((N, (K + 7) // 8 * 8), dtype=w.dtype, device=w.device)
+        buf[:, :K] = w.detach()
+        hit = buf[:, :K]
+        _PADDED_WEIGHTS[key] = hit
+    return hit
+
+
 # ------------------------------------------------------------------------------------------------------- NF4
 @dataclass
 class Nf4Tensors:
@@ -228,8 +248,12 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
             args.reuse_scratch = int(reuse_scratch)
     else:
         N, K = w.shape
+        if w.stride(1) != 1 or w.stride(0) % 8 != 0 or w.stride(0) < K or w.data_ptr() % 16 != 0:
+            raise ValueError("bf16 weight: unit inner stride and a row pitch that is a multiple of 8 elements "
+                             "(ops.padded_weight makes such a view of a ragged [N, K] weight)")
         args.w = Nf4WeightC(None, None, None, None, None, 0.0, int(N), int(K), None, None, 0)
         args.w_bf16 = _p(w)
+        args.ld_scratch = w.stride(0)                # row pitch of the bf16 weight (ABI 4)
     n_out = K if backward else N
     ld_out = (n_out + 7) // 8 * 8
     out_full = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x2.device)
