@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_linear.py -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2

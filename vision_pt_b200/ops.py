@@ -102,24 +102,21 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     return buf[:, :d]
 
 
-_PADDED_WEIGHTS: dict = {}
-
-
 def padded_weight(w: torch.Tensor) -> torch.Tensor:
     """[N, K] view of a frozen bf16 weight whose rows start on 16-byte boundaries (pitch = K rounded up to 8): what the
     tensor-map needs when in_features is ragged (3413 = JiT-H's SwiGLU width, 2730 = JiT-L's).  The padded copy is made
-    once per weight (keyed by storage and version) and zero-filled past K."""
+    once and kept ON the weight object (so it lives and dies with it -- a cache keyed by address would hand a freed
+    weight's copy to whatever is allocated there next) and is rebuilt if the weight is modified in place."""
     N, K = w.shape
     if K % 8 == 0 and w.is_contiguous() and w.data_ptr() % 16 == 0:
         return w
-    key = (w.data_ptr(), w._version, N, K, w.device)
-    hit = _PADDED_WEIGHTS.get(key)
-    if hit is None:
+    hit = getattr(w, "_vpt_padded", None)
+    if hit is None or hit[0] != w._version or hit[1].device != w.device or hit[2] != w.data_ptr():
         buf = torch.zeros((N, (K + 7) // 8 * 8), dtype=w.dtype, device=w.device)
         buf[:, :K] = w.detach()
-        hit = buf[:, :K]
-        _PADDED_WEIGHTS[key] = hit
-    return hit
+        hit = (w._version, buf[:, :K], w.data_ptr())
+        w._vpt_padded = hit
+    return hit[1]
 
 
 # ------------------------------------------------------------------------------------------------------- NF4
