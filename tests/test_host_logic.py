@@ -144,3 +144,20 @@ def test_aspect_ratio_buckets_follow_the_reference_rule():
     big = mod.buckets(1024, 64, 384)
     assert (1024, 1024) in big and (384, 2752) in big and (2752, 384) in big and all(h % 64 == 0 and w % 64 == 0 for h, w in big)
     assert len(big) == len(set(big)) == 21
+
+
+def test_padded_weight_copy_lives_on_the_weight_object():
+    """ops.padded_weight: a ragged [N, K] weight gets a row-padded copy that is cached ON the tensor (a cache keyed by
+    address once handed a freed weight's copy to the next tensor allocated there) and is rebuilt after in-place updates."""
+    import torch
+
+    from vision_pt_b200 import ops
+    a = torch.randn(8, 13).to(torch.bfloat16)
+    pa = ops.padded_weight(a)
+    assert pa.shape == (8, 13) and pa.stride(0) == 16 and torch.equal(pa, a) and ops.padded_weight(a) is pa
+    b = torch.randn(8, 13).to(torch.bfloat16)
+    assert torch.equal(ops.padded_weight(b), b) and not torch.equal(ops.padded_weight(b), pa)
+    a.mul_(2)
+    assert torch.equal(ops.padded_weight(a), a)                    # stale copy replaced after the in-place change
+    c = torch.randn(8, 16).to(torch.bfloat16)
+    assert ops.padded_weight(c) is c                               # already aligned: no copy
