@@ -1,3 +1,4 @@
-timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/r1r_bench_n2.json; python -c "
-import json; d=json.load(open('gpurun_out/r1r_bench_n2.json')); print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['e2e']['value'], d['extra_workload']['value'] if d.get('extra_workload') else None)"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29545 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-200
+timeout 300 python tools/profile_step.py --model JiT-H/16 --res 512 --batch 16 > gpurun_out/r1s_plain.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"attn_fwd_kernel|attn_bwd2_kernel" -s 4 -c 1 -o gpurun_out/r1s_attn80_fwd python tools/profile_step.py --model JiT-H/16 --res 512 --batch 16 > gpurun_out/r1s_ncu1.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"attn_bwd2_kernel" -s 2 -c 1 -o gpurun_out/r1s_attn80_bwd python tools/profile_step.py --model JiT-H/16 --res 512 --batch 16 > gpurun_out/r1s_ncu2.log 2>&1
+ls -la gpurun_out/r1s*
