@@ -45,10 +45,15 @@ template <int HD>
 struct AttnFwdSmemT {
   static constexpr int kBlk = (HD + 63) / 64;          // 64-column (128-byte, swizzled) blocks per row: 80 -> 2, the second
   static constexpr int kTile = kBlk * 16384;           // zero-filled past the head dimension by the TMA unit
-  static constexpr int kStreams = HD == 64 ? 2 : 1;    // 6 tiles per stream: two streams only fit at head_dim 64
-  // per stream (X = 0, 1): Q[2] (item double buffer), K[2], V[2] (key-block stages)
-  static constexpr int kStream = 6 * kTile;
-  static constexpr int kQ = 0, kK = 2 * kTile, kV = 4 * kTile;
+  static constexpr int kStreams = 2;
+  // per stream (X = 0, 1): Q[kQBufs] (items), K[kKVStages], V[kKVStages] (key blocks).  head_dim 64: all double-buffered
+  // (6 x 16 KB); head_dim 80: single-buffered (3 x 32 KB) -- a stream then waits ~1.5 us for every tile it loads, and the
+  // other stream fills that time
+  static constexpr int kQBufs = HD == 64 ? 2 : 1;
+  static constexpr int kKVStages = HD == 64 ? 2 : 1;
+  static constexpr bool kPInPlace = HD != 64;          // TMEM: 2 x (128 + 80 + 64) > 512, so P goes over the S columns it came from
+  static constexpr int kStream = (kQBufs + 2 * kKVStages) * kTile;
+  static constexpr int kQ = 0, kK = kQBufs * kTile, kV = (kQBufs + kKVStages) * kTile;
   static constexpr int kOut = kStreams * kStream;   // 8 softmax warps x one slab of [32 rows x 128 B] (output tile -> TMA store)
   static constexpr int kXchg = kOut + 8 * 4096;   // per stream: 2 column halves x 128 rows, fp32 row maxima (row sums at item end)
   static constexpr int kBars = kXchg + 2 * 1024;
@@ -81,9 +86,9 @@ using AttnFwdSmem = AttnFwdSmemT<64>;
 // tcgen05.ld -> ex2 -> tcgen05.st chains were latency-bound (MUFU 30 % busy, profiles/r1o_attn_fwd_ncu.txt).
 // Warps: 0 / 2 TMA producers of stream A / B (2 also allocates TMEM), 1 / 3 MMA issuers, 4-11 softmax A, 12-19 softmax B.
 // head_dim 80 (JiT-H): the same kernel on two-block tiles -- QK^T runs a fifth k-step over the second block, O += P V uses
-// N = 80 across both blocks (MN-major operand, leading-block stride = one 16 KB block) -- with ONE stream per CTA (six
-// 32 KB tiles fill the shared memory; the second stream's warps retire at once) and the output written straight from
-// registers.
+// N = 80 across both blocks (MN-major operand, leading-block stride = one 16 KB block) -- with single-buffered Q / K / V
+// (three 32 KB tiles per stream), each half's P written over its own S columns (64 half .. 64 half + 31), and the output
+// written straight from registers.
 template <int HD>
 __global__ void __launch_bounds__(640, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -110,7 +115,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nqt = (p.Lq + kAttnTile - 1) / kAttnTile;
   const int num_items = nqt * p.H * p.B;
   const int first_item = blockIdx.x * S::kStreams + X, item_stride = gridDim.x * S::kStreams;
-  const bool idle = X >= S::kStreams;             // head_dim 80: no second stream
+  const bool idle = X >= S::kStreams;
   auto klen_of = [&](int item) {
     if (item >= num_items) return 0;
     if (p.seqlens_k == nullptr) return p.Lk;
@@ -134,7 +139,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   // per stream: S 0..127, O 128..128+HD-1, P (64 columns of bf16 pairs) behind it; stream 1 starts at column 256
-  const uint32_t tS = tmem_base + X * 256, tO = tS + 128, tP = tO + (HD == 64 ? 64 : 80);
+  const uint32_t tS = tmem_base + X * 256, tO = tS + 128, tP = tO + 64;    // tP: head_dim 64 only
   pdl_launch_dependents();
   pdl_wait();
 
@@ -150,15 +155,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int item = first_item; item < num_items; item += item_stride, ++it) {
         const int qt = item % nqt, h = (item / nqt) % p.H, b = item / (nqt * p.H);
         const int nblk = (klen_of(item) + kAttnTile - 1) / kAttnTile;
-        const uint32_t qb = it & 1;
-        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        const uint32_t qb = it % S::kQBufs;
+        mbar_wait(&q_empty[qb], ((it / S::kQBufs) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], kTile);
 #pragma unroll
         for (int blk = 0; blk < S::kBlk; ++blk)
           tma_load_4d(&tmQ, &q_full[qb], sm + S::kQ + qb * kTile + blk * 16384, blk * 64, qt * kAttnTile, h, b);
         for (int j = 0; j < nblk; ++j, ++jj) {
-          const uint32_t s = jj & 1;
-          mbar_wait(&kv_empty[s], ((jj >> 1) & 1) ^ 1);
+          const uint32_t s = jj % S::kKVStages;
+          mbar_wait(&kv_empty[s], ((jj / S::kKVStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * kTile);
 #pragma unroll
           for (int blk = 0; blk < S::kBlk; ++blk) {
@@ -176,19 +181,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t dK_ = umma_smem_desc(0, 16, 1024, kLayoutSW128);
     const uint64_t dMN = umma_smem_desc(0, 16384, 1024, kLayoutSW128);   // MN-major: 64-column blocks 16 KB apart
     uint32_t it = 0, jj = 0, pc = 0;
+    // TMEM columns of the 16 keys of k-step k of P: its own 64 columns, or (in place) the first 32 columns of the S half
+    // the keys belong to
+    auto p_cols = [&](int k) { return S::kPInPlace ? tS + (k >> 2) * 64 + (k & 3) * 8 : tP + k * 8; };
     PROF_DECL(8)
     for (int item = first_item; item < num_items; item += item_stride, ++it) {
       const int kl = klen_of(item);
       const int nblk = (kl + kAttnTile - 1) / kAttnTile;
-      const uint32_t qb = it & 1;
+      const uint32_t qb = it % S::kQBufs;
       const uint64_t qd = dK_ + ((sbase + S::kQ + qb * kTile) >> 4);
       // S = Q K_j^T (the softmax halves have read the previous S: p_full)
       auto issue_s = [&](int j, uint32_t jn) {
-        const uint32_t s = jn & 1;
+        const uint32_t s = jn % S::kKVStages;
         const int valid = min(128, kl - j * 128);
         const int n = (valid + 15) & ~15;
         PROF(0)
-        mbar_wait(&kv_full[s], (jn >> 1) & 1);
+        mbar_wait(&kv_full[s], (jn / S::kKVStages) & 1);
         PROF(1)
         tc_fence_after_sync();
         const uint64_t kd = dK_ + ((sbase + S::kK + s * kTile) >> 4);
@@ -205,11 +213,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         PROF(2)
       };
       PROF(0)
-      mbar_wait(&q_full[qb], (it >> 1) & 1);
+      mbar_wait(&q_full[qb], (it / S::kQBufs) & 1);
       PROF(3)
       if (nblk > 0) issue_s(0, jj);
       for (int j = 0; j < nblk; ++j, ++jj) {
-        const uint32_t s = jj & 1;
+        const uint32_t s = jj % S::kKVStages;
         const uint64_t vd = dMN + ((sbase + S::kV + s * kTile) >> 4);
         const int valid = min(128, kl - j * 128);
         const int n = (valid + 15) & ~15;
@@ -221,9 +229,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (elect_one_sync()) {
           if (n == 128) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_ts(tO, tP + k * 8, vd + k * 128, kIdO, (j | k) != 0);
+            for (int k = 0; k < 8; ++k) umma_ts(tO, p_cols(k), vd + k * 128, kIdO, (j | k) != 0);
           } else {
-            for (int k = 0; k < n / 16; ++k) umma_ts(tO, tP + k * 8, vd + k * 128, kIdO, (j | k) != 0);
+            for (int k = 0; k < n / 16; ++k) umma_ts(tO, p_cols(k), vd + k * 128, kIdO, (j | k) != 0);
           }
           umma_commit(&kv_empty[s]);
         }
@@ -353,7 +361,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ps1 += p1;
             pk[e] = pack_bf16x2(p0, p1);
           }
-          tmem_st16(tP + lane_off + c * 16, pk);
+          // in place: this half's chunk c' = c - 2 half lands in columns 64 half + 16 c' .. + 15, inside S columns the
+          // half has already read (chunk 0: its own first 32; chunk 1: still chunk 0's range)
+          tmem_st16((S::kPInPlace ? tS + 64 * half + (c - 2 * half) * 16 : tP + c * 16) + lane_off, pk);
         }
         l_run += ps0 + ps1;
         tmem_wait_st();

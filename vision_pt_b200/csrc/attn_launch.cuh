@@ -44,7 +44,7 @@ inline int launch_attn_fwd_t(const AttnTensor& q, const AttnTensor& k, const Att
     attr = true;
   }
   const int items = ((Lq + kAttnTile - 1) / kAttnTile) * H * B;
-  const int ctas = (items + Smem::kStreams - 1) / Smem::kStreams;   // one item stream per CTA at head_dim 80, two at 64
+  const int ctas = (items + Smem::kStreams - 1) / Smem::kStreams;   // two item streams per CTA
   const int slots = sm_count();
   VPT_CUDA_OK(launch_pdl(attn_fwd_kernel<HD>, dim3(ctas < slots ? ctas : slots), dim3(640), Smem::kTotal, stream, tq, tk, tv, to, p));
   return 0;
