@@ -4,14 +4,16 @@
   python bench.py --gpus 1 --steps 20 --warmup 5                       # our arm, one GPU
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
       bench.py --gpus N ...                                             # data parallel, one rank per GPU
-  python bench.py --impl reference ...                                  # the reference's CPU path (oracle port)
+  python bench.py --impl reference ...                                  # the reference's own modules on the host CPU
 
 One JSON line on stdout (rank 0).  A "step" is one optimisation step of the named workload: noise + forward + loss +
 backward + LoRA-gradient all-reduce (N > 1) + clip + AdamW, on synthetic images of the named shape with random-init
 weights.  `value` times K CUDA-graph replays with the batch already in HBM; `e2e` times the same K steps through the
 public API with the batch in pinned host memory (H2D copy of the batch and D2H read of the loss inside the timed
-region).  `roofline` is the fused NF4-LoRA GEMM (forward + backward-dX launches of the block linears) timed with CUDA
-events inside real steps.  `cpu_baseline` is the oracle's CPU restatement of the same step on a bounded sample.
+region; the next batch's copy overlaps the running step).  `roofline` is the fused NF4-LoRA GEMM (forward + backward-dX
+launches of the block linears, dequantisation launches included) replayed for >= 2 s.  `cpu_baseline` is the reference's
+own Denoiser on the host cores on a bounded sample; `reference_gpu` is the same reference code in eager bf16 on this GPU
+(NF4 base linear restated: bitsandbytes is absent), both baselines that are measured, never paths the product takes.
 """
 from __future__ import annotations
 
@@ -36,7 +38,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="JiT-B/16", help="JiT-B/16 | JiT-L/16 (the headline workload is JiT-B/16 at every N so that N = 1, 2, 4, 8 measure the same per-GPU work)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary JiT-L/16 data-parallel measurement at N > 1")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary JiT-L/16 measurement")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--rank", type=int, default=16)
@@ -45,7 +47,8 @@ def parse_args():
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "radam_schedulefree"],
                     help="update rule of the timed step (the shipped YAMLs name schedulefree.RAdamScheduleFree)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the restated reference GPU path leg (N = 1)")
+    ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=2)
     return ap.parse_args()
 
@@ -118,7 +121,20 @@ def physical_gpu_index(local: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-def gemm_roofline(step, ops, torch, replay_here: bool = True):
+def _file_hash(path: str) -> str:
+    import hashlib
+    try:
+        return hashlib.sha1(open(path, "rb").read()).hexdigest()[:12]
+    except OSError:
+        return "missing"
+
+
+def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float = 2.0):
+    """Roofline of the dominant kernel (the CTA-pair NF4-LoRA GEMM).  The fused-linear calls AND the batched NF4
+    dequantisation launches of one real step are taped, then replayed back to back in the step's order from a CUDA graph on
+    buffers of the same shapes (inputs rotate over > L2 worth of memory) for >= `min_seconds`, timed with CUDA events on the
+    launching stream; the MEAN replay time is used.  `achieved` counts the GEMM FLOPs over the time of GEMMs + dequantisation
+    launches (the dequantisation is the price of NF4 and carries 0 FLOP); `gemm_only` is the same replay without them."""
     ops.GEMM_TIMER = []
     was = step.use_graph
     step.use_graph = False
@@ -126,8 +142,16 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True):
     torch.cuda.synchronize()
     step.use_graph = was
     recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
-    tape = [r for r in recs if r["nf4"] and r["lora"] and r["scratch"]]
-    if not tape or not replay_here:
+    tape, last_dq = [], None
+    for r in recs:
+        if r["kind"] == "dequant":
+            last_dq = r
+            tape.append(r)
+        elif r["nf4"] and r["lora"] and r["scratch"] and last_dq is not None and r["scratch_ptr"] in last_dq["slot_ptrs"]:
+            r["slot"] = last_dq["slot_ptrs"].index(r["scratch_ptr"])
+            tape.append(r)
+    gemms = [r for r in tape if r["kind"] == "gemm"]
+    if not gemms or not replay_here:
         return None
     dev = torch.device("cuda", torch.cuda.current_device())
     pool: dict = {}
@@ -141,94 +165,217 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True):
             lst.append(t)
         return lst[salt % len(lst)]
 
-    def replay(reuse: bool):
-        outs = []
+    def replay(with_dequant: bool):
+        outs, slots = [], None
         for i, r in enumerate(tape):
+            if r["kind"] == "dequant":
+                # without the dequantisation launches the slots were filled once, outside the timed graph
+                slots = ops.dequant_block(r["weights"], r["downs"], r["ups"], r["transposed"]) if with_dequant else filled[id(r)]
+                continue
             shape, stride, w, bias, down, up, scale, has_res, want_side, backward = r["call"]
             n_out = w.shape[1] if backward else w.shape[0]
             res = buf((shape[0], n_out), (n_out + 7) // 8 * 8, i + 1) if has_res else None
             outs.append(ops.linear_raw(buf(shape, stride, i), w, bias, down, up, scale, res, want_side=want_side,
-                                       backward=backward, reuse_scratch=reuse))
+                                       backward=backward, scratch=slots[r["slot"]]))
         return outs
 
-    def timed(reuse: bool) -> float:
+    # GEMM-only variant: every (block, direction) gets its own pre-filled set of slots (the step's arena is reused per block)
+    filled: dict = {}
+    for r in tape:
+        if r["kind"] == "dequant":
+            slots = ops.dequant_block(r["weights"], r["downs"], r["ups"], r["transposed"])
+            filled[id(r)] = [sl.clone() for sl in slots]
+    torch.cuda.synchronize()
+
+    def timed(with_dequant: bool) -> tuple[float, int]:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
-            replay(reuse)
+            replay(with_dequant)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            keep = replay(reuse)
+            keep = replay(with_dequant)
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        best = 1e30
-        for _ in range(3):
-            e0.record()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        one = max(e0.elapsed_time(e1), 1e-3)
+        n = max(3, int(min_seconds * 1e3 / one) + 1)
+        e0.record()
+        for _ in range(n):
             g.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
         del keep, g
-        return best
+        return ms, n
 
-    ms_gemm = timed(True)
-    ms_call = timed(False)
-    fl = sum(r["flops"] for r in tape)
+    ms_all, n_all = timed(True)
+    ms_gemm, n_gemm = timed(False)
+    fl = sum(r["flops"] for r in gemms)
+    n_dq = sum(1 for r in tape if r["kind"] == "dequant")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained")
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long back-to-back sequence)"
+    peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a >= 2 s back-to-back "
+                "sequence, as that peak was)")
     if not peak:
         peak, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-    traffic = None
+    # DRAM traffic per launch comes from an `ncu --set full` capture of THIS kernel source (profiles/); a capture of an
+    # older source is not reported
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_pair_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_pair_traffic.json")))
+        src_hash = _file_hash(os.path.join(ROOT, "vision_pt_b200", "csrc", "gemm_pair.cuh"))
+        if tj.get("kernel_source_sha1") == src_hash:
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r2_gemm_pair_traffic.json (ncu --set full, same kernel source)"
+        else:
+            traffic_src = "profiles/r2_gemm_pair_traffic.json is from another kernel source: not reported"
     except Exception:
-        pass
-    achieved = fl / (ms_gemm * 1e-3) / 1e12
+        traffic_src = "no ncu capture of this kernel source committed"
+    achieved = fl / (ms_all * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "gemm_pair_kernel (NF4 + LoRA linears of the blocks, forward and backward-dX)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-            "peak_source": peak_src, "launches": len(tape), "avg_launch_us": 1e3 * ms_gemm / len(tape),
-            "flops_per_launch": fl / len(tape),
-            "with_dequant": {"avg_call_us": 1e3 * ms_call / len(tape), "achieved": fl / (ms_call * 1e-3) / 1e12,
-                             "note": "same calls including the per-call NF4 dequantisation kernel (HBM-bound, 0 FLOP counted)"},
-            "how": "CUDA-graph replay of the step's taped calls, inputs rotated over 3 buffers per shape, best of 3"}
+            "traffic_source": traffic_src, "peak_source": peak_src, "launches": len(gemms), "dequant_launches": n_dq,
+            "avg_launch_us": 1e3 * ms_all / len(gemms), "flops_per_launch": fl / len(gemms),
+            "gemm_only": {"avg_launch_us": 1e3 * ms_gemm / len(gemms), "achieved": fl / (ms_gemm * 1e-3) / 1e12,
+                          "frac": fl / (ms_gemm * 1e-3) / 1e12 / peak, "replays": n_gemm,
+                          "note": "same replay with the dequantised weights already in their slots"},
+            "replays": n_all, "replay_ms": ms_all,
+            "how": "CUDA-graph replay of one step's taped GEMM + batched-dequantisation launches in step order, inputs "
+                   "rotated over 3 buffers per shape, mean over a >= 2 s loop; frac INCLUDES the dequantisation launches"}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
+# ------------------------------------------------------------------------------------------------ reference legs
+def _reference_available() -> bool:
+    try:
+        from oracle import refimport
+        return refimport.available()
+    except Exception:
+        return False
+
+
 def run_reference(args) -> None:
-    """The reference's CPU implementation of the path on the host cores: oracle port (the reference is Python and its
-    NF4 arithmetic lives in bitsandbytes, neither of which travels to the GPU box)."""
+    """The reference's CPU implementation of the path on the host cores, all threads: the reference's OWN Denoiser /
+    LoRALinear / scaled_dot_product_attention staged in oracle/_ref (oracle/make_ref.py), NF4 base linear restated
+    (bitsandbytes exists on neither box) -- or the oracle port when the staged reference is missing.  Every step is one
+    FULL batch of the named workload; the number of steps is bounded by a time budget and reported as run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import cpu_step
     model = args.model
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cb = min(args.cpu_batch, args.batch)
-    steps, warm = min(args.steps, 3), min(args.warmup, 1)
-    r = cpu_step.time_train_steps(model=model, batch=cb, height=args.res, width=args.res, steps=steps, warmup=warm,
-                                  rank=args.rank)
+    budget_s = float(os.environ.get("VPT_CPU_BUDGET_S", "150"))
+    want_steps, want_warm = max(1, args.steps), max(1, min(args.warmup, 2))
+    t_start = time.perf_counter()
+    if _reference_available():
+        from oracle import ref_runner
+        kind = "reference"
+        net, cfg = ref_runner.build_reference_jit(model, rank=args.rank, alpha=float(args.rank), device="cpu", dtype=torch.float32)
+        spent = {"t": 0.0}
+
+        def on_step(it, dt):
+            spent["t"] += dt
+            return spent["t"] + dt <= budget_s          # stop before the step that would overrun the budget
+
+        r = ref_runner.train_steps(net, cfg, args.batch, args.res, args.res, steps=want_steps, warmup=want_warm,
+                                   device="cpu", dtype=torch.float32, on_step=on_step)
+        if r["steps"] == 0:                              # a single step took more than the budget: it IS the measurement
+            r = ref_runner.train_steps(net, cfg, args.batch, args.res, args.res, steps=1, warmup=0, device="cpu", dtype=torch.float32)
+        what = ("the reference's own Denoiser + LoRALinear + SDPA (oracle/_ref), NF4 base linear restated with MatMul4Bit "
+                "semantics (no bitsandbytes wheel exists here)")
+    else:
+        from oracle import cpu_step
+        kind = "port"
+        steps = min(want_steps, 3)
+        r = cpu_step.time_train_steps(model=model, batch=args.batch, height=args.res, width=args.res, steps=steps, warmup=1,
+                                      rank=args.rank)
+        r["warmup"] = 1
+        what = "oracle port of the same step (oracle/cpu_step.py)"
     v = r["images_per_s"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": r["warmup"], "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(model, args.batch, args.res, args.rank)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "port",
-                         "sample": f"{cb} images/step x {steps} steps of the same step (fp32, NF4 dequantised per call) on the host CPU"},
+        "config": {"workload": workload_name(model, args.batch, args.res, args.rank), "global_batch": args.batch,
+                   "device": "host CPU", "requested_steps": args.steps, "requested_warmup": args.warmup,
+                   "time_budget_s": budget_s},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": kind,
+                         "sample": f"{r['steps']} full steps of {args.batch} images (fp32, NF4 dequantised per call in forward and "
+                                   f"backward); {what}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line), flush=True)
 
 
+def _reference_from_ours(net, torch):
+    """{module path: oracle Nf4State} and a reference-named state dict taken from OUR model, so that the reference legs
+    run the same weights without re-quantising on the host."""
+    from oracle import nf4 as on
+    states, sd = {}, {}
+    for name, mod in net.named_modules():
+        qs = getattr(mod, "quant_state", None)
+        if qs is not None:
+            path = name[:-len(".linear")] if name.endswith(".linear") else name
+            states[path] = on.Nf4State(packed=qs.packed.cpu(), absmax=qs.absmax.cpu(), nested_absmax=qs.nested_absmax.cpu(),
+                                       nested_code=qs.nested_code.cpu(), code=qs.code.cpu(), offset=float(qs.offset),
+                                       shape=tuple(qs.shape), dtype=qs.dtype)
+    for k, v in net.state_dict().items():
+        if ".lora_" in k or k.endswith(".alpha") or ".weight." in k or v.dtype == torch.uint8:
+            continue
+        sd[k.replace(".linear.", ".")] = v.detach().float().cpu()
+    return states, sd
+
+
+def reference_gpu_leg(net, args, model_name, torch, steps: int = 5, warmup: int = 2):
+    """the reference's GPU path restated without bitsandbytes -- the reference's own Denoiser / LoRALinear /
+    SDPA (oracle/_ref) in bf16 eager on this B200, NF4 base linear = dequantise (torch ops) + torch.matmul in forward and
+    backward, torch.optim.AdamW -- on the same weights and batch size.  A baseline that is measured, not a product path."""
+    if not _reference_available():
+        return {"unavailable": "oracle/_ref is not staged (run python oracle/make_ref.py where /root/reference exists)"}
+    from oracle import ref_runner
+    states, sd = _reference_from_ours(net, torch)
+    dev = next(net.parameters()).device
+    ref, cfg = ref_runner.build_reference_jit(net.config.model_dump(), rank=args.rank, alpha=float(args.rank), device=dev, dtype=torch.bfloat16,
+                                              nf4_states=states, state_dict=sd)
+    r = ref_runner.train_steps(ref, cfg, args.batch, args.res, args.res, steps=steps, warmup=warmup, device=dev,
+                               dtype=torch.bfloat16)
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del ref
+    torch.cuda.empty_cache()
+    return {"value": r["images_per_s"], "unit": UNIT, "ms_per_step": r["s_per_step"] * 1e3, "steps": r["steps"], "warmup": warmup,
+            "kind": "restatement", "dtype": "bf16", "loss": r["loss"], "peak_mem_gb": peak_gb,
+            "what": "reference Denoiser + LoRALinear + F.scaled_dot_product_attention (expanded bool mask) from oracle/_ref, eager "
+                    "PyTorch on the same B200 and weights; NF4 base = torch-op dequantise + matmul in fwd and bwd (bitsandbytes' "
+                    "MatMul4Bit semantics, the wheel itself is absent); clip_grad_norm_ + torch.optim.AdamW"}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
+def _timed_steps(run, steps, barrier, torch, dist, dev, world):
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -255,121 +402,111 @@ def run_ours(args) -> None:
     from vision_pt_b200 import train as T
 
     model_name = args.model
-    net = T.build_jit_qlora(model_name, rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
-    net.set_gradient_checkpointing(args.checkpointing)
     hp = T.TrainHParams(optimizer=args.optimizer)
-    step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
-                               seed=42 + rank, hp=hp)
-    host = T.synthetic_batch(args.batch, args.res, args.res, seed=1000 + rank)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
-
-    def load_batch():
-        step.image.copy_(host[0], non_blocking=True)
-        step.class_ids.copy_(host[1], non_blocking=True)
-        step.attention_mask.copy_(host[2], non_blocking=True)
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local]) if dist.get_backend() == "nccl" else dist.barrier()
 
-    load_batch()
+    def build(name):
+        net = T.build_jit_qlora(name, rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
+        net.set_gradient_checkpointing(args.checkpointing)
+        trainer = T.JiTQLoRATrainer(net, hp=hp, process_group=group, use_graph=not args.no_graph, seed=42 + rank)
+        return net, trainer, trainer.bucket(args.batch, args.res, args.res)
+
+    net, trainer, step = build(model_name)
+    # two distinct pinned host batches alternate through the end-to-end loop
+    hosts = [T.synthetic_batch(args.batch, args.res, args.res, seed=1000 + rank + 7919 * i) for i in range(2)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in hosts[0])
+
+    trainer.train_step(*hosts[0])                 # captures the graph (collective-free warm-up inside) and runs one step
     torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         step.run()
     torch.cuda.synchronize()
     launches_per_step = step.kernel_launches
 
-    # ---- device-resident throughput
+    # ---- device-resident throughput: K graph replays, batch already in HBM
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
-    barrier()
-    torch.cuda.synchronize()
     if sampler is not None:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step.run()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
+    ms_total = _timed_steps(step.run, args.steps, barrier, torch, dist, dev, world)
     clocks = sampler.stop() if sampler is not None else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
     ms_step = ms_total / args.steps
     value = world * args.batch * args.steps / (ms_total * 1e-3)
     final_loss = float(step.loss.item())
     loss_target = step.hp.loss_target
 
-    # ---- end to end through the public API: pinned host batch -> H2D -> step -> D2H loss, every step
-    barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        load_batch()
-        loss = step.run()
-        _ = float(loss.item())          # D2H read of the step's result (synchronises, as a logging trainer would)
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.batch * args.steps / (float(ms2.item()) * 1e-3)
+    # ---- end to end through the public API (JiTQLoRATrainer.train_step): every step copies ITS batch from pinned host
+    # memory (the copy of step t+1 is started on the copy stream while step t computes) and reads a loss back to the
+    # host (the loss of step t-1, through pinned memory, so the read does not stall step t)
+    trainer.prefetch(*hosts[0])
+    counter = {"i": 0}
 
-    # ---- roofline of the dominant kernel (the CTA-pair NF4-LoRA GEMM): the fused-linear calls of one real step are taped,
-    # then replayed back to back from a CUDA graph on buffers of the same shapes (inputs rotate over > L2 worth of memory)
-    # and timed with CUDA events on the launching stream -- once GEMM only (`reuse_scratch`: the dequantised weight is
-    # already in the workspace) and once as issued in the step (dequantisation + GEMM).
-    # Every rank runs the taping step (it contains the gradient all-reduce); only rank 0 replays and reports.
+    def e2e_step():
+        i = counter["i"]
+        trainer.train_step(*hosts[i % 2], prefetch=hosts[(i + 1) % 2])
+        if i > 0:
+            trainer.read_loss(1)
+        counter["i"] = i + 1
+
+    for _ in range(2):
+        e2e_step()
+    ms2 = _timed_steps(e2e_step, args.steps, barrier, torch, dist, dev, world)
+    _ = trainer.read_loss(0)
+    e2e_value = world * args.batch * args.steps / (ms2 * 1e-3)
+
+    # ---- roofline of the dominant kernel; every rank runs the taping step (it contains the gradient all-reduce), only
+    # rank 0 replays and reports
     roof = gemm_roofline(step, ops, torch, replay_here=rank == 0)
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
-    cpu = None
+
+    # ---- the two baselines, rank 0 at N == 1 only: the reference's CPU path on a bounded sample, and the reference's GPU
+    # path restated on this same GPU
+    cpu = ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_step
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        r = cpu_step.time_train_steps(model=model_name if model_name in cpu_step.JIT_CONFIGS else "JiT-B/16",
-                                      batch=args.cpu_batch, height=args.res, width=args.res, steps=args.cpu_steps, warmup=1,
-                                      rank=args.rank)
-        cpu = {"value": r["images_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-               "sample": f"{args.cpu_batch} images/step x {args.cpu_steps} steps of the same step (fp32, NF4 dequantised per call)"}
+        if _reference_available():
+            from oracle import ref_runner
+            states, sd = _reference_from_ours(net, torch)
+            cnet, ccfg = ref_runner.build_reference_jit(net.config.model_dump(), rank=args.rank, alpha=float(args.rank), device="cpu",
+                                                        dtype=torch.float32, nf4_states=states, state_dict=sd)
+            r = ref_runner.train_steps(cnet, ccfg, args.cpu_batch, args.res, args.res, steps=args.cpu_steps, warmup=1,
+                                       device="cpu", dtype=torch.float32)
+            del cnet
+            kind, what = "reference", "the reference's own Denoiser + LoRALinear + SDPA (oracle/_ref), NF4 base linear restated"
+        else:
+            from oracle import cpu_step
+            r = cpu_step.time_train_steps(model=model_name if model_name in cpu_step.JIT_CONFIGS else "JiT-B/16",
+                                          batch=args.cpu_batch, height=args.res, width=args.res, steps=args.cpu_steps, warmup=1,
+                                          rank=args.rank)
+            kind, what = "port", "oracle port (oracle/cpu_step.py)"
+        cpu = {"value": r["images_per_s"], "unit": UNIT, "cores": r["threads"], "kind": kind,
+               "sample": f"{args.cpu_batch} images/step x {r['steps']} steps of the same step (fp32, NF4 dequantised per call); {what}"}
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        try:
+            ref_gpu = reference_gpu_leg(net, args, model_name, torch)
+        except Exception as exc:                     # a baseline must never take the headline down with it
+            ref_gpu = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
-    # ---- secondary workload at N > 1: BASELINE.json configs[2], JiT-L/16 data parallel (same step, same timing rules)
+    # ---- secondary workload: BASELINE.json configs[2], JiT-L/16 (same step, same timing rules), at every N
     extra = None
-    if world > 1 and not args.no_extra and model_name != "JiT-L/16":
-        del step, net
+    fl = T.step_flops(net.config, args.batch, args.res, args.res, rank=args.rank)
+    if not args.no_extra and model_name != "JiT-L/16":
+        del step, trainer, net
         torch.cuda.empty_cache()
-        net = T.build_jit_qlora("JiT-L/16", rank=args.rank, alpha=float(args.rank), device=dev, seed=42)
-        step = T.JiTQLoRATrainStep(net, args.batch, args.res, args.res, process_group=group, use_graph=not args.no_graph,
-                                   seed=42 + rank, hp=hp)
-        load_batch_l = lambda: (step.image.copy_(host[0], non_blocking=True), step.class_ids.copy_(host[1], non_blocking=True),
-                                step.attention_mask.copy_(host[2], non_blocking=True))
-        load_batch_l()
+        net, trainer, step = build("JiT-L/16")
+        trainer.train_step(*hosts[0])
         for _ in range(3):
             step.run()
         ksteps = max(3, args.steps // 2)
-        barrier()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(ksteps):
-            step.run()
-        e1.record()
-        torch.cuda.synchronize()
-        barrier()
-        msl = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(msl, op=dist.ReduceOp.MAX)
+        msl = _timed_steps(step.run, ksteps, barrier, torch, dist, dev, world)
         fl_l = T.step_flops(net.config, args.batch, args.res, args.res, rank=args.rank)
-        extra = {"workload": workload_name("JiT-L/16", args.batch, args.res, args.rank), "value": world * args.batch * ksteps / (float(msl.item()) * 1e-3),
-                 "unit": UNIT, "ms_per_step": float(msl.item()) / ksteps, "steps": ksteps,
-                 "achieved_tflops_step": world * fl_l["total"] / (float(msl.item()) / ksteps * 1e-3) / 1e12}
-        net_cfg_for_flops = T.MODEL_CONFIGS[model_name]()
-    else:
-        net_cfg_for_flops = net.config
+        extra = {"workload": workload_name("JiT-L/16", args.batch, args.res, args.rank), "value": world * args.batch * ksteps / (msl * 1e-3),
+                 "unit": UNIT, "ms_per_step": msl / ksteps, "steps": ksteps, "n_gpus": world,
+                 "achieved_tflops_step": world * fl_l["total"] / (msl / ksteps * 1e-3) / 1e12}
 
     if rank == 0:
-        fl = T.step_flops(net_cfg_for_flops, args.batch, args.res, args.res, rank=args.rank)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -379,13 +516,19 @@ def run_ours(args) -> None:
                        "cuda_graph": not args.no_graph, "gradient_checkpointing": bool(args.checkpointing),
                        "l2": "no flush: one step streams far more than the 126 MB L2 (saved activations of every block)",
                        "optimizer": ("AdamW" if args.optimizer == "adamw" else "schedulefree.RAdamScheduleFree")
-                                    + " over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target},
+                                    + " over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target,
+                       "exchange": (f"chunked NCCL all-reduce of the flat LoRA gradients, {len(step._chunks) if world > 1 else 0} chunks, "
+                                    f"{'inside' if world > 1 and step.nccl_in_graph else 'outside'} the step's CUDA graph") if world > 1 else "none (1 GPU)"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "how": "JiTQLoRATrainer.train_step(batch, prefetch=next): H2D of the next batch on a copy stream, loss of the "
+                           "previous step read from pinned host memory"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "reference_gpu": ref_gpu,
+            "vs_reference_gpu": (value / ref_gpu["value"]) if ref_gpu and ref_gpu.get("value") else None,
             "extra_workload": extra,
             "step_tflops_algorithmic": fl["total"] / 1e12,
             "achieved_tflops_step": world * fl["total"] / (ms_step * 1e-3) / 1e12,

@@ -136,7 +136,7 @@ int vpt_lora_grad_batch(const vpt_lora_grad_item* items, int32_t n_items, vpt_st
  * Attention.forward (src/models/jit/denoiser.py:351-397); the bool key-padding mask is given as seqlens_k[b] = number
  * of leading valid keys (NULL = all).  Tensors are (batch, token, head, head_dim) with element strides (sb, sl, sh);
  * both [B,H,L,hd] and [B,L,H,hd] memory layouts are accepted.  head_dim 64 (JiT-B/L, SDXL) and 80 (JiT-H) run the tcgen05
- * kernels; 32 / 96 / 128 run CUDA-core kernels (and 80 too with VPT_ATTN80_SIMPLE=1 in the environment). */
+ * kernels; 32 / 96 / 128 run CUDA-core kernels. */
 typedef struct {
   const void* ptr;
   int64_t sb, sl, sh;

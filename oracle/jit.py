@@ -60,8 +60,16 @@ def swiglu_gate(g, u):
     return F.silu(g) * u
 
 
+# True: fp32 inputs stay fp32 in attention (a "ground truth" arm for error budgets); the reference itself casts fp32
+# q/k/v to bf16 (src/modules/attention.py:113-118), which is the default here
+ATTENTION_FP32 = False
+
+
 def attention(q, k, v, key_mask=None):
     """q,k,v [B,H,L,hd]; key_mask [B,Lk] (1 = attend).  fp32 inputs are computed in bf16 like the reference."""
+    if q.dtype == torch.float32 and ATTENTION_FP32:
+        key_len = None if key_mask is None else key_mask.bool().sum(dim=1)
+        return attention_explicit(q, k, v, key_len)
     if q.dtype == torch.float32:
         q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
     mask = None

@@ -149,9 +149,9 @@ def quantize_nf4(w: torch.Tensor) -> Nf4State:
 def dequantize_absmax(st: Nf4State) -> torch.Tensor:
     """dequantize_blockwise(absmax, state2) then ``absmax += offset``: two separately rounded fp32 operations."""
     qa = st.absmax.to(torch.int64)
-    idx = torch.arange(qa.shape[0]) // NESTED_BLOCK
+    idx = torch.arange(qa.shape[0], device=qa.device) // NESTED_BLOCK        # runs wherever the tensors live
     am = st.nested_code.to(torch.float32)[qa] * st.nested_absmax.to(torch.float32)[idx]
-    return am + torch.tensor(st.offset, dtype=torch.float32)
+    return am + torch.tensor(st.offset, dtype=torch.float32, device=qa.device)
 
 
 def dequantize_nf4(st: Nf4State) -> torch.Tensor:

@@ -1,4 +1,5 @@
-"""bench.py's reference arm runs on the CPU (the oracle port) and prints one JSON line with the contract's keys."""
+"""bench.py's reference arm runs on the CPU (the reference's own modules staged in oracle/_ref, else the oracle port) and
+prints one JSON line with the contract's keys."""
 import json
 import os
 import subprocess
@@ -9,14 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--cpu-batch", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--batch", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["steps"] == 1 and "batch 2 per GPU" in line["config"]["workload"]      # the label is the work that ran
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "JiT-B/16" in line["config"]["workload"]
 

@@ -30,15 +30,25 @@ def _oracle_params(net):
     return P
 
 
-def test_loss_curve_200_steps_matches_oracle():
+# "mini": a miniature net (small-M prologue GEMM route).  "jit_b_width": JiT-B/16's own widths (D 768, 12 heads, F 2048,
+# bottleneck 128, context 768) at depth 4 on 256-px images, batch 8 -> M = 2640 rows: the CTA-pair GEMM / batched
+# dequantisation route of real training, context tokens joining at block 1.
+@pytest.mark.parametrize("which", ["mini", "jit_b_width"])
+def test_loss_curve_200_steps_matches_oracle(which):
     from vision_pt_b200 import train as T
     from vision_pt_b200.jit import DenoiserConfig
     dev = torch.device("cuda")
-    cfg = DenoiserConfig(patch_size=16, in_channels=3, out_channels=3, hidden_size=128, depth=2, num_heads=2, mlp_ratio=4.0,
-                         bottleneck_dim=32, num_time_tokens=4, rope_axes_dims=[16, 24, 24], context_dim=64,
-                         context_start_block=1)
+    if which == "mini":
+        cfg = DenoiserConfig(patch_size=16, in_channels=3, out_channels=3, hidden_size=128, depth=2, num_heads=2, mlp_ratio=4.0,
+                             bottleneck_dim=32, num_time_tokens=4, rope_axes_dims=[16, 24, 24], context_dim=64,
+                             context_start_block=1)
+        B, H, W, steps = 8, 64, 64, 200
+    else:
+        cfg = DenoiserConfig(patch_size=16, in_channels=3, out_channels=3, hidden_size=768, depth=4, num_heads=12, mlp_ratio=4.0,
+                             bottleneck_dim=128, num_time_tokens=4, rope_axes_dims=[16, 24, 24], context_dim=768,
+                             context_start_block=1)
+        B, H, W, steps = 8, 256, 256, 200
     cfgd = cfg.model_dump()
-    B, H, W, steps = 8, 64, 64, 200
     hp = T.TrainHParams(lr=2e-3, clip_grad_norm=1.0, loss_target="image")
     net = T.build_jit_qlora(cfg, rank=16, alpha=16.0, device=dev, seed=11, lora_up_std=0.02)
     P = _oracle_params(net)                                   # before training: both sides start from the same weights

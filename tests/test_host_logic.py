@@ -161,3 +161,66 @@ def test_padded_weight_copy_lives_on_the_weight_object():
     assert torch.equal(ops.padded_weight(a), a)                    # stale copy replaced after the in-place change
     c = torch.randn(8, 16).to(torch.bfloat16)
     assert ops.padded_weight(c) is c                               # already aligned: no copy
+
+
+def test_attention_masks_must_be_prefix_key_padding_masks():
+    """Advisor finding r1: a non-prefix mask or an additive float mask must be refused, not computed as a prefix."""
+    from vision_pt_b200.modules.attention import key_lengths_from_mask, prefix_key_lengths
+    ok = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1], [0, 0, 0, 0, 0]])
+    assert prefix_key_lengths(ok).tolist() == [3, 5, 0] and prefix_key_lengths(ok.bool()).dtype == torch.int32
+    with pytest.raises(NotImplementedError):
+        prefix_key_lengths(torch.tensor([[0, 1, 1, 1, 1]]))            # left padding
+    with pytest.raises(NotImplementedError):
+        prefix_key_lengths(torch.tensor([[1, 0, 1, 1, 0]]))            # a hole
+    with pytest.raises(TypeError):
+        prefix_key_lengths(torch.zeros(2, 5))                          # F.sdpa-style additive mask: 0.0 means "attend"
+    m4 = ok.bool().view(3, 1, 1, 5).expand(3, 4, 7, 5)
+    assert key_lengths_from_mask(m4, 3, 5).tolist() == [3, 5, 0]
+    with pytest.raises(NotImplementedError):
+        key_lengths_from_mask(torch.ones(3, 4, 7, 5, dtype=torch.bool), 3, 5)   # depends on head / query: not a key-padding mask
+
+
+def test_lora_alpha_follows_load_state_dict_and_assignment():
+    """Advisor finding r1: the kernels scale by a host copy of alpha; it must follow the stored parameter."""
+    from vision_pt_b200.modules.peft import LoRAConfig, LoRALinear
+    lay = LoRALinear(LoRAConfig(rank=4, alpha=2.0, dtype="float32"), nn.Linear(16, 8))
+    assert lay.scale == 0.5
+    sd = {k: v.clone() for k, v in lay.state_dict().items()}
+    sd["alpha"] = torch.tensor(6.0)
+    lay.load_state_dict(sd)
+    assert float(lay.alpha) == 6.0 and lay.scale == 1.5
+    lay.alpha = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+    assert lay.scale == 0.25
+    wrapper = nn.Sequential(lay)                                     # through a parent module's load_state_dict as well
+    sd = {k: v.clone() for k, v in wrapper.state_dict().items()}
+    sd["0.alpha"] = torch.tensor(8.0)
+    wrapper.load_state_dict(sd)
+    assert lay.scale == 2.0
+
+
+def test_gradient_chunk_plan_follows_block_order():
+    """The chunks of the overlapped all-reduce: contiguous flat ranges, last blocks first, covering the buffer once."""
+    from types import SimpleNamespace
+
+    from vision_pt_b200.jit import Denoiser, DenoiserConfig
+    from vision_pt_b200.modules.peft import LoRAConfig, PeftTargetConfig
+    from vision_pt_b200.train import LORA_TARGET, FlatLoRA, JiTQLoRATrainStep
+    cfg = DenoiserConfig(patch_size=16, hidden_size=128, depth=6, num_heads=2, bottleneck_dim=32, context_dim=64)
+    net = Denoiser(cfg).to(torch.bfloat16)
+    net.requires_grad_(False)
+    PeftTargetConfig(include_keys=[LORA_TARGET], config=LoRAConfig(rank=16, alpha=16.0)).replace_to_peft_layer(net)
+    for n, p in net.named_parameters():
+        p.requires_grad_(".lora_" in n)
+    flat = FlatLoRA(net)
+    stub = SimpleNamespace(model=net, flat=flat)
+    for n_chunks in (1, 2, 3):
+        plan = JiTQLoRATrainStep._chunk_plan(stub, n_chunks)
+        assert len(plan) == n_chunks
+        assert plan[0][2] == flat.numel and plan[-1][1] == 0 and plan[-1][0] == 0
+        for (fb_a, lo_a, hi_a), (fb_b, lo_b, hi_b) in zip(plan, plan[1:]):
+            assert lo_a == hi_b and fb_a > fb_b                       # adjacent, and in the order backward finishes them
+        names = {id(p): n for n, p in net.named_parameters()}
+        for fb, lo, hi in plan:                                       # a chunk holds exactly the blocks >= its first block
+            inside = [int(names[id(p)].split(".")[1]) for p, off in zip(flat.params, flat.offsets) if lo <= off < hi]
+            assert min(inside) == fb
+    assert JiTQLoRATrainStep._chunk_plan(stub, 4) == [(0, 0, flat.numel)]   # fewer than 2 blocks per chunk: one exchange

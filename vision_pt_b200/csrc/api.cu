@@ -245,9 +245,8 @@ extern "C" int vpt_attn_fwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, 
                             const int32_t* seqlens_k, float scale, float* lse2, vpt_stream_t stream) {
   VPT_REQUIRE(q && k && v && o && lse2 && B > 0 && H > 0 && Lq > 0 && Lk > 0, "vpt_attn_fwd: bad arguments");
   if (head_dim == 64) return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream));
-  // head_dim 80 (JiT-H): forward on the tensor cores; VPT_ATTN80_SIMPLE=1 keeps the CUDA-core kernel (same lse2 layout)
-  static const bool simple80 = getenv("VPT_ATTN80_SIMPLE") != nullptr;
-  if (head_dim == 80 && !simple80)
+  // head_dim 80 (JiT-H): the same tcgen05 kernels, templated on the head dimension
+  if (head_dim == 80)
     return launch_attn_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, seqlens_k, scale, lse2, S(stream), 80);
   return launch_attn_simple_fwd(AT(q), AT(k), AT(v), AT(o), B, H, Lq, Lk, head_dim, seqlens_k, scale, lse2, S(stream));
 }
@@ -257,8 +256,7 @@ extern "C" int vpt_attn_bwd(const vpt_attn_tensor* q, const vpt_attn_tensor* k, 
                             int32_t Lk, int32_t head_dim, const int32_t* seqlens_k, float scale, const float* lse2,
                             float* delta_ws, vpt_stream_t stream) {
   VPT_REQUIRE(q && k && v && o && d_o && dq_f32 && dk && dv && lse2 && delta_ws, "vpt_attn_bwd: null pointer");
-  static const bool simple80 = getenv("VPT_ATTN80_SIMPLE") != nullptr;
-  if (head_dim == 64 || (head_dim == 80 && !simple80))
+  if (head_dim == 64 || head_dim == 80)
     return launch_attn_bwd(AT(q), AT(k), AT(v), AT(o), AT(d_o), AT(dq_f32), AT(dk), AT(dv), B, H, Lq, Lk, seqlens_k, scale, lse2,
                            delta_ws, S(stream), head_dim);
   return launch_attn_simple_bwd(AT(q), AT(k), AT(v), AT(o), AT(d_o), AT(dq_f32), AT(dk), AT(dv), B, H, Lq, Lk, head_dim, seqlens_k,

@@ -1,6 +1,5 @@
-// Attention forward / backward for head dimensions other than 64 (JiT-H: 80).  CUDA-core kernels, correctness first:
-// the tcgen05 kernels (attention.cuh, attention_bwd.cuh) are built for head_dim 64; a 64 + 16 operand split for 80 fits the
-// TMEM budget (128 + 128 + 3 * 80 = 496 columns) and is the planned replacement.  Same semantics:
+// Attention forward / backward for the head dimensions the tcgen05 kernels (attention.cuh, attention_bwd.cuh: 64 and 80)
+// do not cover: 32, 96, 128.  CUDA-core kernels, correctness first.  Same semantics:
 // softmax(q k^T * scale + key-length mask) v, non-causal, bf16 in / out, fp32 arithmetic, lse2 / delta with the row pitch
 // rounded up to 128 (src/modules/attention.py:98-129, src/models/jit/denoiser.py:351-397 of the reference).
 //

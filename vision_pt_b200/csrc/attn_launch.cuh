@@ -123,7 +123,7 @@ inline int launch_attn_bwd(const AttnTensor& q, const AttnTensor& k, const AttnT
   return launch_attn_bwd_t<64>(q, k, v, o, d_o, dq_f32, dk, dv, B, H, Lq, Lk, seqlens_k, scale, lse2, delta, stream);
 }
 
-// ---- head_dim != 64: CUDA-core kernels (attention_simple.cuh)
+// ---- head_dim 32 / 96 / 128: CUDA-core kernels (attention_simple.cuh)
 inline SimpleAttnTensor SAT(const AttnTensor& t) { return SimpleAttnTensor{static_cast<const __nv_bfloat16*>(t.ptr), t.sb, t.sl, t.sh}; }
 
 template <int HD>
@@ -147,10 +147,9 @@ int launch_attn_simple_bwd_t(const SimpleAttnParams& p, float* delta, cudaStream
 #define VPT_SIMPLE_HD(CALL)                                                                   \
   switch (head_dim) {                                                                         \
     case 32: return CALL(32);                                                                 \
-    case 80: return CALL(80);                                                                 \
     case 96: return CALL(96);                                                                 \
     case 128: return CALL(128);                                                               \
-    default: return fail("attention: head_dim must be 64 (tcgen05 kernels) or 32 / 80 / 96 / 128 (CUDA-core kernels)"); \
+    default: return fail("attention: head_dim must be 64 / 80 (tcgen05 kernels) or 32 / 96 / 128 (CUDA-core kernels)"); \
   }
 
 inline int launch_attn_simple_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, const AttnTensor& o, int B,

@@ -1,7 +1,6 @@
 // Host launcher of gemm_pair_kernel: tensor maps, tile width, one CTA pair per TPC.
 #pragma once
 #include "gemm_pair.cuh"
-#include "gemm_quad.cuh"
 #include <stdlib.h>
 
 #include "host.cuh"
@@ -60,47 +59,6 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
   return 0;
 }
 
-// Cluster-of-4 variant (two pairs share the weight tile by multicast), BN = 192.
-template <bool kLoRA>
-int launch_quad_t(const PairLaunch& g, cudaStream_t stream) {
-  constexpr int BN = 192;
-  using S = QuadSmem<BN, kLoRA>;
-  PairParams p = g.p;
-  p.num_m_pairs = (p.M + 255) / 256;
-  p.num_n_tiles = (p.NO + BN - 1) / BN;
-  CUtensorMap tmA, tmB56, tmB48, tmB32, tmP, tmD, tmR;
-  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  const uint64_t pw = static_cast<uint64_t>(g.ldw) * 2;
-  if (make_tmap_bf16_2d(&tmA, g.act, p.R, p.M, static_cast<uint64_t>(g.lda) * 2, 64, 128, sw)) return 1;
-  if (make_tmap_bf16_2d(&tmB56, g.w, p.R, p.NO, pw, 64, 56, sw)) return 1;
-  if (make_tmap_bf16_2d(&tmB48, g.w, p.R, p.NO, pw, 64, 48, sw)) return 1;
-  if (make_tmap_bf16_2d(&tmB32, g.w, p.R, p.NO, pw, 64, 32, sw)) return 1;
-  tmP = tmA;
-  if (kLoRA && make_tmap_bf16_2d(&tmP, g.p_rows, p.R, kPairRank, static_cast<uint64_t>(g.ldp) * 2, 64, kPairRank, sw)) return 1;
-  if (make_tmap_bf16_2d(&tmD, g.out, p.NO, p.M, static_cast<uint64_t>(g.ldd) * 2, 64, 32, sw)) return 1;
-  tmR = tmD;
-  if (p.residual != nullptr && make_tmap_bf16_2d(&tmR, p.residual, p.NO, p.M, static_cast<uint64_t>(p.ldr) * 2, 64, 32, sw)) return 1;
-  auto kern = gemm_quad_kernel<BN, kLoRA>;
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    VPT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    // clusters of four need two free TPCs in one GPC: fewer than sm_count / 4 may be co-resident (33 of 37 on a B200);
-    // a persistent grid larger than that would serialise a second wave
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(4 * (sm_count() / 4));
-    cfg.blockDim = dim3(kPairThreads);
-    cfg.dynamicSmemBytes = S::kTotal;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = sm_count() / 4;
-    max_clusters = n;
-    if (getenv("VPT_DEBUG") != nullptr) fprintf(stderr, "[vpt] gemm_quad<%d>: smem %d B, max active clusters %d\n", int(kLoRA), S::kTotal, n);
-  }
-  int quads = ((p.num_m_pairs + 1) / 2) * p.num_n_tiles;
-  if (quads > max_clusters) quads = max_clusters;
-  VPT_CUDA_OK(launch_pdl(kern, dim3(4 * quads), dim3(kPairThreads), S::kTotal, stream, tmA, tmB56, tmB48, tmB32, tmP, tmD, tmR, p));
-  return 0;
-}
-
 // Tile width: whole waves of the 74 pairs x UMMA N, with the narrower tile charged for its extra L2 traffic.
 inline int choose_pair_bn(int M, int NO, bool lora) {
   const int pairs = (sm_count() > 0 ? sm_count() : 148) / 2;
@@ -123,8 +81,6 @@ inline int choose_pair_bn(int M, int NO, bool lora) {
 inline int launch_pair(const PairLaunch& g, cudaStream_t stream) {
   const bool lora = g.p_rows != nullptr;
   const int bn = g.bn > 0 ? g.bn : choose_pair_bn(g.p.M, g.p.NO, lora);
-  static const bool use_quads = getenv("VPT_QUAD") != nullptr;   // opt-in: measured slower than pairs
-  if (use_quads && bn == 192 && g.p.M >= 1024) return lora ? launch_quad_t<true>(g, stream) : launch_quad_t<false>(g, stream);
   if (lora) {
     if (bn == 192) return launch_pair_t<192, true>(g, stream);
     if (bn == 128) return launch_pair_t<128, true>(g, stream);

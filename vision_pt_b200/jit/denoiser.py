@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from ..modules.attention import prefix_key_lengths
 from ..modules.norm import get_norm_layer
 from ..modules.peft import LoRALinear
 from ..modules.quant import NF4Linear
@@ -178,6 +179,11 @@ class BottleneckFinalLayer(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------- fused block
+# Called as hook(block_index) at the end of every fused block's backward, once the block's LoRA gradients sit in the flat
+# buffer: the data-parallel trainer issues the all-reduce of finished gradient chunks from here (train.py).
+BLOCK_BACKWARD_HOOK = None
+
+
 class _Lin:
     """What one of the seven block linears contributes to the fused sequence."""
     __slots__ = ("w", "bias", "down", "up", "scale", "rank")
@@ -214,7 +220,7 @@ class JiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cos_sin, seqlens, spec, *lora):
-        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _ = spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _, _ = spec
         B, L, D = x.shape
         M = B * L
         x2 = x.reshape(M, D)
@@ -264,7 +270,7 @@ class JiTBlockFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x2, rstd1, h1, q_pre, k_pre, v, q, k, o2, lse2, x1, rstd2, h2, g, u, a,
          t_q, t_k, t_v, t_o, t_g, t_u, t_3) = ctx.saved_tensors
-        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in = ctx.spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in, block_index = ctx.spec
         pads = ctx.pads
         B, L, D = ctx.dims
         M = B * L
@@ -335,6 +341,8 @@ class JiTBlockFn(torch.autograd.Function):
         lora_grads(2, dv2, t_v, h1, dt_v)
         if items:
             ops.lora_grad_batch(items)
+        if BLOCK_BACKWARD_HOOK is not None:
+            BLOCK_BACKWARD_HOOK(block_index)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.rmsnorm_bwd_raw(dh1, x2, n1w, rstd1, dx1, eps).view(B, L, D)
@@ -358,6 +366,7 @@ class JiTBlock(nn.Module):
         self.norm2 = get_norm_layer(norm_type, hidden_dim, eps=eps)
         self.mlp = SwiGLU(dim=hidden_dim, hidden_dim=int(hidden_dim * mlp_ratio), dropout=ffn_dropout, bias=bias)
         self.use_fused = True
+        self.block_index = -1            # position in JiT.blocks (set by JiT): tells the backward hook how far backward is
 
     def _linears(self):
         return [self.attn.to_q, self.attn.to_k, self.attn.to_v, self.attn.to_o, self.mlp.w_1, self.mlp.w_2, self.mlp.w_3]
@@ -378,7 +387,7 @@ class JiTBlock(nn.Module):
             bf = lambda w: w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
             spec = (lins, bf(self.norm1.weight), bf(self.norm2.weight), bf(self.attn.q_norm.weight),
                     bf(self.attn.k_norm.weight), self.attn.num_heads, self.eps,
-                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in))
+                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in), self.block_index)
             lora = []
             for l in lins:
                 lora += [l.down, l.up]
@@ -408,6 +417,8 @@ class JiT(nn.Module):
             JiTBlock(config.hidden_size, config.num_heads, config.mlp_ratio, config.attn_dropout, config.proj_dropout, 0.0,
                      True, True, True, 1e-6, config.positional_encoding, config.norm_type)
             for _ in range(config.depth)])
+        for i, blk in enumerate(self.blocks):
+            blk.block_index = i
         if config.use_output_bottleneck:
             self.final_layer = BottleneckFinalLayer(config.hidden_size, config.bottleneck_dim, config.patch_size,
                                                     config.in_channels, norm_type="rms")
@@ -485,8 +496,9 @@ class JiT(nn.Module):
 
         cos_sin = self.rope_cos_sin(height, width, ctx_len, image.device)
         # key-padding mask -> per-sample key length (valid context tokens come first, reference class_encoder.py:72-81)
+        # -- a PREFIX mask: anything else is refused by prefix_key_lengths, not silently treated as one)
         if context_mask is not None:
-            seq_ctx = (pre_ctx + context_mask.to(image.device).to(torch.bool).sum(dim=1, dtype=torch.int32)).contiguous()
+            seq_ctx = (pre_ctx + prefix_key_lengths(context_mask.to(image.device))).contiguous()
         else:
             seq_ctx = None
 

@@ -16,8 +16,30 @@ from .. import ops
 AttentionImplementation = Literal["eager", "flash_attention_2", "xformers", "sdpa", "b200"]
 
 
+def prefix_key_lengths(mask2d: torch.Tensor) -> torch.Tensor:
+    """[B, Lk] key-padding mask (bool / integer, True = attend) -> int32 [B] number of leading valid keys.
+
+    The kernels take key LENGTHS, so the valid keys of every sample must come first (what JiT's class / text encoders
+    emit, reference class_encoder.py:72-81).  Anything else -- left padding, holes, a float additive mask -- is refused
+    instead of being silently computed as a prefix: floating-point masks raise TypeError; the prefix property is checked
+    on the host for CPU masks and by a device-side assert for CUDA masks (skipped only while a CUDA graph is being
+    captured: the eager warm-up that precedes every capture has run the check on the same buffers)."""
+    if mask2d.dtype.is_floating_point or mask2d.dtype.is_complex:
+        raise TypeError("attention masks must be bool / integer key-padding masks (True = attend); additive float masks "
+                        "are not supported by the B200 kernels")
+    m = mask2d.to(torch.bool)
+    lens = m.sum(dim=-1, dtype=torch.int32)
+    is_prefix = (m == (torch.arange(m.shape[-1], device=m.device).unsqueeze(0) < lens.unsqueeze(1))).all()
+    if not m.is_cuda:
+        if not bool(is_prefix):
+            raise NotImplementedError("only prefix key-padding masks (valid keys first) run on the B200 attention kernel")
+    elif not torch.cuda.is_current_stream_capturing():
+        torch._assert_async(is_prefix, "attention mask is not a prefix key-padding mask (valid keys must come first)")
+    return lens.contiguous()
+
+
 def key_lengths_from_mask(mask: torch.Tensor | None, batch: int, lk: int) -> torch.Tensor | None:
-    """bool mask broadcastable to [B,H,Lq,Lk] that only depends on (b, key) -> int32 [B] valid-key counts."""
+    """mask broadcastable to [B,H,Lq,Lk] that only depends on (b, key) -> int32 [B] valid-key counts."""
     if mask is None:
         return None
     m = mask
@@ -28,7 +50,7 @@ def key_lengths_from_mask(mask: torch.Tensor | None, batch: int, lk: int) -> tor
     for d in (1, 2):
         if m.shape[d] != 1 and m.stride(d) != 0:
             raise NotImplementedError("only key-padding masks (constant over heads and queries) run on the B200 kernel")
-    return m[:, 0, 0, :].to(torch.bool).sum(dim=-1, dtype=torch.int32).contiguous()
+    return prefix_key_lengths(m[:, 0, 0, :])
 
 
 def scaled_dot_product_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Tensor | None = None,

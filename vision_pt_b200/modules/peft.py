@@ -104,6 +104,19 @@ class LoRALinear(PeftLayer):
     def scale(self) -> float:
         return self._alpha_value / self.rank
 
+    def __setattr__(self, name, value):
+        # `module.alpha = ...` keeps the host copy the fused kernels scale by in step with the stored parameter
+        super().__setattr__(name, value)
+        if name == "alpha" and isinstance(value, torch.Tensor) and not value.is_meta:
+            object.__setattr__(self, "_alpha_value", float(value.detach().float().item()))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # load_state_dict() copies into `alpha` in place: refresh the host copy (reference lora.py:92-104 reads self.alpha)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        a = state_dict.get(prefix + "alpha")
+        if a is not None and not a.is_meta:
+            self._alpha_value = float(a.detach().float().item())
+
     @property
     def fusable(self) -> bool:
         """True when base GEMM + LoRA branch can run as the single fused kernel (CUDA bf16, rank <= 16, no dropout)."""

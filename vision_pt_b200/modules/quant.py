@@ -139,15 +139,21 @@ class NF4Linear(nn.Linear):
             if kind != "nf4":
                 raise NotImplementedError(f"prequantised {kind} weights are not on the hot path")
             meta = _unpack_meta(stats[tag[0]])
-            packed = state_dict[prefix + "weight"]
+            # a module that already lives on a CUDA device keeps its tensors there (a CPU checkpoint loaded into a GPU
+            # model must not leave host pointers behind for the kernels to dereference)
+            here = None if self.weight.is_meta else self.weight.device
+            if here is None and self.bias is not None and not self.bias.is_meta:
+                here = self.bias.device
+            mv = (lambda t: t.to(here)) if here is not None and here.type == "cuda" else (lambda t: t)
+            packed = mv(state_dict[prefix + "weight"])
             self.quant_state = ops.Nf4Tensors(
-                packed=packed, absmax=stats["absmax"], nested_absmax=stats["nested_absmax"].float(),
-                nested_code=stats["nested_quant_map"].float(), code=stats["quant_map"].float(),
+                packed=packed, absmax=mv(stats["absmax"]), nested_absmax=mv(stats["nested_absmax"].float()),
+                nested_code=mv(stats["nested_quant_map"].float()), code=mv(stats["quant_map"].float()),
                 offset=float(meta["nested_offset"]), shape=(int(meta["shape"][0]), int(meta["shape"][1])),
                 dtype=getattr(torch, meta["dtype"]))
             self.weight = nn.Parameter(packed, requires_grad=False)
             if self.bias is not None:
-                self.bias = nn.Parameter(state_dict[prefix + "bias"], requires_grad=False)
+                self.bias = nn.Parameter(mv(state_dict[prefix + "bias"]), requires_grad=False)
             return
         # full-precision weights: plain nn.Linear loading; quantised on the move to CUDA (or right away if already there)
         w = state_dict.get(prefix + "weight")

@@ -63,6 +63,9 @@ def dequant_block(weights: list, downs: list, ups: list, transposed: bool) -> li
         if transposed and d is not None:
             it.lora_down, it.ld_lora_down, it.lora_up = d.data_ptr(), d.stride(0), u.data_ptr()
     _lib.call("vpt_nf4_dequant_batch", arr, len(weights), int(transposed), _stream())
+    if GEMM_TIMER is not None:
+        GEMM_TIMER.append({"kind": "dequant", "weights": list(weights), "downs": list(downs), "ups": list(ups),
+                           "transposed": bool(transposed), "slot_ptrs": [s_.data_ptr() for s_ in slots]})
     return slots
 
 
@@ -232,6 +235,7 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     if prefilled:
         reuse_scratch = True
     if isinstance(w, Nf4Tensors):
+        _need_cuda(w.packed, w.absmax, bias)
         N, K = w.shape
         use_scratch = prefilled or NF4_GEMM_MODE == "scratch" or (NF4_GEMM_MODE == "auto" and M >= NF4_SCRATCH_MIN_M)
         args.w = w.c_struct(for_gemm=not use_scratch)
@@ -284,8 +288,9 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
         e1.record()
         lora = down is not None
         flops = 2.0 * M * K * N + (2.0 * M * RANK * (K + N) if lora else 0.0)
-        timer.append({"e0": e0, "e1": e1, "flops": flops, "M": M, "K": K, "N": N, "bwd": backward, "lora": lora,
+        timer.append({"kind": "gemm", "e0": e0, "e1": e1, "flops": flops, "M": M, "K": K, "N": N, "bwd": backward, "lora": lora,
                       "nf4": isinstance(w, Nf4Tensors), "scratch": scratch is not None,
+                      "scratch_ptr": scratch.data_ptr() if prefilled else None,
                       "call": (x2.shape, x2.stride(0), w, bias, down, up, scale, residual is not None, want_side, backward)})
     return out, side
 
@@ -383,7 +388,7 @@ def nf4_lora_linear(x, w, bias=None, lora_down=None, lora_up=None, scale: float 
 
 
 # ------------------------------------------------------------------------------------------------------- attention
-HEAD_DIMS = (64, 32, 80, 96, 128)     # 64 = tcgen05 kernels (JiT-B/L, SDXL); the rest run attention_simple.cuh (JiT-H: 80)
+HEAD_DIMS = (64, 80, 32, 96, 128)     # 64 / 80 = tcgen05 kernels (JiT-B/L, SDXL / JiT-H); the rest run attention_simple.cuh
 QKNORM_HEAD_DIMS = (64, 80, 96, 128)
 
 
@@ -426,7 +431,7 @@ def attn_bwd_raw(q, k, v, o, d_o, lse2, seqlens_k, scale: float):
     ts = [_at(t) for t in (q, k, v, o, d_o, dq, dk, dv)]
     _lib.call("vpt_attn_bwd", *[C.byref(t) for t in ts], B, H, Lq, Lk, hd, _p(seqlens_k), float(scale), _p(lse2), _p(delta),
               _stream())
-    if hd != 64:
+    if hd not in (64, 80):
         _lib.add_launches(2)          # delta + dQ + dK + dV kernels on the CUDA-core route
     return dq, dk, dv
 

@@ -14,6 +14,7 @@ differences stated in DESIGN.md:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -138,6 +139,9 @@ class TrainHParams:
     # "adamw" (torch.optim.AdamW semantics) or "radam_schedulefree" (schedulefree.RAdamScheduleFree, the optimiser of
     # the shipped YAMLs, configs/jit/x-loss/config.yml:75 with lr 1e-4; package defaults otherwise: no weight decay)
     optimizer: str = "adamw"
+    # micro-steps per optimiser step; gradients are exchanged only on the last one (accelerator.no_sync +
+    # gradient_accumulation_steps of the reference, src/trainer/common.py:322-331) and averaged over all of them
+    grad_accum_steps: int = 1
     sf_r: float = 0.0
     sf_weight_lr_power: float = 2.0
     sf_silent_sgd_phase: bool = True
@@ -188,16 +192,32 @@ class TrainState:
         self.eval_mode = eval_mode
 
 
+def init_communicator(group, device) -> None:
+    """Communicator set-up where every rank is in lock-step (construction of the trainer), never inside a lazily
+    triggered warm-up: one 4-byte all-reduce."""
+    if group is None or torch.distributed.get_world_size(group) == 1:
+        return
+    torch.distributed.all_reduce(torch.zeros(1, device=device), group=group)
+    torch.cuda.synchronize(device)
+
+
 class JiTQLoRATrainStep:
     """One optimisation step of JiT NF4-QLoRA class-to-image training; `run()` replays a captured CUDA graph.
 
     Inputs of a step (static device buffers the caller fills, e.g. by an async copy from pinned host memory):
       image [B,3,H,W] fp16 (the dataset emits fp16, src/dataset/text_to_image.py:152), class_ids [B,T] int64,
-      attention_mask [B,T] int64 (leading ones).  Output: `loss` (fp32 device scalar of the last step)."""
+      attention_mask [B,T] int64 (leading ones).  Output: `loss` (fp32 device scalar of the last step).
+
+    Data parallelism (world > 1): the LoRA-gradient all-reduce is part of the captured graph (`nccl_in_graph`, so a step is
+    ONE graph launch) and is split into `overlap_chunks` pieces: the gradient slices of the last blocks are final long
+    before backward ends, so their all-reduce is issued on a side stream as soon as backward has passed them and runs under
+    the remaining backward.  No collective is ever issued by a warm-up or a capture: ranks may capture new (H, W) buckets
+    at different times without their collectives falling out of step."""
 
     def __init__(self, model: Denoiser, batch: int, height: int, width: int, num_classes: int = 1000,
                  max_token_length: int = 64, hp: TrainHParams | None = None, process_group=None, use_graph: bool = True,
-                 seed: int | None = 0, state: TrainState | None = None):
+                 seed: int | None = 0, state: TrainState | None = None, nccl_in_graph: bool | None = None,
+                 overlap_chunks: int | None = None):
         self.model = model
         self.hp = hp or TrainHParams()
         self.group = process_group
@@ -205,6 +225,7 @@ class JiTQLoRATrainStep:
         dev = next(model.parameters()).device
         self.device = dev
         cfg = model.config
+        fresh_state = state is None
         self.state = state if state is not None else TrainState(model, num_classes)
         self.class_encoder = self.state.class_encoder
         self.flat = self.state.flat
@@ -217,16 +238,84 @@ class JiTQLoRATrainStep:
         self.crop = torch.zeros_like(self.size_info)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
-        self.graph: torch.cuda.CUDAGraph | None = None
-        self.graph_update: torch.cuda.CUDAGraph | None = None
+        self.graph: torch.cuda.CUDAGraph | None = None          # the whole step (or compute only, see capture())
+        self.graph_update: torch.cuda.CUDAGraph | None = None   # clip + update, when the exchange stays outside the graphs
+        self.graph_micro: torch.cuda.CUDAGraph | None = None    # a gradient-accumulation micro-step (compute only)
         self.kernel_launches = 0
+        nccl = self.world > 1 and torch.distributed.get_backend(process_group) == "nccl"
+        if nccl_in_graph is None:
+            nccl_in_graph = os.environ.get("VPT_NCCL_IN_GRAPH", "1") != "0"
+        self.nccl_in_graph = bool(nccl_in_graph) and nccl
+        if overlap_chunks is None:
+            overlap_chunks = int(os.environ.get("VPT_DP_CHUNKS", "2"))
+        self._chunks = self._chunk_plan(max(1, overlap_chunks)) if self.world > 1 else []
+        self._side = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._sent = 0                   # chunks of this step whose all-reduce has been issued
+        self._collectives = False        # only a real step (never a warm-up) may issue collectives
+        if fresh_state:
+            init_communicator(process_group, dev)
         if seed is not None:
             torch.manual_seed(seed)
         model.train()
 
+    # ------------------------------------------------------------------ gradient exchange
+    def _chunk_plan(self, n_chunks: int) -> list[tuple[int, int, int]]:
+        """(first_block, lo, hi): the flat-gradient range [lo, hi) belongs to blocks >= first_block and is complete once
+        backward has passed `first_block`.  Needs the flat buffer to be ordered by block (it is: FlatLoRA walks the
+        modules in order) with every trainable matrix inside a block; otherwise one chunk after backward."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        depth = len(self.model.blocks)
+        start = [None] * depth
+        ok = True
+        for p, off in zip(self.flat.params, self.flat.offsets):
+            n = names.get(id(p), "")
+            if not n.startswith("blocks."):
+                ok = False
+                break
+            b = int(n.split(".")[1])
+            start[b] = off if start[b] is None else min(start[b], off)
+        ok = ok and all(st is not None for st in start) and all(start[i] < start[i + 1] for i in range(depth - 1))
+        total = self.flat.numel
+        if not ok or n_chunks <= 1 or depth < 2 * n_chunks:
+            return [(0, 0, total)]
+        plan, hi = [], total
+        for c in range(n_chunks - 1, 0, -1):          # last blocks first: they finish backward first
+            fb = depth * c // n_chunks
+            plan.append((fb, start[fb], hi))
+            hi = start[fb]
+        plan.append((0, 0, hi))
+        return plan
+
+    def _send_chunk(self, lo: int, hi: int) -> None:
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            torch.distributed.all_reduce(self.flat.grad[lo:hi], group=self.group)
+
+    def _after_block_backward(self, block_index: int) -> None:
+        """Called by JiTBlockFn.backward once block `block_index` has accumulated its LoRA gradients."""
+        if not self._collectives:
+            return
+        while self._sent < len(self._chunks) - 1 and self._chunks[self._sent][0] >= block_index:
+            _, lo, hi = self._chunks[self._sent]
+            self._send_chunk(lo, hi)
+            self._sent += 1
+
+    def _exchange(self) -> float:
+        """The exchange step of data parallelism: SUM all-reduce of the flat LoRA-gradient buffer (NCCL), in chunks of
+        which all but the last were already issued during backward; returns 1 / world."""
+        if self.world == 1:
+            return 1.0
+        if self._collectives:
+            for _, lo, hi in self._chunks[self._sent:]:
+                self._send_chunk(lo, hi)
+            self._sent = 0
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+        return 1.0 / self.world
+
     # ------------------------------------------------------------------ the step itself (eager or under capture)
     def _compute(self) -> None:
-        """Noise, forward, loss, backward: LoRA gradients end up in the flat fp32 buffer.  No communication."""
+        """Noise, forward, loss, backward: LoRA gradients end up in the flat fp32 buffer."""
         hp = self.hp
         images = self.image
         B = images.shape[0]
@@ -240,18 +329,21 @@ class JiTQLoRATrainStep:
                           original_size=self.size_info, target_size=self.size_info, crop_coords=self.crop,
                           context_mask=self.attention_mask)
         loss = ops.flow_loss(pred, images, noisy, t, loss_target=hp.loss_target, clamp_eps=hp.timestep_eps)
-        loss.backward()
+        self._sent = 0
+        from .jit import denoiser as _dn
+        _dn.BLOCK_BACKWARD_HOOK = self._after_block_backward if self.world > 1 else None
+        try:
+            loss.backward()
+        finally:
+            _dn.BLOCK_BACKWARD_HOOK = None
         if not self.flat.direct:
             self.flat.gather_autograd_grads()
         self.loss.copy_(loss.detach())
 
-    def _exchange(self) -> float:
-        """The one collective of the step: SUM all-reduce of the flat LoRA-gradient buffer (NCCL); returns 1 / world."""
-        return self.flat.all_reduce(self.group) if self.world > 1 else 1.0
-
     def _update(self, scale: float) -> None:
         """Gradient-norm clipping + AdamW + zero_grad over the flat buffers (two kernels)."""
         hp = self.hp
+        scale = scale / max(1, hp.grad_accum_steps)
         sumsq = None
         if hp.clip_grad_norm is not None:
             self.sumsq.zero_()
@@ -269,58 +361,125 @@ class JiTQLoRATrainStep:
         ops.adamw_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.step_t, hp.lr, hp.betas, hp.eps,
                        hp.weight_decay, grad_scale=scale, sumsq=sumsq, max_norm=hp.clip_grad_norm or 0.0, zero_grad=True)
 
-    def _step(self) -> None:
+    def _step(self, sync: bool = True) -> None:
         self._compute()
-        self._update(self._exchange())
+        if sync:
+            self._update(self._exchange())
 
-    def capture(self, warmup: int = 2) -> None:
-        """Eager warm-up on a side stream (one-time kernel attribute setup, allocator growth, NCCL init), then capture.
-        One graph at world size 1.  With data parallelism the step is two graphs (compute | update) with the NCCL
-        all-reduce launched between them on the same stream: three launches per step, and no collective inside a capture."""
-        if self.hp.optimizer == "radam_schedulefree":
-            self.state.ensure_z()
-        snap = [t.clone() for t in self.state.tensors()]         # the warm-up steps must not train: a new (H, W) bucket
-        rng = torch.cuda.get_rng_state(self.device)              # may be captured in the middle of a run (nor draw noise)
+    def _warmup(self, n: int) -> None:
+        """Eager steps WITHOUT collectives on a side stream, with every piece of training state restored afterwards: a
+        new (H, W) bucket may be captured in the middle of a run, by one rank only."""
+        snap = [t.clone() for t in self.state.tensors()]
+        grad = self.flat.grad.clone()                            # a capture may fall between accumulation micro-steps
+        rng = torch.cuda.get_rng_state(self.device)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
+            for _ in range(n):
                 self._step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        before = ops._lib.launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        pool = {} if self.state.pool is None else {"pool": self.state.pool}
-        if self.world == 1:
-            with torch.cuda.graph(self.graph, **pool):
-                self._step()
-        else:
-            with torch.cuda.graph(self.graph, **pool):
-                self._compute()
-            self.graph_update = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
-                self._update(1.0 / self.world)
-        self.state.pool = self.graph.pool()
-        self.kernel_launches = ops._lib.launch_count() - before
         for t, t0 in zip(self.state.tensors(), snap):
             t.copy_(t0)
-        self.flat.grad.zero_()
+        self.flat.grad.copy_(grad)
         torch.cuda.set_rng_state(rng, self.device)
         torch.cuda.synchronize()
 
-    def run(self) -> torch.Tensor:
+    def _graph_ctx(self, g: torch.cuda.CUDAGraph):
+        kw = {} if self.state.pool is None else {"pool": self.state.pool}
+        if self.world > 1:
+            kw["capture_error_mode"] = "thread_local"            # NCCL's watchdog thread may touch CUDA during a capture
+        return torch.cuda.graph(g, **kw)
+
+    def capture(self, warmup: int = 2) -> None:
+        """Eager warm-up (one-time kernel attribute setup, allocator growth), then capture.  One graph per step: at
+        world > 1 the chunked NCCL all-reduce is captured with it (fork / join of the side stream become graph edges).
+        With `nccl_in_graph` off (or a non-NCCL backend) the step is two graphs (compute | update) with the all-reduce
+        launched between them."""
+        if self.hp.optimizer == "radam_schedulefree":
+            self.state.ensure_z()
+        self._collectives = False
+        self._warmup(warmup)
+        snap = [t.clone() for t in self.state.tensors()]         # capturing does not execute, but be safe about state
+        grad = self.flat.grad.clone()
+        rng = torch.cuda.get_rng_state(self.device)
+        before = ops._lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        if self.world == 1 or self.nccl_in_graph:
+            self._collectives = self.world > 1
+            with self._graph_ctx(self.graph):
+                self._step()
+            self.state.pool = self.graph.pool()
+        else:
+            with self._graph_ctx(self.graph):
+                self._compute()
+            self.state.pool = self.graph.pool()
+            self.graph_update = torch.cuda.CUDAGraph()
+            with self._graph_ctx(self.graph_update):
+                self._update(1.0 / self.world)
+        self._collectives = False
+        self.kernel_launches = ops._lib.launch_count() - before
+        for t, t0 in zip(self.state.tensors(), snap):
+            t.copy_(t0)
+        self.flat.grad.copy_(grad)
+        torch.cuda.set_rng_state(rng, self.device)
+        torch.cuda.synchronize()
+
+    def capture_micro(self) -> None:
+        """Graph of a gradient-accumulation micro-step: compute only, gradients keep accumulating in the flat buffer."""
+        if self.graph is None:
+            self.capture()
+        snap = [t.clone() for t in self.state.tensors()]
+        grad = self.flat.grad.clone()
+        rng = torch.cuda.get_rng_state(self.device)
+        self.graph_micro = torch.cuda.CUDAGraph()
+        with self._graph_ctx(self.graph_micro):
+            self._compute()
+        for t, t0 in zip(self.state.tensors(), snap):
+            t.copy_(t0)
+        self.flat.grad.copy_(grad)
+        torch.cuda.set_rng_state(rng, self.device)
+        torch.cuda.synchronize()
+
+    def run(self, sync: bool = True) -> torch.Tensor:
+        """sync=False: a micro-step of gradient accumulation -- no exchange, no update (`no_sync` of the reference)."""
         if self.use_graph:
             if self.graph is None:
                 self.capture()
-            self.graph.replay()
-            if self.world > 1:
+            if not sync:
+                if self.graph_micro is None:
+                    self.capture_micro()
+                self.graph_micro.replay()
+            elif self.graph_update is None:
+                self.graph.replay()
+            else:
+                self.graph.replay()
+                self._collectives = True
                 self._exchange()
+                self._collectives = False
                 self.graph_update.replay()
         else:
             before = ops._lib.launch_count()
-            self._step()
+            self._collectives = self.world > 1 and sync
+            try:
+                self._step(sync)
+            finally:
+                self._collectives = False
             self.kernel_launches = ops._lib.launch_count() - before
         return self.loss
+
+
+class _Staged:
+    """One staging slot of the input pipeline: device copies of a host batch made on the copy stream."""
+    __slots__ = ("image", "class_ids", "attention_mask", "ready", "free", "key")
+
+    def __init__(self, step: "JiTQLoRATrainStep"):
+        self.image = torch.empty_like(step.image)
+        self.class_ids = torch.empty_like(step.class_ids)
+        self.attention_mask = torch.empty_like(step.attention_mask)
+        self.ready = torch.cuda.Event()
+        self.free = torch.cuda.Event()
+        self.key = None
 
 
 class JiTQLoRATrainer:
@@ -329,22 +488,39 @@ class JiTQLoRATrainer:
 
     One `JiTQLoRATrainStep` (= one CUDA graph) per (batch, H, W) bucket, created on first use; all of them share the
     LoRA parameters, gradients, AdamW state and graph memory pool of one `TrainState`.  `train_step` takes the host
-    batch exactly as the reference's dataloader yields it (image fp16 [B,3,H,W], class ids, mask), copies it to the
-    bucket's static buffers asynchronously and replays the graph; the returned loss is a device scalar (no sync).
+    batch exactly as the reference's dataloader yields it (image fp16 [B,3,H,W], class ids, mask) and replays the graph.
+
+    Input pipeline: `train_step(batch, prefetch=next_batch)` starts the NEXT batch's host-to-device copy on a copy stream
+    into one of two staging slots of its bucket while this step computes; the step then only pays a device-to-device copy
+    of its own (already resident) batch into the graph's input buffers.  The graph itself is untouched, so a prefetched
+    run is bit-identical to a plain one.  The loss is returned as a device scalar (no sync); `read_loss()` gives the
+    loss of a finished earlier step from pinned host memory without stalling the current one.
 
     Checkpoints: the adapter as safetensors with the reference's key names (`get_adapter_parameters`,
     src/modules/peft/functional.py:114-125: `<path>.lora_down.weight`, `<path>.lora_up.weight`, `<path>.alpha`) and the
     optimiser state (moments by the same names + the step counter) beside it, so a run resumes bit-exactly."""
 
     def __init__(self, model: Denoiser, num_classes: int = 1000, max_token_length: int = 64,
-                 hp: TrainHParams | None = None, process_group=None, use_graph: bool = True, seed: int = 0):
+                 hp: TrainHParams | None = None, process_group=None, use_graph: bool = True, seed: int = 0,
+                 nccl_in_graph: bool | None = None, overlap_chunks: int | None = None):
         self.model = model
         self.num_classes, self.max_token_length = num_classes, max_token_length
         self.hp = hp or TrainHParams()
         self.group = process_group
         self.use_graph = use_graph
+        self.nccl_in_graph, self.overlap_chunks = nccl_in_graph, overlap_chunks
         self.state = TrainState(model, num_classes)
+        self.device = next(model.parameters()).device
+        init_communicator(process_group, self.device)
         self.buckets: dict[tuple[int, int, int], JiTQLoRATrainStep] = {}
+        self._staging: dict[tuple[int, int, int], list[_Staged]] = {}
+        self._stage_turn = 0
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._micro = 0
+        # losses of the last steps in pinned host memory (ring), each guarded by an event
+        self._loss_ring = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._loss_events = [torch.cuda.Event() for _ in range(8)]
+        self._steps_run = 0
         torch.manual_seed(seed)
 
     def bucket(self, batch: int, height: int, width: int) -> JiTQLoRATrainStep:
@@ -352,21 +528,100 @@ class JiTQLoRATrainer:
         step = self.buckets.get(key)
         if step is None:
             step = JiTQLoRATrainStep(self.model, batch, height, width, self.num_classes, self.max_token_length, self.hp,
-                                     self.group, self.use_graph, seed=None, state=self.state)
+                                     self.group, self.use_graph, seed=None, state=self.state,
+                                     nccl_in_graph=self.nccl_in_graph, overlap_chunks=self.overlap_chunks)
             self.buckets[key] = step
         return step
 
-    def train_step(self, image: torch.Tensor, class_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    def precapture(self, shapes) -> None:
+        """Capture the graphs of the given (batch, H, W) buckets up front (optional: buckets are captured lazily, and
+        since no warm-up or capture issues a collective, ranks need not do it in lock-step)."""
+        for b, h, w in shapes:
+            step = self.bucket(b, h, w)
+            if step.use_graph and step.graph is None:
+                step.capture()
+
+    @staticmethod
+    def _check_host_mask(attention_mask: torch.Tensor) -> None:
+        if attention_mask.is_cuda:
+            return                                   # device masks are checked by prefix_key_lengths (device-side assert)
+        from .modules.attention import prefix_key_lengths
+        prefix_key_lengths(attention_mask)           # raises for float / non-prefix masks
+
+    def prefetch(self, image: torch.Tensor, class_ids: torch.Tensor, attention_mask: torch.Tensor) -> None:
+        """Start the host-to-device copy of a FUTURE step's batch on the copy stream (pinned host tensors)."""
+        self._check_host_mask(attention_mask)
+        B, _, H, W = image.shape
+        key = (B, H, W)
+        step = self.bucket(B, H, W)
+        slots = self._staging.setdefault(key, [])
+        slot = next((sl for sl in slots if sl.key is None), None)       # a slot whose batch has been consumed
+        if slot is None:
+            if len(slots) < 2:
+                slots.append(_Staged(step))
+                slot = slots[-1]
+            else:                                                        # more than two batches ahead: replace the older
+                slot = slots[self._stage_turn % 2]
+                self._stage_turn += 1
+        cs = self._copy_stream
+        cs.wait_event(slot.free)                     # the step that last read this slot has copied it out
+        with torch.cuda.stream(cs):
+            slot.image.copy_(image, non_blocking=True)
+            slot.class_ids.copy_(class_ids, non_blocking=True)
+            slot.attention_mask.copy_(attention_mask, non_blocking=True)
+            slot.ready.record(cs)
+        slot.key = (id(image), id(class_ids), id(attention_mask))
+
+    def _staged_for(self, key, image, class_ids, attention_mask) -> _Staged | None:
+        want = (id(image), id(class_ids), id(attention_mask))
+        for slot in self._staging.get(key, ()):
+            if slot.key == want:
+                return slot
+        return None
+
+    def train_step(self, image: torch.Tensor, class_ids: torch.Tensor, attention_mask: torch.Tensor,
+                   prefetch: tuple | None = None) -> torch.Tensor:
         B, _, H, W = image.shape
         if self.state.eval_mode:
             raise RuntimeError("train_step in eval mode: call trainer.train() first (schedule-free optimiser)")
         step = self.bucket(B, H, W)
         if step.use_graph and step.graph is None:
             step.capture()                       # before the copies: warm-up must not consume this batch's buffers
-        step.image.copy_(image, non_blocking=True)
-        step.class_ids.copy_(class_ids, non_blocking=True)
-        step.attention_mask.copy_(attention_mask, non_blocking=True)
-        return step.run()
+        main = torch.cuda.current_stream(self.device)
+        slot = self._staged_for((B, H, W), image, class_ids, attention_mask)
+        if slot is not None:
+            main.wait_event(slot.ready)
+            step.image.copy_(slot.image, non_blocking=True)
+            step.class_ids.copy_(slot.class_ids, non_blocking=True)
+            step.attention_mask.copy_(slot.attention_mask, non_blocking=True)
+            slot.free.record(main)
+            slot.key = None
+        else:
+            self._check_host_mask(attention_mask)
+            step.image.copy_(image, non_blocking=True)
+            step.class_ids.copy_(class_ids, non_blocking=True)
+            step.attention_mask.copy_(attention_mask, non_blocking=True)
+        if prefetch is not None:
+            self.prefetch(*prefetch)
+        accum = max(1, self.hp.grad_accum_steps)
+        self._micro += 1
+        sync = self._micro % accum == 0
+        loss = step.run(sync=sync)
+        i = self._steps_run % 8
+        self._loss_ring[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self._loss_events[i].record(main)
+        self._steps_run += 1
+        return loss
+
+    def read_loss(self, steps_back: int = 1) -> float:
+        """Loss of the step `steps_back` calls ago (1 = the previous call's ... 0 = the call just made, which waits for
+        it), read from pinned host memory after its own event: reading an older step never stalls the running one."""
+        n = self._steps_run - 1 - steps_back
+        if n < 0 or steps_back >= 8:
+            raise IndexError("no such step in the loss ring")
+        i = n % 8
+        self._loss_events[i].synchronize()
+        return float(self._loss_ring[i])
 
     @property
     def global_step(self) -> int:
