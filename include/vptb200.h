@@ -93,6 +93,17 @@ typedef struct {
   int64_t ld_side;             /* row pitch of `side` in elements */
   int32_t reuse_scratch;       /* non-zero: w_scratch already holds this weight in this direction's layout (the previous
                                 * call on the stream used the same weight and direction): skip the dequantisation */
+  /* ABI 5: SwiGLU (src/models/jit/denoiser.py:498-506 and its autograd) fused into the epilogue of the large-M route.
+   *   epilogue = 0  out = in W^T + b (+ residual)                                                       (every linear)
+   *   epilogue = 1  forward call of w_2:  residual = g = w_1(x) [M,N];  out2 = u = w_2(x) + b,  out = silu(g) * u
+   *   epilogue = 2  backward call of w_3: residual = g, in2 = u [M,K];  with da = dy W:  out = dg = da u silu'(g),
+   *                 out2 = du = da silu(g)      (da itself is not written)
+   * Modes 1 and 2 need w_scratch (the CTA-pair kernel); rounding points are those of the unfused kernels. */
+  int32_t epilogue;
+  const void* in2;             /* [M, n_out] bf16, pitch ld_in2 (mode 2) */
+  int64_t ld_in2;
+  void* out2;                  /* [M, n_out] bf16, pitch ld_out2 (modes 1, 2) */
+  int64_t ld_out2;
 } vpt_linear_args;
 
 int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K);

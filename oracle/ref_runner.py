@@ -14,6 +14,7 @@ in forward AND in backward, oracle/nf4.py, plain torch ops on whatever device th
 """
 from __future__ import annotations
 
+import re
 import time
 from types import SimpleNamespace
 
@@ -69,6 +70,22 @@ class RestatedLinear4bit(nn.Linear):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return _MatMul4Bit.apply(x, self.state, self.bias)
+
+
+_WRAPPED = re.compile(r"^(blocks\.\d+\.(?:attn|mlp)\.\w+)\.linear\.(weight|bias)$")
+
+
+def plain_state_dict(lora_wrapped_state: dict) -> dict:
+    """State dict of a LoRA-wrapped, NF4-quantised model (ours or the reference's) -> the keys of the plain Denoiser:
+    `blocks.N.attn.to_q.linear.bias` -> `blocks.N.attn.to_q.bias`; adapter tensors, packed NF4 weights and their statistics
+    are dropped (the block weights are installed from Nf4State objects)."""
+    out = {}
+    for k, v in lora_wrapped_state.items():
+        if ".lora_" in k or k.endswith(".alpha") or ".weight." in k or v.dtype == torch.uint8:
+            continue
+        m = _WRAPPED.match(k)
+        out[f"{m.group(1)}.{m.group(2)}" if m else k] = v.detach().float().cpu()
+    return out
 
 
 def state_to(st: on.Nf4State, device) -> on.Nf4State:

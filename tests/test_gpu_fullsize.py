@@ -78,8 +78,7 @@ def _ours(net, inp, clean):
 
 def _reference_bf16(net, states, model_name, inp, clean):
     from oracle import ref_runner
-    sd = {k.replace(".linear.", "."): v.detach().float().cpu() for k, v in net.state_dict().items()
-          if ".lora_" not in k and not k.endswith(".alpha") and ".weight." not in k and v.dtype != torch.uint8}
+    sd = ref_runner.plain_state_dict(net.state_dict())
     paths = {k[:-len(".linear")]: v for k, v in states.items()}
     ref, _ = ref_runner.build_reference_jit(net.config.model_dump(), rank=16, alpha=16.0, device="cuda", dtype=torch.bfloat16,
                                             nf4_states=paths, state_dict=sd)
@@ -183,7 +182,8 @@ def test_gradient_checkpointing_gives_the_same_step():
     p1, l1, g1 = _ours(net, inp, clean)
     net.set_gradient_checkpointing(True)
     p2, l2, g2 = _ours(net, inp, clean)
-    assert torch.equal(p0, p1) and torch.equal(p0, p2) and l0 == l2
+    assert torch.equal(p0, p1) and torch.equal(p0, p2)
+    assert abs(l0 - l2) <= 1e-6 * abs(l0)              # the loss is an fp32 atomic sum over CTAs: last-bit run-to-run noise
     noise = max(_rel(g1[n], g0[n]) for n in g0)
     diff = max(_rel(g2[n], g0[n]) for n in g0)
     exact = sum(1 for n in g0 if torch.equal(g2[n], g0[n]))

@@ -216,3 +216,46 @@ def test_frozen_bf16_linear_with_ragged_in_features(M, K, N):
     assert rel_err(y, yr) <= TOL and rel_err(x.grad, xr.grad) <= TOL
     pw = ops.padded_weight(w)
     assert pw.shape == (N, K) and pw.stride(0) % 8 == 0 and torch.equal(pw, w) and ops.padded_weight(w) is pw   # cached
+
+
+@pytest.mark.parametrize("M,D,F", [(2640, 768, 2048), (1320, 1024, 2730), (1100, 1280, 3413), (21120, 768, 2048)])
+def test_swiglu_epilogues_equal_the_separate_kernels(M, D, F):
+    """SwiGLU forward fused into the w_2 GEMM's epilogue and SwiGLU backward fused into the w_3 dX GEMM's epilogue (CTA-pair
+    route, include/vptb200.h epilogue = 1 / 2; reference SwiGLU.forward, jit/denoiser.py:498-506) against the same GEMMs
+    followed by the stand-alone swiglu kernels, and against the fp32 oracle formula.  Ragged F (JiT-L 2730, JiT-H 3413)."""
+    from vision_pt_b200 import ops
+    _, _, _ = _make(8, 64, 64, 16, True, True)          # library loaded
+    g_ = torch.Generator().manual_seed(M + F)
+    rnd = lambda *s, std=1.0: (torch.randn(*s, generator=g_) * std).to(torch.bfloat16)
+    code = torch.tensor(on.NF4_CODE.copy())
+    ncode = torch.from_numpy(on.dynamic_map_signed8().copy())
+    w2 = ops.nf4_quantize(rnd(F, D, std=0.05).cuda(), ncode, code)
+    w3 = ops.nf4_quantize(rnd(D, F, std=0.05).cuda(), ncode, code)
+    b2 = rnd(F, std=0.5).cuda()
+    down2, up2 = rnd(16, D, std=0.05).cuda(), rnd(F, 16, std=0.05).cuda()
+    down3, up3 = rnd(16, F, std=0.05)[:, :F].cuda(), rnd(D, 16, std=0.05).cuda()
+    down3 = ops._pad_rank(down3, up3)[0]
+    h, g = rnd(M, D).cuda(), ops._rows(rnd(M, F).cuda())
+    dy = rnd(M, D).cuda()
+    slots_f = ops.dequant_block([w2, w3], [down2, down3], [up2, up3], transposed=False)
+    # ---- forward: u = w_2(h), a = silu(g) * u
+    u_ref, _ = ops.linear_raw(h, w2, b2, down2, up2, 0.5, want_side=True, scratch=slots_f[0])
+    a_ref = ops.swiglu_fwd_raw(g, u_ref)
+    a, u, side = ops.linear_raw(h, w2, b2, down2, up2, 0.5, g, want_side=True, scratch=slots_f[0], epilogue=1)
+    assert torch.equal(u, u_ref) and side is not None
+    gf, uf = g.float(), u_ref.float()
+    a_oracle = oj.swiglu_gate(gf, uf)
+    assert rel_err(a, a_oracle) <= 1e-2 and rel_err(a, a_ref) <= 8e-3      # one bf16 ulp at most (approximate divide)
+    assert float((a != a_ref).float().mean()) < 2e-3
+    # ---- backward: da = dy W_3, (dg, du) = swiglu'(da, g, u)
+    slots_b = ops.dequant_block([w2, w3], [down2, down3], [up2, up3], transposed=True)
+    da_ref, dside_ref = ops.linear_raw(dy, w3, None, down3, up3, 0.5, want_side=True, backward=True, scratch=slots_b[1])
+    dg_ref, du_ref = ops.swiglu_bwd_raw(da_ref, g, u_ref)
+    dg, du, dside = ops.linear_raw(dy, w3, None, down3, up3, 0.5, g, want_side=True, backward=True, scratch=slots_b[1],
+                                   epilogue=2, in2=u_ref)
+    assert torch.equal(dside[:, :M], dside_ref[:, :M])
+    daf = da_ref.float()
+    sg = torch.sigmoid(gf)
+    assert rel_err(du, daf * gf * sg) <= 1e-2 and rel_err(dg, daf * uf * (sg * (1 + gf * (1 - sg)))) <= 1e-2
+    assert rel_err(du, du_ref) <= 8e-3 and rel_err(dg, dg_ref) <= 8e-3
+    assert float((du != du_ref).float().mean()) < 2e-3 and float((dg != dg_ref).float().mean()) < 2e-3

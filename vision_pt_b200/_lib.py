@@ -24,6 +24,7 @@ class LinearArgsC(C.Structure):
         ("ld_lora_down", C.c_int64), ("lora_up", C.c_void_p), ("scale", C.c_float), ("inp", C.c_void_p), ("ld_in", C.c_int64), ("out", C.c_void_p),
         ("ld_out", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64), ("side", C.c_void_p), ("M", C.c_int32),
         ("tile_n", C.c_int32), ("w_scratch", C.c_void_p), ("ld_scratch", C.c_int64), ("scratch_bytes", C.c_int64), ("ld_side", C.c_int64), ("reuse_scratch", C.c_int32),
+        ("epilogue", C.c_int32), ("in2", C.c_void_p), ("ld_in2", C.c_int64), ("out2", C.c_void_p), ("ld_out2", C.c_int64),
     ]
 
 

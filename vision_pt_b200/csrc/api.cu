@@ -22,7 +22,7 @@ static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
 }
 
 extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
-extern "C" int vpt_abi_version(void) { return 4; }
+extern "C" int vpt_abi_version(void) { return 5; }
 
 // ---------------------------------------------------------------------------------------------------- NF4
 extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
@@ -144,6 +144,14 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     g.p.scale = a->scale;
     g.p.side = static_cast<__nv_bfloat16*>(a->side);
     g.p.ld_side = static_cast<long>(a->ld_side);
+    g.epi = a->epilogue;
+    g.out2 = a->out2; g.ldd2 = static_cast<int>(a->ld_out2);
+    g.in2 = a->in2; g.ldr2 = static_cast<int>(a->ld_in2);
+    if (a->epilogue != 0) {
+      VPT_REQUIRE((a->epilogue == 1 && !bwd) || (a->epilogue == 2 && bwd), "vpt_nf4lora_linear: epilogue 1 is a forward mode, 2 a backward mode");
+      VPT_REQUIRE(a->residual && a->out2 && a->ld_out2 % 8 == 0 && a->ld_res % 8 == 0 && (a->epilogue == 1 || (a->in2 && a->ld_in2 % 8 == 0)),
+                  "vpt_nf4lora_linear: fused SwiGLU epilogue needs residual (g), out2 (and in2 = u in mode 2) with pitches that are multiples of 8");
+    }
     if (via_scratch) {
       VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
       VPT_REQUIRE((reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0 && a->scratch_bytes >= vpt_linear_scratch_bytes(N, K),
@@ -180,6 +188,7 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     }
     return launch_pair(g, stream);
   }
+  VPT_REQUIRE(a->epilogue == 0, "vpt_nf4lora_linear: the fused SwiGLU epilogues exist on the large-M (w_scratch) route only");
   const void* w_dense = a->w_bf16;
   long ldw = a->w_bf16 != nullptr ? ld_wb : 0;
   if (via_scratch) {

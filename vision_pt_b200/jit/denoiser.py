@@ -232,10 +232,10 @@ class JiTBlockFn(torch.autograd.Function):
         slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=False) \
             if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue" else None
 
-        def lin(i, inp, residual=None):
+        def lin(i, inp, residual=None, epilogue=0):
             l = lins[i]
             return ops.linear_raw(inp, l.w, l.bias, pads[i][0], pads[i][1], l.scale, residual, want_side=True,
-                                  scratch=slots[i] if slots is not None else None)
+                                  scratch=slots[i] if slots is not None else None, epilogue=epilogue)
 
         h1, rstd1 = ops.rmsnorm_fwd_raw(x2, n1w, eps)
         q_pre, t_q = lin(0, h1)
@@ -250,8 +250,11 @@ class JiTBlockFn(torch.autograd.Function):
         x1, t_o = lin(3, o2, x2)
         h2, rstd2 = ops.rmsnorm_fwd_raw(x1, n2w, eps)
         g, t_g = lin(4, h2)
-        u, t_u = lin(5, h2)
-        a = ops.swiglu_fwd_raw(g, u)
+        if slots is not None and ops.FUSE_SWIGLU:
+            a, u, t_u = lin(5, h2, g, epilogue=1)        # silu(g) * u in the w_2 GEMM's epilogue
+        else:
+            u, t_u = lin(5, h2)
+            a = ops.swiglu_fwd_raw(g, u)
         y, t_3 = lin(6, a, x1)
 
         ctx.spec, ctx.pads, ctx.dims = spec, pads, (B, L, D)
@@ -283,10 +286,10 @@ class JiTBlockFn(torch.autograd.Function):
         slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=True) \
             if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue" else None
 
-        def back(i, dout, residual=None):
+        def back(i, dout, residual=None, epilogue=0, in2=None):
             l = lins[i]
             return ops.linear_raw(dout, l.w, None, pads[i][0], pads[i][1], l.scale, residual, want_side=True, backward=True,
-                                  scratch=slots[i] if slots is not None else None)
+                                  scratch=slots[i] if slots is not None else None, epilogue=epilogue, in2=in2)
 
         # LoRA parameter gradients: collected over the block and reduced by ONE batched launch at the end; linears that
         # share their input (q/k/v <- h1, w_1/w_2 <- h2) form one item so the activation is read once
@@ -314,9 +317,12 @@ class JiTBlockFn(torch.autograd.Function):
             grp[2].append(ops.grad_sink(l.down))
 
         # MLP branch
-        da, dt_3 = back(6, dy2)
+        if slots is not None and ops.FUSE_SWIGLU:
+            dg, du, dt_3 = back(6, dy2, g, epilogue=2, in2=u)   # the SwiGLU backward in the w_3 dX GEMM's epilogue
+        else:
+            da, dt_3 = back(6, dy2)
+            dg, du = ops.swiglu_bwd_raw(da, g, u)
         lora_grads(6, dy2, t_3, a, dt_3)
-        dg, du = ops.swiglu_bwd_raw(da, g, u)
         dh2, dt_g = back(4, dg)
         dh2, dt_u = back(5, du, dh2)
         lora_grads(4, dg, t_g, h2, dt_g)
@@ -498,7 +504,8 @@ class JiT(nn.Module):
         # key-padding mask -> per-sample key length (valid context tokens come first, reference class_encoder.py:72-81)
         # -- a PREFIX mask: anything else is refused by prefix_key_lengths, not silently treated as one)
         if context_mask is not None:
-            seq_ctx = (pre_ctx + prefix_key_lengths(context_mask.to(image.device))).contiguous()
+            # JiT's own mask convention is "1: attend, 0: ignore" in any dtype (reference denoiser.py:375-381: mask.bool())
+            seq_ctx = (pre_ctx + prefix_key_lengths(context_mask.to(image.device) != 0)).contiguous()
         else:
             seq_ctx = None
 

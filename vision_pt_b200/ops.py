@@ -5,6 +5,7 @@ PyTorch only owns memory and streams here; every computation is a kernel of libv
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -20,6 +21,9 @@ RANK = 16  # LoRA rank of the fused kernels; smaller ranks are zero-padded
 #   "auto"     : scratch when M >= NF4_SCRATCH_MIN_M
 NF4_GEMM_MODE = "auto"
 NF4_SCRATCH_MIN_M = 1024
+# SwiGLU forward / backward in the epilogues of the w_2 / w_3-backward GEMMs of the fused block (large-M route); off =
+# separate swiglu_fwd / swiglu_bwd kernels (A/B measurements, VPT_FUSE_SWIGLU=0)
+FUSE_SWIGLU = os.environ.get("VPT_FUSE_SWIGLU", "1") != "0"
 _SCRATCH: dict[tuple, torch.Tensor] = {}
 
 
@@ -220,9 +224,11 @@ def _pad_rank(down: torch.Tensor | None, up: torch.Tensor | None):
 
 def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, scale: float, residual=None,
                want_side: bool = False, backward: bool = False, tile_n: int = 0, reuse_scratch: bool = False,
-               scratch: torch.Tensor | None = None):
+               scratch: torch.Tensor | None = None, epilogue: int = 0, in2: torch.Tensor | None = None):
     """One call of the fused linear.  forward: x2 [M,K] -> y [M,N]; backward: x2 = dy [M,N] -> dx [M,K].
-    `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None).
+    `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None) -- or (out, out2, side) with a
+    fused SwiGLU epilogue (include/vptb200.h): epilogue=1 (forward of w_2, residual = g) gives (a, u, side), epilogue=2
+    (backward of w_3, residual = g, in2 = u) gives (dg, du, side).
     reuse_scratch: the previous call on this stream used the same weight and direction, so the dequantised copy in the
     workspace is still valid and the dequantisation kernel is skipped.  scratch: a slot filled by dequant_block for this
     weight and direction (implies reuse)."""
@@ -277,6 +283,16 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     args.ld_side = ld_side
     args.M = M
     args.tile_n = tile_n
+    out2 = None
+    if epilogue:
+        if scratch is None or residual is None or (epilogue == 2 and in2 is None):
+            raise ValueError("fused SwiGLU epilogue: needs the scratch (CTA-pair) route, residual = g and, in mode 2, in2 = u")
+        out2_full = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x2.device)
+        out2 = out2_full[:, :n_out] if ld_out != n_out else out2_full
+        args.epilogue = int(epilogue)
+        args.out2, args.ld_out2 = _p(out2_full), ld_out
+        if in2 is not None:
+            args.in2, args.ld_in2 = _p(in2), in2.stride(0) if M > 1 else n_out
     timer = GEMM_TIMER
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,7 +307,10 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
         timer.append({"kind": "gemm", "e0": e0, "e1": e1, "flops": flops, "M": M, "K": K, "N": N, "bwd": backward, "lora": lora,
                       "nf4": isinstance(w, Nf4Tensors), "scratch": scratch is not None,
                       "scratch_ptr": scratch.data_ptr() if prefilled else None,
-                      "call": (x2.shape, x2.stride(0), w, bias, down, up, scale, residual is not None, want_side, backward)})
+                      "call": (x2.shape, x2.stride(0), w, bias, down, up, scale, residual is not None, want_side, backward),
+                      "epilogue": int(epilogue)})
+    if epilogue:
+        return out, out2, side
     return out, side
 
 
