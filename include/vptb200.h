@@ -208,6 +208,43 @@ int vpt_unpatchify(const void* patches, void* img, int32_t B, int32_t C, int32_t
 int vpt_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t rows, int64_t row_bytes,
                   vpt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ other block families
+ * The blocks either side of the JiT block that share its linears / attention.  bf16 tensors,
+ * fp32 arithmetic, the reference's bf16 rounding points.
+ *
+ * vpt_layernorm_*: nn.LayerNorm / FP32LayerNorm WITH affine parameters (src/models/sdxl/denoiser.py:248-250,
+ *   src/modules/norm.py:9-17): y = bf16((x - mean) rstd w + b); w / b may be NULL; mean / rstd [rows] fp32 are saved for the
+ *   backward, which gives dx and (optionally, fp32 [D], accumulated) dw / db.
+ * vpt_gated_act_*: a = bf16(bf16(act(gate)) h) and its backward; kind 0 = SiLU (SwiGLU), 1 = GELU erf (GeGLU,
+ *   src/models/sdxl/denoiser.py:175-186: h, gate = the two halves of one projection, hence the row pitches), 2 = GELU tanh.
+ * vpt_act_*: y = bf16(act(x)), dx = dy act'(x) over n contiguous elements (CogView4 FeedForward,
+ *   src/models/cogview4/denoiser.py:312-343: kind 2).
+ * vpt_rope_half: apply_rotary_emb of CogView4 (src/models/cogview4/denoiser.py:203-218) on token-major [B, L, H, hd]:
+ *   tokens l >= l0 rotated by table row l - l0 (cos / sin fp32 [S, hd]), others copied; inverse != 0 is the backward.
+ * vpt_pope_*: apply_pope (src/models/jit/extension/pope.py:6-38): y[.., 2i] = softplus(x_i) cos(phi_i), y[.., 2i+1] = .. sin(phi_i),
+ *   phi = table angle (cos_sin fp32 [L, d, 2]) + learned bias (fp32 [H, d] or NULL); x [B, L, H, d] -> y [B, L, H, 2d].
+ * vpt_token_gather: TREAD routing (train/jit/class_to_image_tread.py:73-118): scatter == 0: dst[b, j] = src[b, idx[j]]
+ *   (src [B, L_full, D] -> dst [B, n, D]); scatter != 0: dst[b, idx[j]] = src[b, j] (src [B, n, D] -> dst [B, L_full, D]). */
+int vpt_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows, int32_t D,
+                      float eps, vpt_stream_t stream);
+int vpt_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, float* dw,
+                      float* db, int64_t rows, int32_t D, vpt_stream_t stream);
+int vpt_gated_act_fwd(const void* h, const void* gate, void* a, int64_t rows, int32_t F, int64_t ldh, int64_t ldg, int64_t lda,
+                      int32_t kind, vpt_stream_t stream);
+int vpt_gated_act_bwd(const void* da, const void* h, const void* gate, void* dh, void* dgate, int64_t rows, int32_t F,
+                      int64_t ldda, int64_t ldh, int64_t ldg, int64_t lddh, int64_t lddg, int32_t kind, vpt_stream_t stream);
+int vpt_act_fwd(const void* x, void* y, int64_t n, int32_t kind, vpt_stream_t stream);
+int vpt_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int32_t kind, vpt_stream_t stream);
+int vpt_rope_half(const void* x, const float* cosv, const float* sinv, void* y, int64_t tokens, int32_t L, int32_t H,
+                  int32_t head_dim, int32_t l0, int64_t ldx, int64_t ldy, int32_t inverse, vpt_stream_t stream);
+int vpt_pope_fwd(const void* x, const float* cos_sin, const float* bias, void* y, int64_t tokens, int32_t L, int32_t H, int32_t d,
+                 int64_t ldx, int64_t ldy, vpt_stream_t stream);
+int vpt_pope_bwd(const void* dy, const void* x, const float* cos_sin, const float* bias, void* dx, int64_t tokens, int32_t L,
+                 int32_t H, int32_t d, int64_t lddy, int64_t ldx, int64_t lddx, vpt_stream_t stream);
+int vpt_token_gather(const void* src, const int64_t* idx, void* dst, int32_t B, int64_t L_full, int64_t n, int32_t D,
+                     int32_t scatter, vpt_stream_t stream);
+
+
 /* ------------------------------------------------------------------------------------------------ optimiser / loss
  * accelerator.clip_grad_norm_ + optimizer.step + zero_grad (src/models/for_training.py:98-109,
  * src/trainer/common.py:382-388) over the flat LoRA buffers: param bf16 [n], grad / exp_avg / exp_avg_sq fp32 [n].

@@ -28,3 +28,10 @@ def lib_built():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.build()
+
+
+@pytest.fixture(scope="session")
+def golden_blocks():
+    """Reference-live vectors of the SDXL / CogView4 blocks and PoPE (tests/golden/make_golden_blocks.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "block_family_vectors.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)

@@ -1,0 +1,229 @@
+"""The block families either side of the JiT block on the GPU: SDXL TransformerBlock, CogView4
+adaLN TransformerBlock + FinalAdaLayerNorm, PoPE, U-JiT skip-merge block, cross-attention JiT block, TREAD routing.
+
+Every module is compared with vectors produced by the REFERENCE's own module run live (tests/golden/make_golden_blocks.py
+-> tests/golden/block_family_vectors.pt: bf16 on the CPU, LoRA rank 16 installed by the reference's PEFT entry point) --
+outputs, input gradients and every LoRA gradient -- and, with the base linears NF4-quantised at realistic widths, with the
+fp32 oracle (oracle/blocks.py, itself pinned to the same vectors in tests/test_oracle_golden.py)."""
+import pytest
+import torch
+
+from oracle import blocks as ob
+from oracle import nf4 as on
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2          # BASELINE.json north_star: block outputs and gradients, max rel err in bf16
+BF = torch.bfloat16
+
+
+def _wrap(block, keys, state=None, rank=16, alpha=8.0, nf4_keys=None):
+    from vision_pt_b200.modules.peft import LoRAConfig, PeftTargetConfig
+    from vision_pt_b200.modules.quant import quantize_inplace
+    block.to(BF).requires_grad_(False)
+    if nf4_keys:
+        quantize_inplace(block, "bnb_nf4", nf4_keys)
+    PeftTargetConfig(include_keys=keys, config=LoRAConfig(rank=rank, alpha=alpha)).replace_to_peft_layer(block)
+    if state is not None:
+        missing, unexpected = block.load_state_dict(state, strict=False)
+        assert not unexpected and not [m for m in missing if "pope_bias" not in m], (missing, unexpected)
+    block.cuda()
+    for n, p in block.named_parameters():
+        p.requires_grad_("lora_" in n and "alpha" not in n)
+    return block
+
+
+def _check(block, call, outs_ref, d_outs, d_in_ref, lora_ref, leaves):
+    outs = block(**call)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    outs = outs[:len(outs_ref)]
+    for o, r in zip(outs, outs_ref):
+        assert rel_err(o, r) <= TOL
+    torch.autograd.backward(list(outs), [d.cuda() for d in d_outs])
+    for k, r in d_in_ref.items():
+        assert rel_err(leaves[k].grad, r) <= TOL, k
+    got = {n: p.grad for n, p in block.named_parameters() if p.requires_grad}
+    assert set(got) == set(lora_ref)
+    for n, r in lora_ref.items():
+        assert rel_err(got[n], r) <= TOL, n
+
+
+def test_sdxl_transformer_block_matches_reference(golden_blocks):
+    from vision_pt_b200.sdxl import TransformerBlock
+    g = golden_blocks["sdxl_block"]
+    blk = _wrap(TransformerBlock(**g["cfg"]), ["attn1", "attn2", "ff."], g["state"])
+    x = g["inputs"]["hidden_states"].cuda().requires_grad_(True)
+    _check(blk, dict(hidden_states=x, context=g["inputs"]["context"].cuda()), g["outputs"], g["d_outputs"], g["d_inputs"],
+           g["lora_grads"], {"hidden_states": x})
+
+
+def test_cogview4_block_matches_reference(golden_blocks):
+    from vision_pt_b200.cogview4 import FinalAdaLayerNorm, TransformerBlock
+    g = golden_blocks["cogview4_block"]
+    blk = _wrap(TransformerBlock(**g["cfg"]), ["attn1", "ff"], g["state"])
+    inp = g["inputs"]
+    leaves = {k: inp[k].cuda().requires_grad_(True) for k in ("hidden_states", "encoder_hidden_states", "time_embed")}
+    rot = tuple(t.cuda() for t in inp["image_rotary_emb"])
+    _check(blk, dict(**leaves, image_rotary_emb=rot), g["outputs"], g["d_outputs"], g["d_inputs"], g["lora_grads"], leaves)
+    f = golden_blocks["cogview4_final_norm"]
+    fin = FinalAdaLayerNorm(hidden_dim=256, condition_dim=64).to(BF)
+    fin.load_state_dict(f["state"])
+    fin.cuda()
+    assert rel_err(fin(f["x"].cuda(), f["cond"].cuda()), f["y"]) <= TOL
+
+
+def test_pope_matches_reference(golden_blocks):
+    from vision_pt_b200.jit.extension import apply_pope, pope_table
+    g = golden_blocks["pope"]
+    table = pope_table(g["freqs_cis"]).cuda()
+    x = g["x"].cuda().requires_grad_(True)
+    y = apply_pope(x, table, g["bias"].cuda())
+    assert rel_err(y, g["y"]) <= 4e-3 and float((y.cpu() != g["y"]).float().mean()) < 0.02      # one bf16 ulp on a few elements
+    y.backward(g["dy"].cuda())
+    assert rel_err(x.grad, g["dx"]) <= 8e-3
+    assert rel_err(apply_pope(g["x"].cuda(), table, None), g["y_nobias"]) <= 4e-3
+
+
+def _cos_sin(freqs_cis):
+    return torch.stack([freqs_cis.real, freqs_cis.imag], dim=-1).float().contiguous().cuda()
+
+
+def test_ujit_block_matches_reference(golden_blocks):
+    from vision_pt_b200.jit.extension import UJiTBlock
+    g = golden_blocks["ujit_block"]
+    blk = _wrap(UJiTBlock(hidden_dim=128, num_heads=2, has_skip_connection=True), ["attn.", "mlp.", "skip_merge"], g["state"])
+    inp = g["inputs"]
+    leaves = {k: inp[k].cuda().requires_grad_(True) for k in ("hidden_states", "skip_hidden_states")}
+    seqlens = inp["mask"].sum(dim=1).to(torch.int32).cuda()
+    valid = inp["mask"].bool()
+    outs = blk(leaves["hidden_states"], _cos_sin(inp["rope_freqs"][0]), leaves["skip_hidden_states"], seqlens)
+    # padded (masked-out) key rows still run as queries in the reference; every row is comparable
+    assert rel_err(outs, g["outputs"][0]) <= TOL
+    outs.backward(g["d_outputs"][0].cuda())
+    for k, r in g["d_inputs"].items():
+        assert rel_err(leaves[k].grad, r) <= TOL, k
+    got = {n: p.grad for n, p in blk.named_parameters() if p.requires_grad}
+    for n, r in g["lora_grads"].items():
+        assert rel_err(got[n], r) <= TOL, n
+    assert valid.shape[1] == outs.shape[1]
+
+
+def test_cross_jit_block_matches_reference(golden_blocks):
+    from vision_pt_b200.jit.extension import CrossJiTBlock
+    g = golden_blocks["cross_jit_block"]
+    blk = _wrap(CrossJiTBlock(hidden_dim=128, num_heads=2), ["attn.", "mlp."], g["state"])
+    inp = g["inputs"]
+    leaves = {k: inp[k].cuda().requires_grad_(True) for k in ("image_hidden_states", "context_hidden_states")}
+    out, ctx_out = blk(leaves["image_hidden_states"], leaves["context_hidden_states"], _cos_sin(inp["image_rope_freqs"][0]),
+                       _cos_sin(inp["context_rope_freqs"][0]), inp["image_mask"].cuda(), inp["context_mask"].cuda())
+    assert rel_err(out, g["outputs"][0]) <= TOL and ctx_out is leaves["context_hidden_states"]
+    out.backward(g["d_outputs"][0].cuda())
+    for k, r in g["d_inputs"].items():
+        assert rel_err(leaves[k].grad, r) <= TOL, k
+    got = {n: p.grad for n, p in blk.named_parameters() if p.requires_grad}
+    for n, r in g["lora_grads"].items():
+        assert rel_err(got[n], r) <= TOL, n
+
+
+def test_tread_routing_round_trip_and_gradients():
+    """keep / route split by one permutation, blocks run on the kept tokens only, re-insertion restores the order
+    (reference train/jit/class_to_image_tread.py:73-118); gather / scatter are bit-exact row copies with exact adjoints."""
+    from vision_pt_b200.jit.extension import keep_and_route_tokens, merge_routed_tokens
+    torch.manual_seed(0)
+    B, L, D = 3, 266, 768
+    x = torch.randn(B, L, D, device="cuda").to(BF).requires_grad_(True)
+    cs = torch.randn(L, 32, 2, device="cuda")
+    mask = torch.ones(B, L, device="cuda")
+    perm = torch.randperm(L, device="cuda")
+    keep, route, kcs, rcs, kmask, rmask, inv = keep_and_route_tokens(x, cs, mask, 0.5, perm)
+    nk = int(L * 0.5)
+    rk, rr = ob.tread_split(x.detach(), perm, nk)
+    assert torch.equal(keep, rk) and torch.equal(route, rr) and torch.equal(kcs, cs[perm[:nk]]) and kmask.shape == (B, nk)
+    merged = merge_routed_tokens(keep * 2, route, inv)              # "blocks" act on the kept tokens only
+    want = ob.tread_merge(rk * 2, rr, perm)
+    assert torch.equal(merged, want)
+    dy = torch.randn_like(merged)
+    merged.backward(dy)
+    ref = x.detach().clone().requires_grad_(True)
+    k2, r2 = ob.tread_split(ref, perm, nk)
+    ob.tread_merge(k2 * 2, r2, perm).backward(dy)
+    assert torch.equal(x.grad, ref.grad)
+
+
+def _oracle_params(block):
+    P = {}
+    for name, p in block.state_dict().items():
+        if ".weight." not in name:
+            P[name] = p.detach().float().cpu()
+    for name, mod in block.named_modules():
+        qs = getattr(mod, "quant_state", None)
+        if qs is not None:
+            st = on.Nf4State(packed=qs.packed.cpu(), absmax=qs.absmax.cpu(), nested_absmax=qs.nested_absmax.cpu(),
+                             nested_code=qs.nested_code.cpu(), code=qs.code.cpu(), offset=float(qs.offset),
+                             shape=tuple(qs.shape), dtype=qs.dtype)
+            P[f"{name}.weight"] = on.dequantize_nf4(st).float()
+    return P
+
+
+def _init(block, seed):
+    torch.manual_seed(seed)
+    for n, p in block.named_parameters():
+        torch.nn.init.normal_(p, std=0.03) if p.dim() > 1 else torch.nn.init.normal_(p, mean=1.0 if ("norm" in n and "weight" in n) else 0.0, std=0.05)
+    return block
+
+
+def test_sdxl_block_nf4_qlora_at_unet_width():
+    """BASELINE.json configs[4]: the D = 640 (10 heads x 64) SDXL block, 1024 latent tokens, 77-token 2048-wide context,
+    NF4 base + LoRA rank 16 on attn1 / attn2 / ff -- output, input gradient and LoRA gradients vs the fp32 oracle."""
+    from vision_pt_b200.sdxl import TransformerBlock
+    blk = _wrap(_init(TransformerBlock(640, 10, 64, context_dim=2048), 1), ["attn1", "attn2", "ff."],
+                nf4_keys=["attn1", "attn2", "ff."], alpha=16.0)
+    for n, p in blk.named_parameters():
+        if "lora_up" in n:
+            torch.nn.init.normal_(p, std=0.02)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 1024, 640, generator=g).to(BF)
+    ctx = torch.randn(2, 77, 2048, generator=g).to(BF)
+    dy = torch.randn(2, 1024, 640, generator=g).to(BF)
+    xg = x.cuda().requires_grad_(True)
+    y = blk(xg, ctx.cuda())
+    y.backward(dy.cuda())
+    P = _oracle_params(blk)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if "lora_down" in k or "lora_up" in k}
+    P.update(leaves)
+    xr = x.float().requires_grad_(True)
+    yr = ob.sdxl_block(P, xr, ctx.float(), 10, alpha=16.0)
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= TOL and rel_err(xg.grad, xr.grad) <= TOL
+    worst = max(rel_err(p.grad, leaves[n].grad) for n, p in blk.named_parameters() if p.requires_grad)
+    assert worst <= TOL, worst
+
+
+def test_cogview4_block_nf4_qlora_at_dit_width():
+    """A CogView4-style block at D = 1024 (16 heads x 64), 1024 image + 64 text tokens, NF4 base + LoRA rank 16, adaLN
+    shift / scale / gate from a 512-wide time embedding -- vs the fp32 oracle."""
+    from vision_pt_b200.cogview4 import TransformerBlock
+    blk = _wrap(_init(TransformerBlock(1024, 16, 512), 3), ["attn1", "ff"], nf4_keys=["attn1.to_", "ff.net"], alpha=16.0)
+    for n, p in blk.named_parameters():
+        if "lora_up" in n:
+            torch.nn.init.normal_(p, std=0.02)
+    g = torch.Generator().manual_seed(4)
+    x, enc = torch.randn(2, 1024, 1024, generator=g).to(BF), torch.randn(2, 64, 1024, generator=g).to(BF)
+    te = (torch.randn(2, 512, generator=g) * 0.5).to(BF)
+    ang = torch.randn(1024, 32, generator=g) * 2.0
+    fr = torch.cat([ang, ang], dim=-1)
+    rot = (fr.cos(), fr.sin())
+    dy, de = torch.randn(2, 1024, 1024, generator=g).to(BF), torch.randn(2, 64, 1024, generator=g).to(BF)
+    xg, eg = x.cuda().requires_grad_(True), enc.cuda().requires_grad_(True)
+    y, ye = blk(xg, eg, te.cuda(), tuple(t.cuda() for t in rot))
+    torch.autograd.backward([y, ye], [dy.cuda(), de.cuda()])
+    P = _oracle_params(blk)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if "lora_down" in k or "lora_up" in k}
+    P.update(leaves)
+    xr, er = x.float().requires_grad_(True), enc.float().requires_grad_(True)
+    yr, yer = ob.cogview4_block(P, xr, er, te.float(), rot, 16, alpha=16.0)
+    torch.autograd.backward([yr, yer], [dy.float(), de.float()])
+    assert rel_err(y, yr) <= TOL and rel_err(ye, yer) <= TOL
+    assert rel_err(xg.grad, xr.grad) <= TOL and rel_err(eg.grad, er.grad) <= TOL
+    worst = max(rel_err(p.grad, leaves[n].grad) for n, p in blk.named_parameters() if p.requires_grad)
+    assert worst <= TOL, worst

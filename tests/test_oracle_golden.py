@@ -128,3 +128,62 @@ def test_nf4_state_dict_key_set():
     assert set(d) == {"absmax", "quant_map", "nested_absmax", "nested_quant_map", "quant_state.bitsandbytes__nf4"}
     back = on.Nf4State.from_dict(st.packed, d)
     assert torch.equal(on.dequantize_nf4(back), on.dequantize_nf4(st))
+
+
+# ---------------------------------------------------------------------------------------------- other block families
+def _rel(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def test_sdxl_block_oracle_matches_reference(golden_blocks):
+    """oracle/blocks.py:sdxl_block against the reference's TransformerBlock run live (bf16 on the CPU, LoRA rank 16)."""
+    from oracle import blocks as ob
+    g = golden_blocks["sdxl_block"]
+    P = {k: v.clone() for k, v in g["state"].items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if "lora_down" in k or "lora_up" in k}
+    P.update(leaves)
+    x = g["inputs"]["hidden_states"].clone().requires_grad_(True)
+    y = ob.sdxl_block(P, x, g["inputs"]["context"], g["cfg"]["num_heads"], alpha=g["alpha"])
+    assert _rel(y, g["outputs"][0]) <= 1e-2                    # same ops in the same dtype: identical up to kernel choice
+    y.backward(g["d_outputs"][0])
+    assert _rel(x.grad, g["d_inputs"]["hidden_states"]) <= 2e-2
+    for n, ref in g["lora_grads"].items():
+        assert _rel(leaves[n].grad, ref) <= 2e-2, n
+
+
+def test_cogview4_block_oracle_matches_reference(golden_blocks):
+    from oracle import blocks as ob
+    g = golden_blocks["cogview4_block"]
+    P = {k: v.clone() for k, v in g["state"].items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if "lora_down" in k or "lora_up" in k}
+    P.update(leaves)
+    inp = g["inputs"]
+    x = inp["hidden_states"].clone().requires_grad_(True)
+    e = inp["encoder_hidden_states"].clone().requires_grad_(True)
+    t = inp["time_embed"].clone().requires_grad_(True)
+    y, ye = ob.cogview4_block(P, x, e, t, inp["image_rotary_emb"], g["cfg"]["num_attention_heads"], alpha=g["alpha"])
+    assert _rel(y, g["outputs"][0]) <= 1e-2 and _rel(ye, g["outputs"][1]) <= 1e-2
+    torch.autograd.backward([y, ye], g["d_outputs"])
+    assert _rel(x.grad, g["d_inputs"]["hidden_states"]) <= 2e-2
+    assert _rel(e.grad, g["d_inputs"]["encoder_hidden_states"]) <= 2e-2
+    assert _rel(t.grad, g["d_inputs"]["time_embed"]) <= 2e-2
+    for n, ref in g["lora_grads"].items():
+        assert _rel(leaves[n].grad, ref) <= 2e-2, n
+    f = golden_blocks["cogview4_final_norm"]
+    assert _rel(ob.cogview4_final_norm(f["state"], f["x"], f["cond"]), f["y"]) <= 1e-2
+
+
+def test_pope_and_tread_oracle(golden_blocks):
+    from oracle import blocks as ob
+    g = golden_blocks["pope"]
+    x = g["x"].clone().requires_grad_(True)
+    y = ob.pope(x, g["freqs_cis"], g["bias"])
+    assert torch.equal(y, g["y"]) and torch.equal(ob.pope(g["x"], g["freqs_cis"], None), g["y_nobias"])
+    y.backward(g["dy"])
+    assert _rel(x.grad, g["dx"]) <= 1e-6
+    # TREAD: split by a permutation and re-insert = identity (reference class_to_image_tread.py:73-118 and its re-merge)
+    t = torch.randn(2, 13, 8)
+    perm = torch.randperm(13)
+    keep, route = ob.tread_split(t, perm, 5)
+    assert keep.shape[1] == 5 and route.shape[1] == 8 and torch.equal(ob.tread_merge(keep, route, perm), t)

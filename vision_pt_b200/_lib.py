@@ -70,6 +70,16 @@ SIGNATURES: dict[str, list] = {
     "vpt_patchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     "vpt_unpatchify": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     "vpt_copy_rows": [_P, _I64, _P, _I64, _I64, _I64, _P],
+    "vpt_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P],
+    "vpt_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    "vpt_gated_act_fwd": [_P, _P, _P, _I64, _I32, _I64, _I64, _I64, _I32, _P],
+    "vpt_gated_act_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _I64, _I64, _I64, _I64, _I64, _I32, _P],
+    "vpt_act_fwd": [_P, _P, _I64, _I32, _P],
+    "vpt_act_bwd": [_P, _P, _P, _I64, _I32, _P],
+    "vpt_rope_half": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I64, _I64, _I32, _P],
+    "vpt_pope_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I64, _I64, _P],
+    "vpt_pope_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I64, _I64, _I64, _P],
+    "vpt_token_gather": [_P, _P, _P, _I32, _I64, _I64, _I32, _I32, _P],
     "vpt_grad_sumsq": [_P, _I64, _F, _P, _P],
     "vpt_adamw_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _F, _P, _I32, _P],
     "vpt_radam_schedulefree_step": [_P, _P, _P, _P, _I64, _D, _D, _D, _F, _F, _D, _D, _I32, _F, _P, _F, _P, _P, _I32, _P],

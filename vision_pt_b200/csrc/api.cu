@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include "attn_launch.cuh"
+#include "blocks_ext.cuh"
 #include "elementwise.cuh"
 #include "gemm_launch.cuh"
 #include "gemm_pair_launch.cuh"
@@ -351,19 +352,25 @@ extern "C" int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void
   VPT_CUDA_OK(launch_pdl(swiglu_bwd_kernel, dim3(blocks_for(rows * (f8 / 8), 256, 148 * 32)), dim3(256), 0, S(stream), BF(da), BF(g), BF(u), BFM(dg), BFM(du), rows, F, ldda, ldg, ldu, lddg, lddu));
   return 0;
 }
+// chunks per lane of the row-per-warp LayerNorm kernels: D <= 1024, 2048, 4096
+#define VPT_LN_DISPATCH(D_, CALL) do { if ((D_) <= 1024) { CALL(4); } else if ((D_) <= 2048) { CALL(8); } else { CALL(16); } } while (0)
 extern "C" int vpt_ln_modulate_fwd(const void* x, const void* scale, const void* shift, void* y, float* mean, float* rstd,
                                    int64_t rows, int32_t L, int32_t D, float eps, vpt_stream_t stream) {
-  VPT_REQUIRE(x && scale && shift && y && rows > 0 && L > 0 && D % 8 == 0 && D <= 2048, "vpt_ln_modulate_fwd: bad arguments");
-  ln_modulate_fwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(scale), BF(shift), BFM(y), mean, rstd, rows, L, D, eps);
+  VPT_REQUIRE(x && scale && shift && y && rows > 0 && L > 0 && D % 8 == 0 && D <= 4096, "vpt_ln_modulate_fwd: bad arguments");
+#define VPT_CALL(CH) ln_modulate_fwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(scale), BF(shift), BFM(y), mean, rstd, rows, L, D, eps)
+  VPT_LN_DISPATCH(D, VPT_CALL);
+#undef VPT_CALL
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }
 extern "C" int vpt_ln_modulate_bwd(const void* dy, const void* x, const void* scale, const float* mean, const float* rstd,
                                    void* dx, float* dscale, float* dshift, int64_t rows, int32_t L, int32_t D,
                                    vpt_stream_t stream) {
-  VPT_REQUIRE(dy && x && scale && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 2048, "vpt_ln_modulate_bwd: bad arguments");
+  VPT_REQUIRE(dy && x && scale && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 4096, "vpt_ln_modulate_bwd: bad arguments");
   VPT_REQUIRE((dscale == nullptr) == (dshift == nullptr), "vpt_ln_modulate_bwd: dscale and dshift go together");
-  ln_modulate_bwd_kernel<<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(scale), mean, rstd, BFM(dx), dscale, dshift, rows, L, D);
+#define VPT_CALL(CH) ln_modulate_bwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(scale), mean, rstd, BFM(dx), dscale, dshift, rows, L, D)
+  VPT_LN_DISPATCH(D, VPT_CALL);
+#undef VPT_CALL
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -381,6 +388,90 @@ extern "C" int vpt_gate_residual_bwd(const void* dy, const void* h, const void* 
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }
+// ---- block families either side of the JiT block (SDXL, CogView4, JiT extensions): blocks_ext.cuh
+extern "C" int vpt_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows,
+                                 int32_t D, float eps, vpt_stream_t stream) {
+  VPT_REQUIRE(x && y && rows > 0 && D > 0 && D % 8 == 0 && D <= 4096 && ((mean == nullptr) == (rstd == nullptr)), "vpt_layernorm_fwd: bad arguments");
+#define VPT_CALL(CH) layernorm_fwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(w), BF(b), BFM(y), mean, rstd, rows, D, eps)
+  VPT_LN_DISPATCH(D, VPT_CALL);
+#undef VPT_CALL
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                                 float* dw, float* db, int64_t rows, int32_t D, vpt_stream_t stream) {
+  VPT_REQUIRE(dy && x && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 4096, "vpt_layernorm_bwd: bad arguments");
+#define VPT_CALL(CH) layernorm_bwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(w), mean, rstd, BFM(dx), dw, db, rows, D)
+  VPT_LN_DISPATCH(D, VPT_CALL);
+#undef VPT_CALL
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_gated_act_fwd(const void* h, const void* gate, void* a, int64_t rows, int32_t F, int64_t ldh, int64_t ldg,
+                                 int64_t lda, int32_t kind, vpt_stream_t stream) {
+  const int64_t f8 = (F + 7) / 8 * 8;
+  VPT_REQUIRE(h && gate && a && rows > 0 && F > 0 && kind >= 0 && kind <= 2 && (ldh | ldg | lda) % 8 == 0 && ldh >= f8 && ldg >= f8 && lda >= f8,
+              "vpt_gated_act_fwd: bad arguments (row pitches must be multiples of 8 and cover F rounded up to 8)");
+  VPT_REQUIRE(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(a)) & 15) == 0, "vpt_gated_act_fwd: 16-byte alignment");
+  gated_act_fwd_kernel<<<blocks_for(rows * (f8 / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(h), BF(gate), BFM(a), rows, F, ldh, ldg, lda, kind);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_gated_act_bwd(const void* da, const void* h, const void* gate, void* dh, void* dgate, int64_t rows, int32_t F,
+                                 int64_t ldda, int64_t ldh, int64_t ldg, int64_t lddh, int64_t lddg, int32_t kind, vpt_stream_t stream) {
+  const int64_t f8 = (F + 7) / 8 * 8;
+  VPT_REQUIRE(da && h && gate && dh && dgate && rows > 0 && F > 0 && kind >= 0 && kind <= 2 && (ldda | ldh | ldg | lddh | lddg) % 8 == 0 &&
+                  ldda >= f8 && ldh >= f8 && ldg >= f8 && lddh >= f8 && lddg >= f8, "vpt_gated_act_bwd: bad arguments");
+  VPT_REQUIRE(((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(dh) |
+                reinterpret_cast<uintptr_t>(dgate)) & 15) == 0, "vpt_gated_act_bwd: 16-byte alignment");
+  gated_act_bwd_kernel<<<blocks_for(rows * (f8 / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(da), BF(h), BF(gate), BFM(dh), BFM(dgate), rows, F, ldda, ldh, ldg, lddh, lddg, kind);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_act_fwd(const void* x, void* y, int64_t n, int32_t kind, vpt_stream_t stream) {
+  VPT_REQUIRE(x && y && n > 0 && n % 8 == 0 && kind >= 0 && kind <= 2, "vpt_act_fwd: bad arguments (n must be a multiple of 8)");
+  act_fwd_kernel<<<blocks_for(n / 8, 256, 148 * 32), 256, 0, S(stream)>>>(BF(x), BFM(y), n / 8, kind);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int32_t kind, vpt_stream_t stream) {
+  VPT_REQUIRE(dy && x && dx && n > 0 && n % 8 == 0 && kind >= 0 && kind <= 2, "vpt_act_bwd: bad arguments");
+  act_bwd_kernel<<<blocks_for(n / 8, 256, 148 * 32), 256, 0, S(stream)>>>(BF(dy), BF(x), BFM(dx), n / 8, kind);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_rope_half(const void* x, const float* cosv, const float* sinv, void* y, int64_t tokens, int32_t L, int32_t H,
+                             int32_t head_dim, int32_t l0, int64_t ldx, int64_t ldy, int32_t inverse, vpt_stream_t stream) {
+  VPT_REQUIRE(x && cosv && sinv && y && tokens > 0 && L > 0 && H > 0 && head_dim % 16 == 0 && l0 >= 0 && ldx % 8 == 0 && ldy % 8 == 0,
+              "vpt_rope_half: bad arguments (head_dim must be a multiple of 16)");
+  rope_half_kernel<<<blocks_for(tokens * H * (head_dim / 16), 256, 148 * 32), 256, 0, S(stream)>>>(BF(x), cosv, sinv, BFM(y), tokens, L, H, head_dim, l0, ldx, ldy, inverse);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_pope_fwd(const void* x, const float* cos_sin, const float* bias, void* y, int64_t tokens, int32_t L, int32_t H,
+                            int32_t d, int64_t ldx, int64_t ldy, vpt_stream_t stream) {
+  VPT_REQUIRE(x && cos_sin && y && tokens > 0 && L > 0 && H > 0 && d % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "vpt_pope_fwd: bad arguments");
+  pope_fwd_kernel<<<blocks_for(tokens * H * (d / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(x), cos_sin, bias, BFM(y), tokens, L, H, d, ldx, ldy);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_pope_bwd(const void* dy, const void* x, const float* cos_sin, const float* bias, void* dx, int64_t tokens,
+                            int32_t L, int32_t H, int32_t d, int64_t lddy, int64_t ldx, int64_t lddx, vpt_stream_t stream) {
+  VPT_REQUIRE(dy && x && cos_sin && dx && tokens > 0 && L > 0 && H > 0 && d % 8 == 0 && (lddy | ldx | lddx) % 8 == 0, "vpt_pope_bwd: bad arguments");
+  pope_bwd_kernel<<<blocks_for(tokens * H * (d / 8), 256, 148 * 32), 256, 0, S(stream)>>>(BF(dy), BF(x), cos_sin, bias, BFM(dx), tokens, L, H, d, lddy, ldx, lddx);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_token_gather(const void* src, const int64_t* idx, void* dst, int32_t B, int64_t L_full, int64_t n, int32_t D,
+                                int32_t scatter, vpt_stream_t stream) {
+  VPT_REQUIRE(src && idx && dst && B > 0 && L_full > 0 && n > 0 && n <= L_full && D % 8 == 0, "vpt_token_gather: bad arguments");
+  VPT_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "vpt_token_gather: 16-byte alignment");
+  token_gather_kernel<<<blocks_for(static_cast<long>(B) * n * (D / 8), 256, 148 * 32), 256, 0, S(stream)>>>(
+      BF(src), reinterpret_cast<const long*>(idx), BFM(dst), B, static_cast<long>(L_full), static_cast<long>(n), D, scatter);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 static int patch_common(const void* src, void* dst, int B, int C, int H, int W, int p, int order, bool to_patches, cudaStream_t s) {
   VPT_REQUIRE(src && dst && B > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0 && (order == 0 || order == 1), "patchify: bad arguments");
   const long total = static_cast<long>(B) * C * H * W;

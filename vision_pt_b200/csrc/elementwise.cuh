@@ -350,6 +350,8 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __r
 
 // ------------------------------------------------------------------------------------------- LayerNorm + adaLN
 // n = bf16(LN_noaffine(x)); y = bf16( bf16(n * bf16(1 + scale[b])) + shift[b] );  x [B*L, D], scale/shift [B, D]
+// kCh = 16-byte chunks per lane: D <= 256 * kCh (CogView4's hidden width 4096 needs 16)
+template <int kCh>
 __global__ void __launch_bounds__(kEwThreads)
 ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ scale,
                        const __nv_bfloat16* __restrict__ shift, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
@@ -359,10 +361,10 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   if (row >= rows) return;
   const long b = row / L;
   const int nch = D >> 3;
-  uint4 v[kEwMaxChunks];
+  uint4 v[kCh];
   float s1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
       v[i] = ld_stream(x + row * D + c * 8);
@@ -375,7 +377,7 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   const float mean = warp_sum(s1) / static_cast<float>(D);
   float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
       float f[8];
@@ -390,7 +392,7 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     rstd_out[row] = rstd;
   }
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
       float f[8], sc[8], sh[8], o[8];
@@ -407,6 +409,7 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   }
 }
 // dx = LN_bwd(dy * (1 + scale));  dscale[b] += sum_l dy * n;  dshift[b] += sum_l dy   (fp32 atomics, [B, D])
+template <int kCh>
 __global__ void __launch_bounds__(kEwThreads)
 ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                        const __nv_bfloat16* __restrict__ scale, const float* __restrict__ mean_in,
@@ -418,10 +421,10 @@ ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   const long b = row / L;
   const int nch = D >> 3;
   const float mean = mean_in[row], rstd = rstd_in[row];
-  uint4 vx[kEwMaxChunks], vg[kEwMaxChunks];
+  uint4 vx[kCh], vg[kCh];
   float sa = 0.f, sb = 0.f;   // sum(dn), sum(dn * n)
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
       vx[i] = ld_stream(x + row * D + c * 8);
@@ -446,7 +449,7 @@ ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   sa = warp_sum(sa) / static_cast<float>(D);
   sb = warp_sum(sb) / static_cast<float>(D);
 #pragma unroll
-  for (int i = 0; i < kEwMaxChunks; ++i) {
+  for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
       float fx[8], fg[8], sc[8], o[8];

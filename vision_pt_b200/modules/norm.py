@@ -19,14 +19,11 @@ class FP32RMSNorm(nn.RMSNorm):
 
 
 class FP32LayerNorm(nn.LayerNorm):
-    """LayerNorm with fp32 statistics.  Without affine parameters it is the modulate kernel with scale = shift = 0."""
+    """LayerNorm with fp32 statistics over the last dimension, with or without affine parameters (reference norm.py:9-17:
+    F.layer_norm on the fp32 copy, cast back): one fused pass, rows up to 4096 wide."""
 
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
-        if self.weight is not None or hidden_states.dim() != 3:
-            raise NotImplementedError("the fused path covers the affine-free LayerNorm of the adaLN blocks on [B, L, D]")
-        b, _, d = hidden_states.shape
-        zeros = torch.zeros((b, d), dtype=hidden_states.dtype, device=hidden_states.device)
-        return ops.ln_modulate(hidden_states, zeros, zeros, self.eps)
+        return ops.layer_norm(hidden_states, self.weight, self.bias, self.eps)
 
 
 class SingleAdaLayerNormZeroOutput(NamedTuple):

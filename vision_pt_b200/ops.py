@@ -827,3 +827,261 @@ def copy_token_slots(dst3: torch.Tensor, start: int, src3: torch.Tensor | None) 
         return
     _lib.call("vpt_copy_rows", _p(view), dst3.stride(0) * es, _p(src3), 0 if src3 is None else src3.stride(0) * es, B,
               n * D * es, _stream())
+
+
+# ------------------------------------------------------------------------------------------------------- other block families
+# Kernels of csrc/blocks_ext.cuh: what the SDXL / CogView4 / JiT-extension blocks need beyond the JiT block's own kernels.
+ACT_KINDS = {"silu": 0, "gelu": 1, "gelu_tanh": 2, "gelu_pytorch_tanh": 2}
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm / FP32LayerNorm with (or without) affine parameters over the last dimension of a bf16 tensor."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        if x.dtype != torch.bfloat16:
+            raise TypeError("fused LayerNorm runs on bfloat16 activations")
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D).contiguous()
+        rows = x2.shape[0]
+        wb = None if w is None else w.detach().to(torch.bfloat16).contiguous()
+        bb = None if b is None else b.detach().to(torch.bfloat16).contiguous()
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.call("vpt_layernorm_fwd", _p(x2), _p(wb), _p(bb), _p(y), _p(mean), _p(rstd), rows, D, float(eps), _stream())
+        ctx.save_for_backward(x2, wb, mean, rstd)
+        ctx.grads = (w is not None and w.requires_grad, b is not None and b.requires_grad, None if w is None else w.dtype)
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, mean, rstd = ctx.saved_tensors
+        rows, D = x2.shape
+        wg, bg, wdt = ctx.grads
+        dy2 = dy.to(torch.bfloat16).reshape(rows, D).contiguous()
+        dx = torch.empty_like(x2)
+        dw = torch.zeros(D, dtype=torch.float32, device=x2.device) if wg else None
+        db = torch.zeros(D, dtype=torch.float32, device=x2.device) if bg else None
+        _lib.call("vpt_layernorm_bwd", _p(dy2), _p(x2), _p(wb), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), rows, D, _stream())
+        return dx.reshape(dy.shape), (dw.to(wdt) if wg else None), (db.to(wdt) if bg else None), None
+
+
+def layer_norm(x, weight=None, bias=None, eps: float = 1e-5):
+    _need_cuda(x)
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+class GatedActFn(torch.autograd.Function):
+    """bf16(bf16(act(gate)) * h): GeGLU (h, gate = halves of one projection: views with the projection's row pitch are fine)."""
+
+    @staticmethod
+    def forward(ctx, h, gate, kind):
+        F_ = h.shape[-1]
+        h2, g2 = _rows(h), _rows(gate)
+        rows = h2.shape[0]
+        ld = (F_ + 7) // 8 * 8
+        a_full = torch.empty((rows, ld), dtype=torch.bfloat16, device=h.device)
+        _lib.call("vpt_gated_act_fwd", _p(h2), _p(g2), _p(a_full), rows, F_, h2.stride(0) if rows > 1 else ld,
+                  g2.stride(0) if rows > 1 else ld, ld, int(kind), _stream())
+        ctx.save_for_backward(h2, g2)
+        ctx.kind = int(kind)
+        a = a_full[:, :F_] if ld != F_ else a_full
+        return a.reshape(h.shape)
+
+    @staticmethod
+    def backward(ctx, da):
+        h2, g2 = ctx.saved_tensors
+        rows, F_ = h2.shape
+        ld = (F_ + 7) // 8 * 8
+        da2 = _rows(da.to(torch.bfloat16))
+        dh = torch.empty((rows, ld), dtype=torch.bfloat16, device=h2.device)
+        dg = torch.empty((rows, ld), dtype=torch.bfloat16, device=h2.device)
+        one = lambda t: t.stride(0) if rows > 1 else ld
+        _lib.call("vpt_gated_act_bwd", _p(da2), _p(h2), _p(g2), _p(dh), _p(dg), rows, F_, one(da2), one(h2), one(g2), ld, ld,
+                  ctx.kind, _stream())
+        if ld != F_:
+            dh, dg = dh[:, :F_], dg[:, :F_]
+        return dh.reshape(da.shape), dg.reshape(da.shape), None
+
+
+def gated_act(h, gate, kind: str = "gelu"):
+    _need_cuda(h, gate)
+    return GatedActFn.apply(h, gate, ACT_KINDS[kind])
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        xc = x.contiguous()
+        if xc.numel() % 8 != 0 or xc.dtype != torch.bfloat16:
+            raise ValueError("fused activation: bf16 tensors with a multiple of 8 elements")
+        y = torch.empty_like(xc)
+        _lib.call("vpt_act_fwd", _p(xc), _p(y), xc.numel(), int(kind), _stream())
+        ctx.save_for_backward(xc)
+        ctx.kind = int(kind)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        dyc = dy.to(torch.bfloat16).contiguous()
+        dx = torch.empty_like(xc)
+        _lib.call("vpt_act_bwd", _p(dyc), _p(xc), _p(dx), xc.numel(), ctx.kind, _stream())
+        return dx, None
+
+
+def activation(x, kind: str = "gelu_tanh"):
+    _need_cuda(x)
+    return ActFn.apply(x, ACT_KINDS[kind])
+
+
+def _rope_half_call(x4, cos, sin, l0, inverse):
+    B, L, H, hd = x4.shape
+    xc = x4.contiguous()
+    y = torch.empty_like(xc)
+    _lib.call("vpt_rope_half", _p(xc), _p(cos), _p(sin), _p(y), B * L, L, H, hd, int(l0), H * hd, H * hd, int(inverse), _stream())
+    return y
+
+
+class RopeHalfFn(torch.autograd.Function):
+    """CogView4 apply_rotary_emb on token-major [B, L, H, hd]; tokens before `l0` (the text stream) pass through."""
+
+    @staticmethod
+    def forward(ctx, x4, cos, sin, l0):
+        ctx.save_for_backward(cos, sin)
+        ctx.l0 = l0
+        return _rope_half_call(x4, cos, sin, l0, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos, sin = ctx.saved_tensors
+        return _rope_half_call(dy.to(torch.bfloat16), cos, sin, ctx.l0, True), None, None, None
+
+
+def rope_half(x4, cos, sin, l0: int = 0):
+    """x4 [B, L, H, hd] bf16; cos / sin fp32 [L - l0, hd] (contiguous)."""
+    _need_cuda(x4)
+    if x4.dtype != torch.bfloat16 or x4.shape[-1] % 16 != 0:
+        raise ValueError("rope_half: bf16 [B, L, H, hd] with hd a multiple of 16")
+    cos = cos.to(device=x4.device, dtype=torch.float32).contiguous()
+    sin = sin.to(device=x4.device, dtype=torch.float32).contiguous()
+    if cos.shape != (x4.shape[1] - l0, x4.shape[3]) or sin.shape != cos.shape:
+        raise ValueError("rope_half: cos / sin must be [L - l0, head_dim]")
+    return RopeHalfFn.apply(x4, cos, sin, int(l0))
+
+
+class PopeFn(torch.autograd.Function):
+    """apply_pope on token-major [B, L, H, d] -> [B, L, H, 2d] (interleaved re / im); frozen learned bias only."""
+
+    @staticmethod
+    def forward(ctx, x4, cos_sin, bias):
+        B, L, H, d = x4.shape
+        xc = x4.contiguous()
+        y = torch.empty((B, L, H, 2 * d), dtype=torch.bfloat16, device=x4.device)
+        _lib.call("vpt_pope_fwd", _p(xc), _p(cos_sin), _p(bias), _p(y), B * L, L, H, d, H * d, 2 * H * d, _stream())
+        ctx.save_for_backward(xc, cos_sin, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, cos_sin, bias = ctx.saved_tensors
+        B, L, H, d = xc.shape
+        dyc = dy.to(torch.bfloat16).contiguous()
+        dx = torch.empty_like(xc)
+        _lib.call("vpt_pope_bwd", _p(dyc), _p(xc), _p(cos_sin), _p(bias), _p(dx), B * L, L, H, d, 2 * H * d, H * d, H * d, _stream())
+        return dx, None, None
+
+
+def pope(x4, cos_sin, learned_bias=None):
+    """x4 [B, L, H, d] bf16; cos_sin fp32 [L, d, 2]; learned_bias fp32 [H, d] or None (must not require grad here)."""
+    _need_cuda(x4)
+    if learned_bias is not None and learned_bias.requires_grad:
+        raise NotImplementedError("PoPE's learned phase bias is frozen on the fused path")
+    if x4.dtype != torch.bfloat16 or x4.shape[-1] % 8 != 0:
+        raise ValueError("pope: bf16 [B, L, H, d] with d a multiple of 8")
+    cs = cos_sin.to(device=x4.device, dtype=torch.float32).contiguous()
+    if cs.shape != (x4.shape[1], x4.shape[3], 2):
+        raise ValueError("pope: cos_sin must be [L, d, 2]")
+    b = None if learned_bias is None else learned_bias.detach().to(device=x4.device, dtype=torch.float32).contiguous()
+    return PopeFn.apply(x4, cs, b)
+
+
+def _token_gather_call(src3, idx, n_full, scatter, dst=None):
+    B, _, D = src3.shape
+    sc = src3.contiguous()
+    n = idx.numel()
+    if dst is None:
+        if scatter:
+            dst = torch.zeros((B, n_full, D), dtype=sc.dtype, device=sc.device)
+        else:
+            dst = torch.empty((B, n, D), dtype=sc.dtype, device=sc.device)
+    _lib.call("vpt_token_gather", _p(sc), _p(idx), _p(dst), B, n_full, n, D, int(scatter), _stream())
+    return dst
+
+
+class TokenGatherFn(torch.autograd.Function):
+    """out[b, j] = x[b, idx[j]] for a [B, L, D] token buffer (TREAD: keep / route subsets of one random permutation)."""
+
+    @staticmethod
+    def forward(ctx, x3, idx):
+        ctx.save_for_backward(idx)
+        ctx.n_full = x3.shape[1]
+        return _token_gather_call(x3, idx, x3.shape[1], False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return _token_gather_call(dy, idx, ctx.n_full, True), None
+
+
+class TokenScatterFn(torch.autograd.Function):
+    """out[b, idx[j]] = x[b, j]; rows of out not named by idx are zero.  idx must hold unique positions."""
+
+    @staticmethod
+    def forward(ctx, x3, idx, n_full):
+        ctx.save_for_backward(idx)
+        return _token_gather_call(x3, idx, n_full, True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return _token_gather_call(dy, idx, dy.shape[1], False), None, None
+
+
+class TokenMergeFn(torch.autograd.Function):
+    """out[b, idx_a[j]] = a[b, j], out[b, idx_b[j]] = b[b, j]: two disjoint index sets that together cover every row."""
+
+    @staticmethod
+    def forward(ctx, a3, b3, idx_a, idx_b):
+        L = idx_a.numel() + idx_b.numel()
+        out = torch.empty((a3.shape[0], L, a3.shape[2]), dtype=a3.dtype, device=a3.device)
+        _token_gather_call(a3, idx_a, L, True, out)
+        _token_gather_call(b3, idx_b, L, True, out)
+        ctx.save_for_backward(idx_a, idx_b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx_a, idx_b = ctx.saved_tensors
+        L = dy.shape[1]
+        return _token_gather_call(dy, idx_a, L, False), _token_gather_call(dy, idx_b, L, False), None, None
+
+
+def token_merge(a3, b3, idx_a, idx_b):
+    return TokenMergeFn.apply(a3, b3, _check_tokens(a3, idx_a), _check_tokens(b3, idx_b))
+
+
+def _check_tokens(x3, idx):
+    _need_cuda(x3, idx)
+    if x3.dim() != 3 or x3.element_size() != 2 or x3.shape[-1] % 8 != 0:
+        raise ValueError("token gather / scatter: 2-byte [B, L, D] tensors with D a multiple of 8")
+    return idx.to(device=x3.device, dtype=torch.int64).contiguous()
+
+
+def token_gather(x3, idx):
+    return TokenGatherFn.apply(x3, _check_tokens(x3, idx))
+
+
+def token_scatter(x3, idx, n_full: int):
+    return TokenScatterFn.apply(x3, _check_tokens(x3, idx), int(n_full))
