@@ -417,7 +417,8 @@ def run_ours(args) -> None:
     hosts = [T.synthetic_batch(args.batch, args.res, args.res, seed=1000 + rank + 7919 * i) for i in range(2)]
     h2d_bytes = sum(t.numel() * t.element_size() for t in hosts[0])
 
-    trainer.train_step(*hosts[0])                 # captures the graph (collective-free warm-up inside) and runs one step
+    trainer.precapture([(args.batch, args.res, args.res)])   # every rank, in lock-step: the all-reduce goes into the graph
+    trainer.train_step(*hosts[0])
     torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         step.run()
@@ -504,6 +505,7 @@ def run_ours(args) -> None:
         del step, trainer, net
         torch.cuda.empty_cache()
         net, trainer, step = build("JiT-L/16")
+        trainer.precapture([(args.batch, args.res, args.res)])
         trainer.train_step(*hosts[0])
         for _ in range(3):
             step.run()
@@ -545,7 +547,13 @@ def run_ours(args) -> None:
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without communicator tear-down: destroying a NCCL communicator whose all-reduce is referenced by live CUDA
+        # graphs blocked in ncclCommDestroy on the 2-GPU box (both ranks had printed; profiles/r2f_dp_variants.txt)
+        torch.cuda.synchronize()
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -83,8 +83,9 @@ def _worker(rank: int, world: int, port: int, backend: str, q):
         # ---------------------------------------------------------------- (2) lazy capture of different buckets per rank
         hp = T.TrainHParams(lr=2e-3, clip_grad_norm=1.0)
         tr = T.JiTQLoRATrainer(net, num_classes=10, max_token_length=16, hp=hp, process_group=dist.group.WORLD, use_graph=True,
-                               seed=100 + rank)
+                               seed=100 + rank, overlap_chunks=2)      # exercise the chunked exchange (default: 1 chunk)
         shapes = [(4, 64, 64), (4, 64, 128), (4, 128, 64)]
+        tr.precapture(shapes[:1])          # bucket 0 in lock-step (NCCL: all-reduce inside its graph); 1 and 2 are met lazily
         order = [0, 1, 0, 2, 1, 2] if rank == 0 else [1, 1, 2, 0, 0, 2]     # new buckets appear at different steps per rank
         batches = [T.synthetic_batch(b, h, w, num_classes=10, max_token_length=16, seed=7 * rank + i)
                    for i, (b, h, w) in enumerate(shapes)]
@@ -98,13 +99,22 @@ def _worker(rank: int, world: int, port: int, backend: str, q):
         dist.all_gather(gathered, mine_p)
         out["params_identical"] = bool(torch.equal(gathered[0], gathered[1]))
         out["trained"] = bool(not torch.equal(tr.state.flat.param, p_start))
-        step0 = next(iter(tr.buckets.values()))
+        step0 = tr.buckets[shapes[0]]
         out["nccl_in_graph"] = bool(step0.nccl_in_graph)
         out["chunks"] = len(step0._chunks)
-        out["one_graph_per_step"] = step0.graph_update is None
+        out["one_graph_per_step"] = step0.graph_update is None              # the precaptured bucket
+        out["lazy_buckets_two_graphs"] = all(tr.buckets[s_].graph_update is not None for s_ in shapes[1:])
+        tr.close()                         # graphs referencing the communicator go first (see JiTQLoRATrainer.close)
+        out["closed"] = True
         q.put((rank, out))
     finally:
-        dist.destroy_process_group()
+        import threading
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=30)                 # a tear-down that blocks must not turn into a hung test: report it instead
+        if t.is_alive():
+            q.put((rank + 100, {"destroy_hung": True}))
+            os._exit(0)
 
 
 def test_two_ranks_match_one_rank_and_stay_in_lockstep():
@@ -117,19 +127,27 @@ def test_two_ranks_match_one_rank_and_stay_in_lockstep():
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=240)
     hung = [p for p in procs if p.is_alive()]
     for p in hung:
         p.kill()                          # the exact processes this test started
     assert not hung, "a rank hung (collectives out of step?)"
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    res = dict(q.get(timeout=10) for _ in range(2))
-    print(f"\nDP world 2 over {backend}: {res[0]}")
+    got = []
+    while len(got) < 4:
+        try:
+            got.append(q.get(timeout=5))
+        except Exception:
+            break
+    res = dict(got)
+    print(f"\nDP world 2 over {backend}: {res.get(0)}")
+    assert 100 not in res and 101 not in res, "destroy_process_group blocked after trainer.close()"
     for r in (0, 1):
         assert res[r]["scale"] == 0.5
         assert res[r]["dp_vs_single"] <= 2e-2, res[r]           # bf16 activations, different M tiling; fp32 accumulation
         assert res[r]["params_identical"] and res[r]["trained"], res[r]
         assert res[r]["chunks"] == 2
+        assert res[r]["lazy_buckets_two_graphs"], res[r]
         if backend == "nccl":
             assert res[r]["nccl_in_graph"] and res[r]["one_graph_per_step"], res[r]
 

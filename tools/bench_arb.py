@@ -56,8 +56,8 @@ def main() -> None:
     tr = T.JiTQLoRATrainer(net, hp=T.TrainHParams(optimizer=args.optimizer), process_group=group, seed=42 + rank)
     bks = buckets()
     host = {hw: T.synthetic_batch(args.batch, hw[0], hw[1], seed=7 + i) for i, hw in enumerate(bks)}
-    for hw in bks:                                   # capture every bucket's graph (warm-up does not train)
-        tr.train_step(*host[hw])
+    # capture every bucket's graph up front, all ranks in lock-step: the LoRA-gradient all-reduce is then part of each graph
+    tr.precapture([(args.batch, hw[0], hw[1]) for hw in bks])
     torch.cuda.synchronize()
     g = torch.Generator().manual_seed(1000 + rank)   # every rank draws its own bucket per step
     order = [bks[int(torch.randint(len(bks), (1,), generator=g))] for _ in range(args.steps)]

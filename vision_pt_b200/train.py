@@ -247,7 +247,10 @@ class JiTQLoRATrainStep:
             nccl_in_graph = os.environ.get("VPT_NCCL_IN_GRAPH", "1") != "0"
         self.nccl_in_graph = bool(nccl_in_graph) and nccl
         if overlap_chunks is None:
-            overlap_chunks = int(os.environ.get("VPT_DP_CHUNKS", "2"))
+            # 1 = one all-reduce after backward.  Measured on 2 B200 (profiles/r2f_dp_variants.txt): splitting it so that the
+            # last blocks' chunk runs under the rest of backward is SLOWER (14.62 vs 14.46 ms / step, JiT-B): the NCCL kernel
+            # takes SMs from the persistent GEMMs for longer than the 11 MB exchange costs when it runs alone
+            overlap_chunks = int(os.environ.get("VPT_DP_CHUNKS", "1"))
         self._chunks = self._chunk_plan(max(1, overlap_chunks)) if self.world > 1 else []
         self._side = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._sent = 0                   # chunks of this step whose all-reduce has been issued
@@ -391,11 +394,15 @@ class JiTQLoRATrainStep:
             kw["capture_error_mode"] = "thread_local"            # NCCL's watchdog thread may touch CUDA during a capture
         return torch.cuda.graph(g, **kw)
 
-    def capture(self, warmup: int = 2) -> None:
-        """Eager warm-up (one-time kernel attribute setup, allocator growth), then capture.  One graph per step: at
-        world > 1 the chunked NCCL all-reduce is captured with it (fork / join of the side stream become graph edges).
-        With `nccl_in_graph` off (or a non-NCCL backend) the step is two graphs (compute | update) with the all-reduce
-        launched between them."""
+    def capture(self, warmup: int = 2, in_lockstep: bool = False) -> None:
+        """Eager warm-up (one-time kernel attribute setup, allocator growth), then capture.
+
+        `in_lockstep=True` (JiTQLoRATrainer.precapture: every rank captures the same sequence of buckets at the same time):
+        at world > 1 the chunked NCCL all-reduce is captured INTO the step's graph (fork / join of the side stream become
+        graph edges), so a step is one graph launch.  A capture that only this rank performs (a bucket met for the first
+        time in the middle of a run) keeps the collective OUT of its graphs -- compute | update with the all-reduce
+        launched between them: NCCL may exchange buffer registrations between ranks while a collective is being captured,
+        which a lone rank would wait for forever."""
         if self.hp.optimizer == "radam_schedulefree":
             self.state.ensure_z()
         self._collectives = False
@@ -405,7 +412,7 @@ class JiTQLoRATrainStep:
         rng = torch.cuda.get_rng_state(self.device)
         before = ops._lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        if self.world == 1 or self.nccl_in_graph:
+        if self.world == 1 or (self.nccl_in_graph and in_lockstep):
             self._collectives = self.world > 1
             with self._graph_ctx(self.graph):
                 self._step()
@@ -534,12 +541,29 @@ class JiTQLoRATrainer:
         return step
 
     def precapture(self, shapes) -> None:
-        """Capture the graphs of the given (batch, H, W) buckets up front (optional: buckets are captured lazily, and
-        since no warm-up or capture issues a collective, ranks need not do it in lock-step)."""
+        """Capture the graphs of the given (batch, H, W) buckets up front.  COLLECTIVE at world > 1: every rank must call it
+        with the same list at the same point -- in exchange the gradient all-reduce is captured into each step's graph
+        (one launch per step, chunks overlapped with backward).  Buckets that are not precaptured are captured lazily by
+        the rank that meets them, with the all-reduce between two graphs; both kinds interoperate (the collective is the
+        same), so ranks may meet new buckets at different times."""
         for b, h, w in shapes:
             step = self.bucket(b, h, w)
             if step.use_graph and step.graph is None:
-                step.capture()
+                step.capture(in_lockstep=True)
+
+    def close(self) -> None:
+        """Drop every captured graph (and the shared graph pool).  Call before torch.distributed.destroy_process_group():
+        tearing down a NCCL communicator whose collectives are still referenced by live CUDA graphs blocks in
+        ncclCommDestroy (observed with NCCL 2.28.9)."""
+        import gc
+        torch.cuda.synchronize(self.device)
+        for step in self.buckets.values():
+            step.graph = step.graph_update = step.graph_micro = None
+        self.buckets.clear()
+        self._staging.clear()
+        self.state.pool = None
+        gc.collect()
+        torch.cuda.synchronize(self.device)
 
     @staticmethod
     def _check_host_mask(attention_mask: torch.Tensor) -> None:
