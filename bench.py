@@ -143,14 +143,19 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float
     torch.cuda.synchronize()
     step.use_graph = was
     recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
-    tape, last_dq = [], None
+    # a GEMM reads the slots of one of the last two dequantisation launches (the next block's launch is issued ahead of the
+    # current block's GEMMs: ops.DequantPrefetcher)
+    tape, recent = [], []
     for r in recs:
         if r["kind"] == "dequant":
-            last_dq = r
+            recent = (recent + [r])[-2:]
             tape.append(r)
-        elif r["nf4"] and r["lora"] and r["scratch"] and last_dq is not None and r["scratch_ptr"] in last_dq["slot_ptrs"]:
-            r["slot"] = last_dq["slot_ptrs"].index(r["scratch_ptr"])
-            tape.append(r)
+        elif r["nf4"] and r["lora"] and r["scratch"]:
+            for dq in reversed(recent):
+                if r["scratch_ptr"] in dq["slot_ptrs"]:
+                    r["slot"], r["dq"] = dq["slot_ptrs"].index(r["scratch_ptr"]), id(dq)
+                    tape.append(r)
+                    break
     gemms = [r for r in tape if r["kind"] == "gemm"]
     if not gemms or not replay_here:
         return None
@@ -167,12 +172,16 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float
         return lst[salt % len(lst)]
 
     def replay(with_dequant: bool):
-        outs, slots = [], None
+        outs, live = [], {}
         for i, r in enumerate(tape):
             if r["kind"] == "dequant":
-                # without the dequantisation launches the slots were filled once, outside the timed graph
-                slots = ops.dequant_block(r["weights"], r["downs"], r["ups"], r["transposed"]) if with_dequant else filled[id(r)]
+                # without the dequantisation launches the slots were filled once, outside the timed graph; with them, the
+                # launches alternate between the same two arenas as in the step
+                tag = ("roofline",) + tuple(r["arena_tag"] or ())
+                live[id(r)] = ops.dequant_block(r["weights"], r["downs"], r["ups"], r["transposed"], arena_tag=tag) \
+                    if with_dequant else filled[id(r)]
                 continue
+            slots = live[r["dq"]]
             shape, stride, w, bias, down, up, scale, has_res, want_side, backward = r["call"]
             n_out = w.shape[1] if backward else w.shape[0]
             res = buf((shape[0], n_out), (n_out + 7) // 8 * 8, i + 1) if has_res else None

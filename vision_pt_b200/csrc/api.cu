@@ -357,7 +357,7 @@ extern "C" int vpt_swiglu_bwd(const void* da, const void* g, const void* u, void
 extern "C" int vpt_ln_modulate_fwd(const void* x, const void* scale, const void* shift, void* y, float* mean, float* rstd,
                                    int64_t rows, int32_t L, int32_t D, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(x && scale && shift && y && rows > 0 && L > 0 && D % 8 == 0 && D <= 4096, "vpt_ln_modulate_fwd: bad arguments");
-#define VPT_CALL(CH) ln_modulate_fwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(scale), BF(shift), BFM(y), mean, rstd, rows, L, D, eps)
+#define VPT_CALL(CH) VPT_CUDA_OK(launch_pdl(ln_modulate_fwd_kernel<CH>, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(x), BF(scale), BF(shift), BFM(y), mean, rstd, static_cast<long>(rows), L, D, eps))
   VPT_LN_DISPATCH(D, VPT_CALL);
 #undef VPT_CALL
   VPT_CUDA_OK(cudaGetLastError());
@@ -368,7 +368,7 @@ extern "C" int vpt_ln_modulate_bwd(const void* dy, const void* x, const void* sc
                                    vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && scale && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 4096, "vpt_ln_modulate_bwd: bad arguments");
   VPT_REQUIRE((dscale == nullptr) == (dshift == nullptr), "vpt_ln_modulate_bwd: dscale and dshift go together");
-#define VPT_CALL(CH) ln_modulate_bwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(scale), mean, rstd, BFM(dx), dscale, dshift, rows, L, D)
+#define VPT_CALL(CH) VPT_CUDA_OK(launch_pdl(ln_modulate_bwd_kernel<CH>, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(dy), BF(x), BF(scale), mean, rstd, BFM(dx), dscale, dshift, static_cast<long>(rows), L, D))
   VPT_LN_DISPATCH(D, VPT_CALL);
 #undef VPT_CALL
   VPT_CUDA_OK(cudaGetLastError());
@@ -392,7 +392,7 @@ extern "C" int vpt_gate_residual_bwd(const void* dy, const void* h, const void* 
 extern "C" int vpt_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows,
                                  int32_t D, float eps, vpt_stream_t stream) {
   VPT_REQUIRE(x && y && rows > 0 && D > 0 && D % 8 == 0 && D <= 4096 && ((mean == nullptr) == (rstd == nullptr)), "vpt_layernorm_fwd: bad arguments");
-#define VPT_CALL(CH) layernorm_fwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(x), BF(w), BF(b), BFM(y), mean, rstd, rows, D, eps)
+#define VPT_CALL(CH) VPT_CUDA_OK(launch_pdl(layernorm_fwd_kernel<CH>, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(x), BF(w), BF(b), BFM(y), mean, rstd, static_cast<long>(rows), D, eps))
   VPT_LN_DISPATCH(D, VPT_CALL);
 #undef VPT_CALL
   VPT_CUDA_OK(cudaGetLastError());

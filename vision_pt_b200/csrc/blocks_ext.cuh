@@ -22,25 +22,22 @@ __global__ void __launch_bounds__(kEwThreads)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ b,
                      __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, int D,
                      float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nch = D >> 3;
   uint4 v[kCh];
-  float s1 = 0.f;
 #pragma unroll
   for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
-    if (c < nch) {
-      v[i] = ld_stream(x + row * D + c * 8);
-      float f[8];
-      ew_unpack8(v[i], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s1 += f[e];
-    }
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (c < nch) v[i] = ld_stream(x + row * D + c * 8);
   }
-  const float mean = warp_sum(s1) / static_cast<float>(D);
-  float s2 = 0.f;
+  // one reduction round for mean and variance: shifted moments (see ln_modulate_fwd_kernel)
+  const float x0 = __shfl_sync(0xffffffffu, ew_lo(v[0].x), 0);
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
@@ -48,10 +45,21 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       float f[8];
       ew_unpack8(v[i], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s2 += (f[e] - mean) * (f[e] - mean);
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[e] - x0;
+        s1 += d;
+        s2 += d * d;
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(D) + eps);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float m1 = s1 / static_cast<float>(D);
+  const float mean = x0 + m1;
+  const float rstd = rsqrtf(fmaxf(s2 / static_cast<float>(D) - m1 * m1, 0.f) + eps);
   if (lane == 0 && mean_out != nullptr) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
@@ -82,15 +90,22 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nch = D >> 3;
-  const float mean = mean_in[row], rstd = rstd_in[row];
   uint4 vx[kCh], vg[kCh];
+#pragma unroll
+  for (int i = 0; i < kCh; ++i) {                  // every load of the row is in flight before the first use
+    const int c = lane + i * 32;
+    vx[i] = vg[i] = make_uint4(0, 0, 0, 0);
+    if (c < nch) {
+      vx[i] = ld_stream(x + row * D + c * 8);
+      vg[i] = ld_stream(dy + row * D + c * 8);
+    }
+  }
+  const float mean = mean_in[row], rstd = rstd_in[row];
   float sa = 0.f, sb = 0.f;
 #pragma unroll
   for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
-      vx[i] = ld_stream(x + row * D + c * 8);
-      vg[i] = ld_stream(dy + row * D + c * 8);
       float fx[8], fg[8], fw[8];
       ew_unpack8(vx[i], fx);
       ew_unpack8(vg[i], fg);
@@ -161,7 +176,12 @@ gated_act_fwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* _
     ew_unpack8(ld_stream(h + r * ldh + c * 8), fh);
     ew_unpack8(ld_stream(gate + r * ldg + c * 8), fg);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = ew_round(act_value(fg[e], kind)) * fh[e];
+    for (int e = 0; e < 8; e += 2) {
+      float aa = act_value(fg[e], kind), ab = act_value(fg[e + 1], kind);
+      ew_round2(aa, ab);
+      o[e] = aa * fh[e];
+      o[e + 1] = ab * fh[e + 1];
+    }
     st_stream(a + r * lda + c * 8, ew_pack8(o));
   }
 }
@@ -180,9 +200,13 @@ gated_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* 
     ew_unpack8(ld_stream(h + r * ldh + c * 8), fh);
     ew_unpack8(ld_stream(gate + r * ldg + c * 8), fg);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      oh[e] = fa[e] * ew_round(act_value(fg[e], kind));
+    for (int e = 0; e < 8; e += 2) {
+      float aa = act_value(fg[e], kind), ab = act_value(fg[e + 1], kind);
+      ew_round2(aa, ab);
+      oh[e] = fa[e] * aa;
+      oh[e + 1] = fa[e + 1] * ab;
       og[e] = fa[e] * fh[e] * act_deriv(fg[e], kind);
+      og[e + 1] = fa[e + 1] * fh[e + 1] * act_deriv(fg[e + 1], kind);
     }
     st_stream(dh + r * lddh + c * 8, ew_pack8(oh));
     st_stream(dgate + r * lddg + c * 8, ew_pack8(og));

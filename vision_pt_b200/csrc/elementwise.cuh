@@ -24,6 +24,13 @@ __device__ __forceinline__ uint32_t ew_pack(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float ew_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Two values rounded to bf16 and back through ONE full-rate bf16x2 pack (F2FP) + two ALU ops.  ew_round costs a quarter-rate
+// F2F per element, which put the kernels with several rounding points per element (adaLN modulate: 3) at ~0.5 of the HBM rate.
+__device__ __forceinline__ void ew_round2(float& a, float& b) {
+  const uint32_t p = ew_pack(a, b);
+  a = ew_lo(p);
+  b = ew_hi(p);
+}
 __device__ __forceinline__ void ew_unpack8(const uint4& v, float (&f)[8]) {
   f[0] = ew_lo(v.x); f[1] = ew_hi(v.x); f[2] = ew_lo(v.y); f[3] = ew_hi(v.y);
   f[4] = ew_lo(v.z); f[5] = ew_hi(v.z); f[6] = ew_lo(v.w); f[7] = ew_hi(v.w);
@@ -316,7 +323,12 @@ swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __re
     ew_unpack8(ld_stream(g + r * ldg + c * 8), fg);
     ew_unpack8(ld_stream(u + r * ldu + c * 8), fu);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = ew_round(fg[e] / (1.f + __expf(-fg[e]))) * fu[e];
+    for (int e = 0; e < 8; e += 2) {
+      float sa_ = fg[e] / (1.f + __expf(-fg[e])), sb_ = fg[e + 1] / (1.f + __expf(-fg[e + 1]));
+      ew_round2(sa_, sb_);
+      o[e] = sa_ * fu[e];
+      o[e + 1] = sb_ * fu[e + 1];
+    }
     st_stream(a + r * lda + c * 8, ew_pack8(o));
   }
 }
@@ -356,26 +368,24 @@ __global__ void __launch_bounds__(kEwThreads)
 ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ scale,
                        const __nv_bfloat16* __restrict__ shift, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                        float* __restrict__ rstd_out, long rows, int L, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const long b = row / L;
   const int nch = D >> 3;
   uint4 v[kCh];
-  float s1 = 0.f;
 #pragma unroll
   for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
-    if (c < nch) {
-      v[i] = ld_stream(x + row * D + c * 8);
-      float f[8];
-      ew_unpack8(v[i], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s1 += f[e];
-    }
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (c < nch) v[i] = ld_stream(x + row * D + c * 8);
   }
-  const float mean = warp_sum(s1) / static_cast<float>(D);
-  float s2 = 0.f;
+  // mean and variance in ONE reduction round: moments of (x - x0), x0 = the row's first element (a shift keeps the
+  // single-pass form free of cancellation when |mean| >> std); two dependent reductions cost the row a second latency chain
+  const float x0 = __shfl_sync(0xffffffffu, ew_lo(v[0].x), 0);
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
@@ -383,10 +393,21 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
       float f[8];
       ew_unpack8(v[i], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s2 += (f[e] - mean) * (f[e] - mean);
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[e] - x0;
+        s1 += d;
+        s2 += d * d;
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(D) + eps);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float m1 = s1 / static_cast<float>(D);
+  const float mean = x0 + m1;
+  const float rstd = rsqrtf(fmaxf(s2 / static_cast<float>(D) - m1 * m1, 0.f) + eps);
   if (lane == 0 && mean_out != nullptr) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
@@ -400,35 +421,52 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
       ew_unpack8(*reinterpret_cast<const uint4*>(scale + b * D + c * 8), sc);
       ew_unpack8(*reinterpret_cast<const uint4*>(shift + b * D + c * 8), sh);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float n = ew_round((f[e] - mean) * rstd);
-        o[e] = ew_round(n * ew_round(1.f + sc[e])) + sh[e];
+      for (int e = 0; e < 8; e += 2) {
+        float na = (f[e] - mean) * rstd, nb = (f[e + 1] - mean) * rstd;
+        float sa_ = 1.f + sc[e], sb_ = 1.f + sc[e + 1];
+        ew_round2(na, nb);
+        ew_round2(sa_, sb_);
+        float ta = na * sa_, tb = nb * sb_;
+        ew_round2(ta, tb);
+        o[e] = ta + sh[e];
+        o[e + 1] = tb + sh[e + 1];
       }
       st_stream(y + row * D + c * 8, ew_pack8(o));
     }
   }
 }
 // dx = LN_bwd(dy * (1 + scale));  dscale[b] += sum_l dy * n;  dshift[b] += sum_l dy   (fp32 atomics, [B, D])
+// All loads of the row (x, dy) are requested before the first use: 2 * kCh independent 16-byte loads in flight per lane
+// (interleaving load and use left the D = 4096 rows at 0.34 of the HBM rate, profiles/r2h_membound.txt).
 template <int kCh>
 __global__ void __launch_bounds__(kEwThreads)
 ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                        const __nv_bfloat16* __restrict__ scale, const float* __restrict__ mean_in,
                        const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
                        float* __restrict__ dshift, long rows, int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const long b = row / L;
   const int nch = D >> 3;
-  const float mean = mean_in[row], rstd = rstd_in[row];
   uint4 vx[kCh], vg[kCh];
+#pragma unroll
+  for (int i = 0; i < kCh; ++i) {
+    const int c = lane + i * 32;
+    vx[i] = vg[i] = make_uint4(0, 0, 0, 0);
+    if (c < nch) {
+      vx[i] = ld_stream(x + row * D + c * 8);
+      vg[i] = ld_stream(dy + row * D + c * 8);
+    }
+  }
+  const float mean = mean_in[row], rstd = rstd_in[row];
   float sa = 0.f, sb = 0.f;   // sum(dn), sum(dn * n)
 #pragma unroll
   for (int i = 0; i < kCh; ++i) {
     const int c = lane + i * 32;
     if (c < nch) {
-      vx[i] = ld_stream(x + row * D + c * 8);
-      vg[i] = ld_stream(dy + row * D + c * 8);
       float fx[8], fg[8], sc[8];
       ew_unpack8(vx[i], fx);
       ew_unpack8(vg[i], fg);

@@ -220,7 +220,7 @@ class JiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cos_sin, seqlens, spec, *lora):
-        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _, _ = spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _, block_index, nxt, _ = spec
         B, L, D = x.shape
         M = B * L
         x2 = x.reshape(M, D)
@@ -228,9 +228,17 @@ class JiTBlockFn(torch.autograd.Function):
             x2 = x2.contiguous()
         pads = [ops._pad_rank(l.down, l.up) for l in lins]
 
-        # all seven NF4 weights of the block dequantised by one launch into L2-resident slots
-        slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=False) \
-            if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue" else None
+        # all seven NF4 weights of the block dequantised by one launch into L2-resident slots -- by the previous block's
+        # prefetch when there was one; and the NEXT block's launch goes out now, on the side stream
+        slots = None
+        if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue":
+            slots = ops.PREFETCH.take(("f", block_index))
+            if slots is None:
+                slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=False,
+                                          arena_tag=("pf", torch.cuda.current_stream().cuda_stream, block_index & 1))
+            if nxt is not None and slots is not None:
+                ops.PREFETCH.issue(("f", block_index + 1), [l.w for l in nxt], [None] * len(nxt), [None] * len(nxt), False,
+                                   (block_index + 1) & 1)
 
         def lin(i, inp, residual=None, epilogue=0):
             l = lins[i]
@@ -273,7 +281,7 @@ class JiTBlockFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x2, rstd1, h1, q_pre, k_pre, v, q, k, o2, lse2, x1, rstd2, h2, g, u, a,
          t_q, t_k, t_v, t_o, t_g, t_u, t_3) = ctx.saved_tensors
-        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in, block_index = ctx.spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in, block_index, _, prv = ctx.spec
         pads = ctx.pads
         B, L, D = ctx.dims
         M = B * L
@@ -283,8 +291,16 @@ class JiTBlockFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         grads: list = [None] * 14
 
-        slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=True) \
-            if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue" else None
+        slots = None
+        if M >= ops.NF4_SCRATCH_MIN_M and ops.NF4_GEMM_MODE != "prologue":
+            slots = ops.PREFETCH.take(("b", block_index))
+            if slots is None:
+                slots = ops.dequant_block([l.w for l in lins], [p_[0] for p_ in pads], [p_[1] for p_ in pads], transposed=True,
+                                          arena_tag=("pf", torch.cuda.current_stream().cuda_stream, block_index & 1))
+            if prv is not None and slots is not None:
+                ppads = [ops._pad_rank(l.down, l.up) for l in prv]
+                ops.PREFETCH.issue(("b", block_index - 1), [l.w for l in prv], [p_[0] for p_ in ppads], [p_[1] for p_ in ppads], True,
+                                   (block_index - 1) & 1)
 
         def back(i, dout, residual=None, epilogue=0, in2=None):
             l = lins[i]
@@ -384,16 +400,27 @@ class JiTBlock(nn.Module):
                 and all(_linear_ok(l) for l in self._linears())
                 and self.attn.attn_dropout.p == 0 and self.attn.proj_dropout.p == 0 and self.mlp.ffn_dropout.p == 0)
 
-    def forward(self, hidden_states, cos_sin, seqlens=None, ctx_tail=None, n_keep=0, fresh_in=False):
+    def forward(self, hidden_states, cos_sin, seqlens=None, ctx_tail=None, n_keep=0, fresh_in=False, prefetch=False):
         """ctx_tail [B, L - n_keep, D]: when given, rows n_keep.. of the OUTPUT are replaced by it (fresh context tokens for
         the next block).  fresh_in: rows n_keep.. of the INPUT were produced that way by the previous block, so the
         gradient with respect to them is dropped."""
         if self.fused_eligible(hidden_states):
             lins = [_Lin(l) for l in self._linears()]
             bf = lambda w: w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
+            # neighbours whose dequantisation this block may start early (ops.DequantPrefetcher); only all-NF4, LoRA rank <= 16
+            # neighbours qualify, and only when blocks run strictly in order (no per-block recomputation)
+            nxt = prv = None
+            if ops.PREFETCH_DEQUANT and prefetch:
+                nb, pb = self.__dict__.get("_next_block"), self.__dict__.get("_prev_block")
+                ok = lambda b_: b_ is not None and b_.fused_eligible(hidden_states) and all(
+                    isinstance(l.w, ops.Nf4Tensors) and l.rank <= ops.RANK for l in (_Lin(m) for m in b_._linears()))
+                if ok(nb):
+                    nxt = [_Lin(m) for m in nb._linears()]
+                if ok(pb) and torch.is_grad_enabled():
+                    prv = [_Lin(m) for m in pb._linears()]
             spec = (lins, bf(self.norm1.weight), bf(self.norm2.weight), bf(self.attn.q_norm.weight),
                     bf(self.attn.k_norm.weight), self.attn.num_heads, self.eps,
-                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in), self.block_index)
+                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in), self.block_index, nxt, prv)
             lora = []
             for l in lins:
                 lora += [l.down, l.up]
@@ -425,6 +452,9 @@ class JiT(nn.Module):
             for _ in range(config.depth)])
         for i, blk in enumerate(self.blocks):
             blk.block_index = i
+            # plain references (not sub-modules): who runs before / after this block, for the dequantisation prefetch
+            blk.__dict__["_prev_block"] = self.blocks[i - 1] if i > 0 else None
+            blk.__dict__["_next_block"] = self.blocks[i + 1] if i + 1 < len(self.blocks) else None
         if config.use_output_bottleneck:
             self.final_layer = BottleneckFinalLayer(config.hidden_size, config.bottleneck_dim, config.patch_size,
                                                     config.in_channels, norm_type="rms")
@@ -484,7 +514,7 @@ class JiT(nn.Module):
         if self.gradient_checkpointing and self.training:
             import torch.utils.checkpoint as checkpoint
             return checkpoint.checkpoint(block, tokens, cos_sin, seqlens, ctx_tail, n_keep, fresh_in, use_reentrant=False)
-        return block(tokens, cos_sin, seqlens, ctx_tail, n_keep, fresh_in)
+        return block(tokens, cos_sin, seqlens, ctx_tail, n_keep, fresh_in, True)    # blocks run in order: prefetch allowed
 
     def forward(self, image, timestep, context, original_size, target_size, crop_coords, context_mask=None):
         cfg = self.config
@@ -509,6 +539,7 @@ class JiT(nn.Module):
         else:
             seq_ctx = None
 
+        ops.PREFETCH.reset()                         # nothing left over from an abandoned pass
         tokens = torch.cat([patches, size_embed, time_tokens], dim=1)
         # context slots stay in the token buffer between blocks (JiTBlock.forward: ctx_tail) when nothing upstream trains
         keep_slots = not cfg.do_context_fuse and not context_embed.requires_grad
@@ -525,6 +556,7 @@ class JiT(nn.Module):
             fresh = refresh
             if not cfg.do_context_fuse and i >= cfg.context_start_block and not keep_slots:
                 tokens = tokens[:, :-ctx_len, :]
+        ops.PREFETCH.reset()
         patches = self.final_layer(tokens[:, :n_patch, :])
         return self.unpatchify(patches, height=height, width=width)
 
