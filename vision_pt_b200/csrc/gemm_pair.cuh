@@ -58,10 +58,16 @@ struct PairSmem {
 #define VPT_PAIR_MAX_STAGES 6
 #endif
   // slab rings per lane quarter: ring 0 = in1 -> D (in place), ring 1 = in2 / D2 of the SwiGLU modes.  An input is fetched
-  // kSlabs - 2 chunks ahead of its use
+  // kSlabs0 - 2 chunks ahead of its use (a slab lives from its prefetch to the end of its store: distance + 2 chunks).
+  // Mode 1's ring 1 only carries an output (u), so two slabs do; that leaves ring 0 its four slabs = distance 2, like
+  // mode 0.  Mode 2 has inputs in both rings: 3 + 3 (distance 1) keeps four pipeline stages, 4 + 4 would leave three.
+#ifndef VPT_PAIR_M2_SLABS
+#define VPT_PAIR_M2_SLABS 3
+#endif
   static constexpr int kRings = kEpi == 0 ? 1 : 2;
-  static constexpr int kSlabs = kEpi == 0 ? 4 : 3;
-  static constexpr int kOutBytes = 4 * kRings * kSlabs * kSlabBytes;
+  static constexpr int kSlabs0 = kEpi == 2 ? VPT_PAIR_M2_SLABS : 4;
+  static constexpr int kSlabs1 = kEpi == 0 ? 0 : (kEpi == 1 ? 2 : VPT_PAIR_M2_SLABS);
+  static constexpr int kOutBytes = 4 * (kSlabs0 + kSlabs1) * kSlabBytes;
   static constexpr int kTsBytes = 128 * 32;
   static constexpr int kQBytes = (BN / 2) * 32;
   static constexpr int kBiasBytes = BN * 4;
@@ -73,7 +79,7 @@ struct PairSmem {
   static constexpr int kOffQ = kOffTs + kTsBytes;
   static constexpr int kOffBias = kOffQ + kQBytes;
   static constexpr int kOffBars = kOffBias + kBiasBytes;
-  static constexpr int kNumBars = 2 * kStages + 7 + 4 * kRings * kSlabs;
+  static constexpr int kNumBars = 2 * kStages + 7 + 4 * (kSlabs0 + kSlabs1);
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -121,7 +127,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full2 = tmem_full + 2;        // [2] per CTA: rank-16 update finished
   uint64_t* tmem_empty = tmem_full2 + 2;       // [2] leader's: 16 epilogue warps (both CTAs) drained the buffer
   uint64_t* ts_full = tmem_empty + 2;          // [1] leader's: 8 staging warps (both CTAs) staged Ts / Q
-  uint64_t* res_full = ts_full + 1;            // [4 quarters][kRings][kSlabs] prefetched input slab landed
+  uint64_t* res_full = ts_full + 1;            // [4 quarters][kSlabs0 + kSlabs1] prefetched input slab landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kOffTmemSlot);
   float* s_bias = reinterpret_cast<float*>(smem + S::kOffBias);
 
@@ -145,7 +151,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_empty[b], 2 * kPairEpiWarps);
     }
     mbar_init(ts_full, 8);
-    for (int i = 0; i < 4 * S::kRings * S::kSlabs; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 4 * (S::kSlabs0 + S::kSlabs1); ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -257,12 +263,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     const int et = threadIdx.x - kPairEpiWarp0 * 32;
     const uint32_t ts_bar = mapa_shared(smem_u32(ts_full), 0);
-    uint8_t* ring0 = smem + S::kOffOut + q * S::kRings * S::kSlabs * S::kSlabBytes;
-    uint8_t* ring1 = ring0 + S::kSlabs * S::kSlabBytes;                      // only when kRings == 2
-    uint64_t* res0 = res_full + q * S::kRings * S::kSlabs;
-    uint64_t* res1 = res0 + S::kSlabs;
+    uint8_t* ring0 = smem + S::kOffOut + q * (S::kSlabs0 + S::kSlabs1) * S::kSlabBytes;
+    uint8_t* ring1 = ring0 + S::kSlabs0 * S::kSlabBytes;                     // only when kRings == 2
+    uint64_t* res0 = res_full + q * (S::kSlabs0 + S::kSlabs1);
+    uint64_t* res1 = res0 + S::kSlabs0;
     constexpr int kChunks = BN / 64;             // 64-column output chunks per tile
-    constexpr int kAhead = S::kSlabs - 2;        // input prefetch distance in chunks
+    constexpr int kAhead = S::kSlabs0 - 2;       // input prefetch distance in chunks
+    constexpr int kS1 = S::kSlabs1 > 0 ? S::kSlabs1 : 1;
     const bool has_in1 = kEpi != 0 || p.residual != nullptr;
     constexpr bool kIn2 = kEpi == 2;
     constexpr bool kOut2 = kEpi != 0;
@@ -276,12 +283,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g = static_cast<int>(c % kChunks);
       const int rm0 = (t / p.num_n_tiles) * 256 + static_cast<int>(rank) * 128 + q * 32;
       const int ro0 = (t % p.num_n_tiles) * BN + g * 64;
-      const uint32_t sl = c % S::kSlabs;
+      const uint32_t sl = c % S::kSlabs0;
       mbar_arrive_expect_tx(&res0[sl], S::kSlabBytes);
       tma_load_2d(&tmR, &res0[sl], ring0 + sl * S::kSlabBytes, ro0, rm0);
       if (kIn2) {
-        mbar_arrive_expect_tx(&res1[sl], S::kSlabBytes);
-        tma_load_2d(&tmR2, &res1[sl], ring1 + sl * S::kSlabBytes, ro0, rm0);
+        const uint32_t sl1 = c % kS1;
+        mbar_arrive_expect_tx(&res1[sl1], S::kSlabBytes);
+        tma_load_2d(&tmR2, &res1[sl1], ring1 + sl1 * S::kSlabBytes, ro0, rm0);
       }
     };
     if (has_in1 && pair_lead && lane == 0) {
@@ -345,16 +353,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
 #pragma unroll 1
       for (int g = 0; g < kChunks; ++g, ++chunk_no) {
-        const uint32_t sl = chunk_no % S::kSlabs;
+        const uint32_t sl = chunk_no % S::kSlabs0;
+        const uint32_t sl1 = chunk_no % kS1;
         uint8_t* slab = ring0 + sl * S::kSlabBytes;
-        uint8_t* slab2 = ring1 + sl * S::kSlabBytes;
+        uint8_t* slab2 = ring1 + sl1 * S::kSlabBytes;
         if (pair_lead && lane == 0) {
-          tma_store_wait_read<1>();                // the slabs of chunk_no - 2 (= chunk_no + kAhead mod kSlabs) are free again
+          tma_store_wait_read<1>();                // the slabs of chunk_no - 2 (= chunk_no + kAhead mod kSlabs0) are free again
           if (has_in1) prefetch_in(chunk_no + kAhead);
         }
         __syncwarp();
-        if (has_in1) mbar_wait(&res0[sl], (chunk_no / S::kSlabs) & 1);
-        if (kIn2) mbar_wait(&res1[sl], (chunk_no / S::kSlabs) & 1);
+        // a two-slab ring is rewritten two chunks after its store was issued: the partner warp may only write once the
+        // leader has seen that store drain (deeper rings get this from the previous chunk's barrier)
+        if (kOut2 && S::kSlabs1 < 3) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (has_in1) mbar_wait(&res0[sl], (chunk_no / S::kSlabs0) & 1);
+        if (kIn2) mbar_wait(&res1[sl1], (chunk_no / kS1) & 1);
         const uint32_t srow = smem_u32(slab) + lane * 128;
         const uint32_t srow2 = smem_u32(slab2) + lane * 128;
         const int c = g * 2 + half;                // this warp's 32-column group of the tile
