@@ -79,7 +79,7 @@ def test_swiglu(rows, F):
     assert rel_err(gg.grad, gr.grad) <= 2e-2 and rel_err(ug.grad, ur.grad) <= 2e-2
 
 
-@pytest.mark.parametrize("B,L,D", [(2, 37, 128), (3, 100, 768), (2, 65, 1280)])
+@pytest.mark.parametrize("B,L,D", [(2, 37, 128), (3, 100, 768), (2, 65, 1280), (2, 130, 2560), (2, 77, 4096)])   # 2560 / 4096: CogView4 widths
 def test_adaln_modulate_and_gate(B, L, D):
     from vision_pt_b200 import ops
     torch.manual_seed(D + L)
@@ -172,3 +172,27 @@ def test_copy_token_slots(B, L, D, start):
     ops.copy_token_slots(got, start, None)
     assert torch.equal(got, want)
     assert torch.equal(got[:, :start], buf[:, :start])
+
+
+@pytest.mark.parametrize("rows,D,affine", [(300, 640, True), (131, 1280, True), (70, 64, False), (90, 4096, True), (64, 2560, False)])
+def test_layernorm_affine(rows, D, affine):
+    """nn.LayerNorm / FP32LayerNorm (src/modules/norm.py:9-17, src/models/sdxl/denoiser.py:248-250) with and without affine
+    parameters, forward, dx and dw / db, narrow (register-cached) and wide (D > 2048: two-pass) rows."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(rows + D)
+    x, dy = (torch.randn(rows, D) * 2 + 0.5).to(torch.bfloat16), torch.randn(rows, D).to(torch.bfloat16)
+    w = (torch.randn(D) * 0.3 + 1).to(torch.bfloat16) if affine else None
+    b = (torch.randn(D) * 0.3).to(torch.bfloat16) if affine else None
+    xg = x.cuda().requires_grad_(True)
+    wg = w.cuda().requires_grad_(True) if affine else None
+    bg = b.cuda().requires_grad_(True) if affine else None
+    y = ops.layer_norm(xg, wg, bg, 1e-5)
+    y.backward(dy.cuda())
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True) if affine else None
+    br = b.float().requires_grad_(True) if affine else None
+    yr = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= 1e-2 and rel_err(xg.grad, xr.grad) <= 2e-2
+    if affine:
+        assert rel_err(wg.grad, wr.grad) <= 2e-2 and rel_err(bg.grad, br.grad) <= 2e-2

@@ -368,6 +368,12 @@ extern "C" int vpt_ln_modulate_bwd(const void* dy, const void* x, const void* sc
                                    vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && scale && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 4096, "vpt_ln_modulate_bwd: bad arguments");
   VPT_REQUIRE((dscale == nullptr) == (dshift == nullptr), "vpt_ln_modulate_bwd: dscale and dshift go together");
+  static const int wide_min = getenv("VPT_LN_BWD_WIDE_MIN_D") ? atoi(getenv("VPT_LN_BWD_WIDE_MIN_D")) : 2049;   // A/B switch
+  if (D >= wide_min) {
+    VPT_CUDA_OK(launch_pdl(ln_modulate_bwd_wide_kernel, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(dy), BF(x),
+                           BF(scale), mean, rstd, BFM(dx), dscale, dshift, static_cast<long>(rows), L, D, 0));
+    return 0;
+  }
 #define VPT_CALL(CH) VPT_CUDA_OK(launch_pdl(ln_modulate_bwd_kernel<CH>, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(dy), BF(x), BF(scale), mean, rstd, BFM(dx), dscale, dshift, static_cast<long>(rows), L, D))
   VPT_LN_DISPATCH(D, VPT_CALL);
 #undef VPT_CALL
@@ -401,6 +407,13 @@ extern "C" int vpt_layernorm_fwd(const void* x, const void* w, const void* b, vo
 extern "C" int vpt_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
                                  float* dw, float* db, int64_t rows, int32_t D, vpt_stream_t stream) {
   VPT_REQUIRE(dy && x && mean && rstd && dx && rows > 0 && D % 8 == 0 && D <= 4096, "vpt_layernorm_bwd: bad arguments");
+  static const int wide_min = getenv("VPT_LN_BWD_WIDE_MIN_D") ? atoi(getenv("VPT_LN_BWD_WIDE_MIN_D")) : 2049;
+  if (D >= wide_min && (D > 2048 || (dw == nullptr) == (db == nullptr))) {   // dw / db accumulate like dscale / dshift with one "sample" (b = 0)
+    VPT_REQUIRE((dw == nullptr) == (db == nullptr), "vpt_layernorm_bwd: rows wider than 2048 take dw and db together");
+    VPT_CUDA_OK(launch_pdl(ln_modulate_bwd_wide_kernel, dim3(blocks_for(rows, kEwThreads / 32, 1L << 30)), dim3(kEwThreads), 0, S(stream), BF(dy), BF(x),
+                           BF(w), mean, rstd, BFM(dx), dw, db, static_cast<long>(rows), 1, D, 1));
+    return 0;
+  }
 #define VPT_CALL(CH) layernorm_bwd_kernel<CH><<<blocks_for(rows, kEwThreads / 32, 1L << 30), kEwThreads, 0, S(stream)>>>(BF(dy), BF(x), BF(w), mean, rstd, BFM(dx), dw, db, rows, D)
   VPT_LN_DISPATCH(D, VPT_CALL);
 #undef VPT_CALL

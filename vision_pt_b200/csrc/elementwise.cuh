@@ -504,6 +504,92 @@ ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   }
 }
 
+// Wide rows (D > 2048): the row is NOT cached in registers -- pass 1 reads x, dy for the two row sums, pass 2 reads them again
+// (from L2: the row was just there) and writes dx.  ~40 registers instead of ~200, so six times as many rows are in flight per
+// SM and one warp's arithmetic hides under the others' loads; HBM traffic is unchanged (profiles/r2_membound.json).
+__global__ void __launch_bounds__(kEwThreads)
+ln_modulate_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                            const __nv_bfloat16* __restrict__ scale, const float* __restrict__ mean_in,
+                            const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
+                            float* __restrict__ dshift, long rows, int L, int D, int affine) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (kEwThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long b = affine ? 0 : row / L;             // affine: `scale` is the LayerNorm weight [D] (or nullptr), dn = dy * w
+  const int nch = D >> 3;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float sa = 0.f, sb = 0.f;
+  for (int c0 = lane; c0 < nch; c0 += 128) {       // four independent 16-byte loads of each input per trip
+    uint4 vx[4], vg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      vx[u] = vg[u] = make_uint4(0, 0, 0, 0);
+      if (c < nch) {
+        vx[u] = *reinterpret_cast<const uint4*>(x + row * D + c * 8);
+        vg[u] = *reinterpret_cast<const uint4*>(dy + row * D + c * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      if (c < nch) {
+        float fx[8], fg[8], sc[8];
+        ew_unpack8(vx[u], fx);
+        ew_unpack8(vg[u], fg);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sc[e] = affine ? 1.f : 0.f;
+        if (scale != nullptr) ew_unpack8(*reinterpret_cast<const uint4*>(scale + b * D + c * 8), sc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float n = (fx[e] - mean) * rstd;
+          const float dn = fg[e] * (affine ? sc[e] : 1.f + sc[e]);
+          sa += dn;
+          sb += dn * n;
+          if (dscale != nullptr) {
+            atomicAdd(dscale + b * D + c * 8 + e, fg[e] * n);
+            atomicAdd(dshift + b * D + c * 8 + e, fg[e]);
+          }
+        }
+      }
+    }
+  }
+  sa = warp_sum(sa) / static_cast<float>(D);
+  sb = warp_sum(sb) / static_cast<float>(D);
+  for (int c0 = lane; c0 < nch; c0 += 128) {
+    uint4 vx[4], vg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      vx[u] = vg[u] = make_uint4(0, 0, 0, 0);
+      if (c < nch) {
+        vx[u] = *reinterpret_cast<const uint4*>(x + row * D + c * 8);
+        vg[u] = *reinterpret_cast<const uint4*>(dy + row * D + c * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      if (c < nch) {
+        float fx[8], fg[8], sc[8], o[8];
+        ew_unpack8(vx[u], fx);
+        ew_unpack8(vg[u], fg);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sc[e] = affine ? 1.f : 0.f;
+        if (scale != nullptr) ew_unpack8(*reinterpret_cast<const uint4*>(scale + b * D + c * 8), sc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float n = (fx[e] - mean) * rstd;
+          o[e] = rstd * (fg[e] * (affine ? sc[e] : 1.f + sc[e]) - sa - n * sb);
+        }
+        st_stream(dx + row * D + c * 8, ew_pack8(o));
+      }
+    }
+  }
+}
+
 // y = bf16( x + bf16(h * gate[b]) )
 __global__ void __launch_bounds__(256)
 gate_residual_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ h,

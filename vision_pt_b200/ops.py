@@ -908,8 +908,9 @@ class LayerNormFn(torch.autograd.Function):
         wg, bg, wdt = ctx.grads
         dy2 = dy.to(torch.bfloat16).reshape(rows, D).contiguous()
         dx = torch.empty_like(x2)
-        dw = torch.zeros(D, dtype=torch.float32, device=x2.device) if wg else None
-        db = torch.zeros(D, dtype=torch.float32, device=x2.device) if bg else None
+        both = D > 2048 and (wg or bg)          # the wide-row kernel accumulates dw and db together
+        dw = torch.zeros(D, dtype=torch.float32, device=x2.device) if (wg or both) else None
+        db = torch.zeros(D, dtype=torch.float32, device=x2.device) if (bg or both) else None
         _lib.call("vpt_layernorm_bwd", _p(dy2), _p(x2), _p(wb), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), rows, D, _stream())
         return dx.reshape(dy.shape), (dw.to(wdt) if wg else None), (db.to(wdt) if bg else None), None
 
