@@ -186,7 +186,7 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float
             n_out = w.shape[1] if backward else w.shape[0]
             res = buf((shape[0], n_out), (n_out + 7) // 8 * 8, i + 1) if has_res else None
             outs.append(ops.linear_raw(buf(shape, stride, i), w, bias, down, up, scale, res, want_side=want_side,
-                                       backward=backward, scratch=slots[r["slot"]]))
+                                       backward=backward, scratch=slots[r["slot"]], n_sections=r.get("n_sections", 1)))
         return outs
 
     # GEMM-only variant: every (block, direction) gets its own pre-filled set of slots (the step's arena is reused per block)

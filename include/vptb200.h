@@ -104,9 +104,17 @@ typedef struct {
   int64_t ld_in2;
   void* out2;                  /* [M, n_out] bf16, pitch ld_out2 (modes 1, 2) */
   int64_t ld_out2;
+  /* ABI 6: several linears over the SAME input as one forward call (q | k | v, src/models/jit/denoiser.py:351-363).  w_bf16
+   * (or the filled w_scratch) holds their [N_i, K] weights stacked to [n_sections * N_i, K] (w.N = the total), bias and
+   * lora_up are stacked the same way, lora_down holds 16 rows per section [16 * n_sections, K], side gets 16 rows per section
+   * [16 * n_sections, ld_side]; section i's output columns get section i's LoRA pair.  N_i must be a multiple of 128.
+   * 0 / 1 = one linear.  Forward calls with epilogue 0 only. */
+  int32_t n_sections;
 } vpt_linear_args;
 
 int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K);
+/* bytes ONE direction needs (what vpt_nf4_dequant_batch writes; a slot filled by it may be this small) */
+int64_t vpt_linear_scratch_bytes_dir(int32_t N, int32_t K, int32_t transposed);
 
 /* Fills the workspaces of up to 8 linears in ONE launch (the seven NF4 weights of a transformer block): slot i gets what
  * vpt_nf4lora_linear_fwd (transposed = 0) or _bwd_dx (transposed = 1; lora_down / lora_up given when the linear has

@@ -22,10 +22,10 @@ def test_header_symbols_exported(lib_built):
 
 def test_python_binding_covers_header(lib_built):
     from vision_pt_b200 import _lib
-    bound = set(_lib.SIGNATURES) | {"vpt_last_error", "vpt_abi_version", "vpt_linear_scratch_bytes"}
+    bound = set(_lib.SIGNATURES) | {"vpt_last_error", "vpt_abi_version", "vpt_linear_scratch_bytes", "vpt_linear_scratch_bytes_dir"}
     assert bound == set(_declared())
     lib = _lib.load()
-    assert lib.vpt_abi_version() == 5
+    assert lib.vpt_abi_version() == 6
     assert lib.vpt_linear_scratch_bytes(768, 2048) >= 2 * 768 * 2048
 
 

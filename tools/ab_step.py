@@ -24,7 +24,8 @@ args = ap.parse_args()
 VARIANTS = {
     "default": {},
     "separate swiglu kernels": {"FUSE_SWIGLU": False},
-    "dequant prefetch on a side stream": {"PREFETCH_DEQUANT": True},
+    "no dequant prefetch": {"PREFETCH_DEQUANT": False},
+    "separate q / k / v GEMMs": {"FUSE_QKV": False},
 }
 net = T.build_jit_qlora(args.model, device="cuda", seed=42)
 state = T.TrainState(net)

@@ -25,6 +25,7 @@ class LinearArgsC(C.Structure):
         ("ld_out", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64), ("side", C.c_void_p), ("M", C.c_int32),
         ("tile_n", C.c_int32), ("w_scratch", C.c_void_p), ("ld_scratch", C.c_int64), ("scratch_bytes", C.c_int64), ("ld_side", C.c_int64), ("reuse_scratch", C.c_int32),
         ("epilogue", C.c_int32), ("in2", C.c_void_p), ("ld_in2", C.c_int64), ("out2", C.c_void_p), ("ld_out2", C.c_int64),
+        ("n_sections", C.c_int32),
     ]
 
 
@@ -105,6 +106,8 @@ def load() -> C.CDLL:
     lib.vpt_abi_version.restype = C.c_int
     lib.vpt_linear_scratch_bytes.restype = C.c_int64
     lib.vpt_linear_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.vpt_linear_scratch_bytes_dir.restype = C.c_int64
+    lib.vpt_linear_scratch_bytes_dir.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

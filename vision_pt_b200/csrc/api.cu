@@ -23,7 +23,7 @@ static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
 }
 
 extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
-extern "C" int vpt_abi_version(void) { return 5; }
+extern "C" int vpt_abi_version(void) { return 6; }
 
 // ---------------------------------------------------------------------------------------------------- NF4
 extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
@@ -85,6 +85,14 @@ extern "C" int64_t vpt_linear_scratch_bytes(int32_t N, int32_t K) {
   const int64_t bwd = static_cast<int64_t>(K) * ldn + 16 * ldn + static_cast<int64_t>(K) * 16;
   return 2 * (fwd > bwd ? fwd : bwd) + 256;
 }
+// What ONE direction of a weight needs in its workspace slot: [N, ldk] for the forward; [K, ldn] + the transposed LoRA
+// copies for the backward.  Forward slots of this size are gap-free for N % 128 == 0, so the slots of q | k | v laid out one
+// after the other ARE the stacked [3N, K] weight of the sectioned forward call (vpt_linear_args.n_sections).
+extern "C" int64_t vpt_linear_scratch_bytes_dir(int32_t N, int32_t K, int32_t transposed) {
+  const int64_t ldk = (K + 7) / 8 * 8, ldn = (N + 7) / 8 * 8;
+  const int64_t e = transposed ? static_cast<int64_t>(K) * ldn + 16 * ldn + static_cast<int64_t>(K) * 16 : static_cast<int64_t>(N) * ldk;
+  return 2 * e;
+}
 extern "C" int vpt_nf4_dequant_batch(const vpt_nf4_dequant_item* items, int32_t n_items, int32_t transposed, vpt_stream_t stream) {
   VPT_REQUIRE(items != nullptr && n_items > 0 && n_items <= kDqMaxItems, "vpt_nf4_dequant_batch: 1..8 items");
   DequantBatch bp{};
@@ -94,8 +102,8 @@ extern "C" int vpt_nf4_dequant_batch(const vpt_nf4_dequant_item* items, int32_t 
     const int N = s.w.N, K = s.w.K;
     VPT_REQUIRE(N > 0 && K > 0 && s.w.packed && s.w.qabsmax && s.w.nested_absmax && s.w.nested_code && s.w.code && s.w_scratch,
                 "vpt_nf4_dequant_batch: NF4 tensors / workspace missing");
-    VPT_REQUIRE((reinterpret_cast<uintptr_t>(s.w_scratch) & 15) == 0 && s.scratch_bytes >= vpt_linear_scratch_bytes(N, K),
-                "vpt_nf4_dequant_batch: w_scratch must be 16-byte aligned and hold vpt_linear_scratch_bytes(N, K) bytes");
+    VPT_REQUIRE((reinterpret_cast<uintptr_t>(s.w_scratch) & 15) == 0 && s.scratch_bytes >= vpt_linear_scratch_bytes_dir(N, K, transposed),
+                "vpt_nf4_dequant_batch: w_scratch must be 16-byte aligned and hold vpt_linear_scratch_bytes_dir(N, K, transposed) bytes");
     DequantItem& d = bp.items[i];
     d.packed = s.w.packed; d.qabsmax = s.w.qabsmax; d.nested_absmax = s.w.nested_absmax; d.nested_code = s.w.nested_code;
     d.code = s.w.code; d.offset = s.w.offset; d.N = N; d.K = K;
@@ -145,6 +153,12 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     g.p.scale = a->scale;
     g.p.side = static_cast<__nv_bfloat16*>(a->side);
     g.p.ld_side = static_cast<long>(a->ld_side);
+    g.p.sec_n = 0;
+    if (a->n_sections > 1) {
+      VPT_REQUIRE(!bwd && a->epilogue == 0 && N % a->n_sections == 0 && (N / a->n_sections) % 128 == 0,
+                  "vpt_nf4lora_linear: n_sections is a forward option; every section must be a multiple of 128 columns wide");
+      g.p.sec_n = N / a->n_sections;
+    }
     g.epi = a->epilogue;
     g.out2 = a->out2; g.ldd2 = static_cast<int>(a->ld_out2);
     g.in2 = a->in2; g.ldr2 = static_cast<int>(a->ld_in2);
@@ -155,8 +169,9 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     }
     if (via_scratch) {
       VPT_REQUIRE(a->w.packed && a->w.qabsmax && a->w.nested_absmax && a->w.nested_code && a->w.code, "vpt_nf4lora_linear: NF4 tensors missing");
-      VPT_REQUIRE((reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0 && a->scratch_bytes >= vpt_linear_scratch_bytes(N, K),
-                  "vpt_nf4lora_linear: w_scratch must be 16-byte aligned and hold vpt_linear_scratch_bytes(N, K) bytes");
+      VPT_REQUIRE((reinterpret_cast<uintptr_t>(a->w_scratch) & 15) == 0 &&
+                      a->scratch_bytes >= (a->reuse_scratch ? vpt_linear_scratch_bytes_dir(N, K, bwd) : vpt_linear_scratch_bytes(N, K)),
+                  "vpt_nf4lora_linear: w_scratch must be 16-byte aligned and hold vpt_linear_scratch_bytes(N, K) bytes (a pre-filled slot: _dir)");
       __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(a->w_scratch);
       const long n = static_cast<long>(N) * K;
       if (!bwd) {
@@ -189,7 +204,7 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     }
     return launch_pair(g, stream);
   }
-  VPT_REQUIRE(a->epilogue == 0, "vpt_nf4lora_linear: the fused SwiGLU epilogues exist on the large-M (w_scratch) route only");
+  VPT_REQUIRE(a->epilogue == 0 && a->n_sections <= 1, "vpt_nf4lora_linear: the fused SwiGLU epilogues and n_sections exist on the large-M (CTA-pair) route only");
   const void* w_dense = a->w_bf16;
   long ldw = a->w_bf16 != nullptr ? ld_wb : 0;
   if (via_scratch) {

@@ -44,6 +44,11 @@ struct PairParams {
   __nv_bfloat16* side;             // Ts^T [16, ld_side] or nullptr (the layout lora_grad reads by TMA)
   long ld_side;
   int num_m_pairs, num_n_tiles;
+  // Several linears that share their input as ONE GEMM (q | k | v: reference Attention.forward, jit/denoiser.py:351-363):
+  // the output columns are `sec_n`-wide sections, each with its own LoRA pair -- P holds 16 rows per section, a tile takes
+  // the rows of the section it lies in (tiles never straddle sections: BN divides sec_n), `side` holds 16 rows per section.
+  // 0 = one section.
+  int sec_n;
 };
 
 template <int BN, bool kLoRA, int kEpi = 0>
@@ -193,7 +198,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_arrive_cluster(bar);
             tma_load_2d_pair(&tmA, bar, sa, ks * 64, m0);
             tma_load_2d_pair(&tmB1, bar, sb, ks * 64, o0 + S::kNH);
-            if (kLoRA) tma_load_2d_pair(&tmP, bar, sb + (S::kNH - kPairRank) * 128, ks * 64, 0);
+            if (kLoRA) tma_load_2d_pair(&tmP, bar, sb + (S::kNH - kPairRank) * 128, ks * 64, p.sec_n > 0 ? (o0 / p.sec_n) * kPairRank : 0);
           }
         }
       }
@@ -335,8 +340,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ts_s = smem_u32(smem + S::kOffTs) + (row >> 3) * 256 + (row & 7) * 16;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ts_s), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ts_s + 128), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-          if (nt == 0 && m < p.M && p.side != nullptr) {
-            unsigned short* dst = reinterpret_cast<unsigned short*>(p.side) + m;     // lanes = consecutive m: coalesced
+          const int sec = p.sec_n > 0 ? o0 / p.sec_n : 0;
+          const bool first_of_section = p.sec_n > 0 ? (o0 - sec * p.sec_n == 0) : (nt == 0);
+          if (first_of_section && m < p.M && p.side != nullptr) {
+            unsigned short* dst = reinterpret_cast<unsigned short*>(p.side) + static_cast<size_t>(sec) * kPairRank * p.ld_side + m;   // lanes = consecutive m: coalesced
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               dst[static_cast<size_t>(2 * i) * p.ld_side] = static_cast<unsigned short>(pk[i] & 0xffffu);

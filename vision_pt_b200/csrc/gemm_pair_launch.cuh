@@ -37,7 +37,8 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
   if (make_tmap_bf16_2d(&tmB0, g.w, p.R, p.NO, static_cast<uint64_t>(g.ldw) * 2, 64, S::kNH, sw)) return 1;
   if (make_tmap_bf16_2d(&tmB1, g.w, p.R, p.NO, static_cast<uint64_t>(g.ldw) * 2, 64, kLoRA ? S::kNH - kPairRank : S::kNH, sw)) return 1;
   tmP = tmA;
-  if (kLoRA && make_tmap_bf16_2d(&tmP, g.p_rows, p.R, kPairRank, static_cast<uint64_t>(g.ldp) * 2, 64, kPairRank, sw)) return 1;
+  const int n_sec = p.sec_n > 0 ? (p.NO + p.sec_n - 1) / p.sec_n : 1;
+  if (kLoRA && make_tmap_bf16_2d(&tmP, g.p_rows, p.R, static_cast<uint64_t>(kPairRank) * n_sec, static_cast<uint64_t>(g.ldp) * 2, 64, kPairRank, sw)) return 1;
   if (make_tmap_bf16_2d(&tmD, g.out, p.NO, p.M, static_cast<uint64_t>(g.ldd) * 2, 64, 32, sw)) return 1;
   tmR = tmD;
   if (p.residual != nullptr && make_tmap_bf16_2d(&tmR, p.residual, p.NO, p.M, static_cast<uint64_t>(p.ldr) * 2, 64, 32, sw)) return 1;
@@ -69,13 +70,14 @@ int launch_pair_t(const PairLaunch& g, cudaStream_t stream) {
 }
 
 // Tile width: whole waves of the 74 pairs x UMMA N, with the narrower tile charged for its extra L2 traffic.
-inline int choose_pair_bn(int M, int NO, bool lora) {
+inline int choose_pair_bn(int M, int NO, bool lora, int sec_n = 0) {
   const int pairs = (sm_count() > 0 ? sm_count() : 148) / 2;
   const int cands[2] = {192, 128};
-  int best = 192;
+  int best = 0;
   double best_cost = 1e30;
   for (int c = 0; c < 2; ++c) {
     const int bn = cands[c];
+    if (sec_n > 0 && sec_n % bn != 0) continue;          // a tile must lie inside one section
     const long tiles = static_cast<long>((M + 255) / 256) * ((NO + bn - 1) / bn);
     const long rounds = (tiles + pairs - 1) / pairs;
     const double cost = static_cast<double>(rounds) * (bn + (lora ? kPairRank : 0)) * (bn == 128 ? 1.12 : 1.0);
@@ -89,8 +91,9 @@ inline int choose_pair_bn(int M, int NO, bool lora) {
 
 inline int launch_pair(const PairLaunch& g, cudaStream_t stream) {
   const bool lora = g.p_rows != nullptr;
-  const int bn = g.bn > 0 ? g.bn : choose_pair_bn(g.p.M, g.p.NO, lora);
-  if (bn != 192 && bn != 128) return fail("unsupported tile width");
+  const int bn = g.bn > 0 ? g.bn : choose_pair_bn(g.p.M, g.p.NO, lora, g.p.sec_n);
+  if (bn != 192 && bn != 128) return fail("unsupported tile width (sections must be multiples of 128)");
+  if (g.p.sec_n > 0 && (g.p.sec_n % bn != 0 || g.p.NO % g.p.sec_n != 0)) return fail("sections: the section width must divide the output width and be a multiple of the tile width");
   if (g.epi != 0) {
     if (g.p.residual == nullptr || g.out2 == nullptr || (g.epi == 2 && g.in2 == nullptr))
       return fail("fused SwiGLU epilogue: in1 (residual) / out2 / in2 missing");

@@ -220,7 +220,7 @@ class JiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cos_sin, seqlens, spec, *lora):
-        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _, block_index, nxt, _ = spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _, block_index, nxt, _, qkv_bias = spec
         B, L, D = x.shape
         M = B * L
         x2 = x.reshape(M, D)
@@ -246,9 +246,21 @@ class JiTBlockFn(torch.autograd.Function):
                                   scratch=slots[i] if slots is not None else None, epilogue=epilogue)
 
         h1, rstd1 = ops.rmsnorm_fwd_raw(x2, n1w, eps)
-        q_pre, t_q = lin(0, h1)
-        k_pre, t_k = lin(1, h1)
-        v, t_v = lin(2, h1)
+        wqkv = None
+        if slots is not None and qkv_bias is not False and ops.FUSE_QKV and D % 128 == 0 and all(
+                pads[i][0] is not None and lins[i].scale == lins[0].scale and tuple(lins[i].w.shape) == (D, D) for i in range(3)):
+            wqkv = ops.fused_rows_view(slots[0:3], D, D)          # the three forward slots ARE the stacked [3D, D] weight
+        if wqkv is not None:
+            # q | k | v as ONE GEMM over h1 (three sections, each with its own LoRA pair): h1 is read once, one launch
+            qkv, t_qkv = ops.linear_raw(h1, wqkv, qkv_bias, ops.stacked([pads[i][0] for i in range(3)]),
+                                        ops.stacked([pads[i][1] for i in range(3)]), lins[0].scale, None, want_side=True,
+                                        n_sections=3, tape_slot=slots[0])
+            q_pre, k_pre, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+            t_q, t_k, t_v = t_qkv[0:16], t_qkv[16:32], t_qkv[32:48]
+        else:
+            q_pre, t_q = lin(0, h1)
+            k_pre, t_k = lin(1, h1)
+            v, t_v = lin(2, h1)
         q = ops.qknorm_rope_fwd_raw(q_pre, qnw, cos_sin, H, L, eps)
         k = ops.qknorm_rope_fwd_raw(k_pre, knw, cos_sin, H, L, eps)
         hd = D // H
@@ -281,7 +293,7 @@ class JiTBlockFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x2, rstd1, h1, q_pre, k_pre, v, q, k, o2, lse2, x1, rstd2, h2, g, u, a,
          t_q, t_k, t_v, t_o, t_g, t_u, t_3) = ctx.saved_tensors
-        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in, block_index, _, prv = ctx.spec
+        lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, fresh_in, block_index, _, prv, _ = ctx.spec
         pads = ctx.pads
         B, L, D = ctx.dims
         M = B * L
@@ -393,6 +405,21 @@ class JiTBlock(nn.Module):
     def _linears(self):
         return [self.attn.to_q, self.attn.to_k, self.attn.to_v, self.attn.to_o, self.mlp.w_1, self.mlp.w_2, self.mlp.w_3]
 
+    def _stacked_qkv_bias(self, lins):
+        """[3D] bias of the q | k | v call (frozen: built once per version of the three biases); None = no biases,
+        False = mixed (the fused call is not taken)."""
+        bs = [lins[i].bias for i in range(3)]
+        if all(b is None for b in bs):
+            return None
+        if any(b is None for b in bs):
+            return False
+        key = tuple((b.data_ptr(), b._version, b.device) for b in bs)
+        hit = self.__dict__.get("_qkv_bias_cache")
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([b.detach().to(torch.bfloat16) for b in bs]))
+            self.__dict__["_qkv_bias_cache"] = hit
+        return hit[1]
+
     def fused_eligible(self, x: torch.Tensor) -> bool:
         norms = [self.norm1, self.norm2, self.attn.q_norm, self.attn.k_norm]
         return (self.use_fused and x.is_cuda and x.dtype == torch.bfloat16 and self.attn.head_dim in ops.QKNORM_HEAD_DIMS
@@ -420,7 +447,8 @@ class JiTBlock(nn.Module):
                     prv = [_Lin(m) for m in pb._linears()]
             spec = (lins, bf(self.norm1.weight), bf(self.norm2.weight), bf(self.attn.q_norm.weight),
                     bf(self.attn.k_norm.weight), self.attn.num_heads, self.eps,
-                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in), self.block_index, nxt, prv)
+                    ctx_tail.detach() if ctx_tail is not None else None, n_keep, bool(fresh_in), self.block_index, nxt, prv,
+                    self._stacked_qkv_bias(lins))
             lora = []
             for l in lins:
                 lora += [l.down, l.up]

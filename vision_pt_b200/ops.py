@@ -24,6 +24,9 @@ NF4_SCRATCH_MIN_M = 1024
 # SwiGLU forward / backward in the epilogues of the w_2 / w_3-backward GEMMs of the fused block (large-M route); off =
 # separate swiglu_fwd / swiglu_bwd kernels (A/B measurements, VPT_FUSE_SWIGLU=0)
 FUSE_SWIGLU = os.environ.get("VPT_FUSE_SWIGLU", "1") != "0"
+# q | k | v of the fused block as ONE forward GEMM over the stacked dequantised weights (three 25 us launches -> one);
+# VPT_FUSE_QKV=0 = three calls
+FUSE_QKV = os.environ.get("VPT_FUSE_QKV", "1") != "0"
 _SCRATCH: dict[tuple, torch.Tensor] = {}
 
 
@@ -51,7 +54,8 @@ def dequant_block(weights: list, downs: list, ups: list, transposed: bool, arena
         return None
     lib = _lib.load()
     dev = weights[0].packed.device
-    sizes = [(int(lib.vpt_linear_scratch_bytes(w.shape[0], w.shape[1])) + 255) // 256 * 256 for w in weights]
+    # one direction's bytes per slot: forward slots of N % 128 == 0 weights are then gap-free (see fused_rows_view)
+    sizes = [(int(lib.vpt_linear_scratch_bytes_dir(w.shape[0], w.shape[1], int(transposed))) + 255) // 256 * 256 for w in weights]
     key = (dev.index, arena_tag if arena_tag is not None else torch.cuda.current_stream(dev).cuda_stream, bool(transposed))
     arena = _ARENA.get(key)
     if arena is None or arena.numel() < sum(sizes):
@@ -74,6 +78,39 @@ def dequant_block(weights: list, downs: list, ups: list, transposed: bool, arena
                            "transposed": bool(transposed), "slot_ptrs": [s_.data_ptr() for s_ in slots],
                            "arena_tag": arena_tag})
     return slots
+
+
+def fused_rows_view(slots: list[torch.Tensor], n_rows: int, k: int) -> torch.Tensor | None:
+    """The forward slots of several [n_rows, k] weights, laid out back to back by dequant_block, as ONE bf16 [len * n_rows, k]
+    weight (row pitch k rounded up to 8) -- what the sectioned forward call takes.  None when they are not adjacent."""
+    ldk = (k + 7) // 8 * 8
+    need = n_rows * ldk * 2
+    for a, b in zip(slots, slots[1:]):
+        if a.numel() != need or b.data_ptr() != a.data_ptr() + need:
+            return None
+    if slots[-1].numel() < need:
+        return None
+    base = slots[0]
+    flat = base.new_empty(0).set_(base.untyped_storage(), base.storage_offset(), (need * len(slots),), (1,))
+    return flat.view(torch.bfloat16).view(len(slots) * n_rows, ldk)[:, :k]
+
+
+def stacked(tensors: list[torch.Tensor]) -> torch.Tensor:
+    """Row-wise concatenation of 2-D (or 1-D) tensors; a zero-copy view when they already sit back to back in one storage
+    (the q / k / v LoRA matrices inside train.FlatLoRA's buffer), a copy otherwise."""
+    first = tensors[0]
+    ok = all(t.is_contiguous() and t.dtype == first.dtype and t.shape[1:] == first.shape[1:] for t in tensors)
+    if ok:
+        for a, b in zip(tensors, tensors[1:]):
+            if a.untyped_storage().data_ptr() != b.untyped_storage().data_ptr() or \
+                    b.data_ptr() != a.data_ptr() + a.numel() * a.element_size():
+                ok = False
+                break
+    if not ok:
+        return torch.cat(tensors, dim=0)
+    rows = sum(t.shape[0] for t in tensors)
+    shape = (rows,) + tuple(first.shape[1:])
+    return first.new_empty(0).set_(first.untyped_storage(), first.storage_offset(), shape, first.stride())
 
 
 class DequantPrefetcher:
@@ -271,11 +308,14 @@ def _pad_rank(down: torch.Tensor | None, up: torch.Tensor | None):
 
 def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, scale: float, residual=None,
                want_side: bool = False, backward: bool = False, tile_n: int = 0, reuse_scratch: bool = False,
-               scratch: torch.Tensor | None = None, epilogue: int = 0, in2: torch.Tensor | None = None):
+               scratch: torch.Tensor | None = None, epilogue: int = 0, in2: torch.Tensor | None = None, n_sections: int = 1,
+               tape_slot: torch.Tensor | None = None):
     """One call of the fused linear.  forward: x2 [M,K] -> y [M,N]; backward: x2 = dy [M,N] -> dx [M,K].
     `w` is the NF4 tensor set or a plain bf16 [N,K] weight.  Returns (out, side or None) -- or (out, out2, side) with a
     fused SwiGLU epilogue (include/vptb200.h): epilogue=1 (forward of w_2, residual = g) gives (a, u, side), epilogue=2
-    (backward of w_3, residual = g, in2 = u) gives (dg, du, side).
+    (backward of w_3, residual = g, in2 = u) gives (dg, du, side).  n_sections > 1: `w` is a bf16 weight holding several
+    linears stacked row-wise (q | k | v over one input), bias / lora_up stacked alike, lora_down 16 rows per section; the side
+    tensor then has 16 rows per section.  tape_slot: the dequantisation slot such a stacked weight starts at (bench taping).
     reuse_scratch: the previous call on this stream used the same weight and direction, so the dequantised copy in the
     workspace is still valid and the dequantisation kernel is skipped.  scratch: a slot filled by dequant_block for this
     weight and direction (implies reuse)."""
@@ -314,7 +354,12 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     out = out_full[:, :n_out] if ld_out != n_out else out_full
     # the rank-16 projection, kept for the parameter gradients in the [16, M] layout vpt_lora_grad_batch reads by TMA
     ld_side = (M + 7) // 8 * 8
-    side = torch.empty((RANK, ld_side), dtype=torch.bfloat16, device=x2.device) if (want_side and down is not None) else None
+    side = torch.empty((RANK * max(1, n_sections), ld_side), dtype=torch.bfloat16, device=x2.device) \
+        if (want_side and down is not None) else None
+    if n_sections > 1:
+        if isinstance(w, Nf4Tensors) or backward or epilogue or down is None or down.shape[0] != RANK * n_sections:
+            raise ValueError("n_sections: a forward call on a stacked bf16 weight with 16 lora_down rows per section")
+        args.n_sections = int(n_sections)
     args.bias = _p(bias)
     args.lora_down = _p(down)
     args.ld_lora_down = down.stride(0) if down is not None else 0
@@ -350,10 +395,12 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     if timer is not None:
         e1.record()
         lora = down is not None
-        flops = 2.0 * M * K * N + (2.0 * M * RANK * (K + N) if lora else 0.0)
+        flops = 2.0 * M * K * N + (2.0 * M * RANK * (max(1, n_sections) * K + N) if lora else 0.0)
+        if tape_slot is not None:            # a stacked weight made of dequantised NF4 slots counts as the NF4 route it is
+            scratch, prefilled = tape_slot, True
         timer.append({"kind": "gemm", "e0": e0, "e1": e1, "flops": flops, "M": M, "K": K, "N": N, "bwd": backward, "lora": lora,
-                      "nf4": isinstance(w, Nf4Tensors), "scratch": scratch is not None,
-                      "scratch_ptr": scratch.data_ptr() if prefilled else None,
+                      "nf4": isinstance(w, Nf4Tensors) or tape_slot is not None, "scratch": scratch is not None,
+                      "scratch_ptr": scratch.data_ptr() if prefilled else None, "n_sections": int(n_sections),
                       "call": (x2.shape, x2.stride(0), w, bias, down, up, scale, residual is not None, want_side, backward),
                       "epilogue": int(epilogue)})
     if epilogue:

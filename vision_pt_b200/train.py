@@ -78,11 +78,21 @@ class FlatLoRA:
 
     def __init__(self, model: nn.Module):
         self.params: list[nn.Parameter] = []
-        for mod in model.modules():
-            if isinstance(mod, LoRALinear):
-                for p in (mod.lora_down.weight, mod.lora_up.weight):
-                    if p.requires_grad:
-                        self.params.append(p)
+        mods = [(n, m) for n, m in model.named_modules() if isinstance(m, LoRALinear)]
+        i = 0
+        while i < len(mods):
+            # q / k / v of one attention: the three lora_down matrices back to back, then the three lora_up matrices, so that
+            # the fused block's single q | k | v GEMM takes them as two zero-copy views (ops.stacked)
+            group = [mods[i]]
+            stem = mods[i][0].rsplit(".", 1)[0]
+            if mods[i][0].endswith(".to_q") and i + 2 < len(mods) and mods[i + 1][0] == f"{stem}.to_k" and mods[i + 2][0] == f"{stem}.to_v":
+                group = mods[i:i + 3]
+            for pick in ("lora_down", "lora_up") if len(group) == 3 else (None,):
+                for _, mod in group:
+                    for p in ((mod.lora_down.weight, mod.lora_up.weight) if pick is None else (getattr(mod, pick).weight,)):
+                        if p.requires_grad:
+                            self.params.append(p)
+            i += len(group)
         if not self.params:
             raise ValueError("no trainable LoRA parameters")
         dev = self.params[0].device
