@@ -259,3 +259,23 @@ def test_swiglu_epilogues_equal_the_separate_kernels(M, D, F):
     assert rel_err(du, daf * gf * sg) <= 1e-2 and rel_err(dg, daf * uf * (sg * (1 + gf * (1 - sg)))) <= 1e-2
     assert rel_err(du, du_ref) <= 8e-3 and rel_err(dg, dg_ref) <= 8e-3
     assert float((du != du_ref).float().mean()) < 2e-3 and float((dg != dg_ref).float().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("rank", [32, 64])
+def test_lora_rank_above_16_takes_the_composition(rank):
+    """LoRAConfig.rank is free in the reference (src/modules/peft/lora.py:11-16).  The fused kernel folds ranks up to 16 into
+    the GEMM; larger ranks run the reference's composition -- the NF4 base through the fused kernel, the two skinny LoRA
+    GEMMs, scale and add as separate launches -- with the same result."""
+    layer, w_ref, x = _make(300, 768, 768, rank, True, bias=True)
+    assert not layer.fusable
+    xg = x.cuda().requires_grad_(True)
+    y = layer(xg)
+    dy = torch.randn(300, 768).to(torch.bfloat16)
+    y.backward(dy.cuda())
+    xr = x.clone().float().requires_grad_(True)
+    down = layer.lora_down.weight.detach().cpu().float().requires_grad_(True)
+    up = layer.lora_up.weight.detach().cpu().float().requires_grad_(True)
+    yr = oj.lora_linear(xr, oj.dense_weight(w_ref).float(), layer.linear.bias.detach().cpu().float(), down, up, alpha=2.0)
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= TOL and rel_err(xg.grad, xr.grad) <= TOL
+    assert rel_err(layer.lora_down.weight.grad, down.grad) <= TOL and rel_err(layer.lora_up.weight.grad, up.grad) <= TOL
