@@ -171,16 +171,30 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float
             lst.append(t)
         return lst[salt % len(lst)]
 
+    side = torch.cuda.Stream()
+
     def replay(with_dequant: bool):
-        outs, live = [], {}
+        outs, live, ready = [], {}, {}
+        main = torch.cuda.current_stream()
         for i, r in enumerate(tape):
             if r["kind"] == "dequant":
                 # without the dequantisation launches the slots were filled once, outside the timed graph; with them, the
-                # launches alternate between the same two arenas as in the step
+                # launches go out exactly as in the step: at their position in the tape (one block ahead of their GEMMs), on
+                # a side stream, into the same two alternating arenas; the first GEMM that reads a slot waits for its event
+                if not with_dequant:
+                    live[id(r)] = filled[id(r)]
+                    continue
                 tag = ("roofline",) + tuple(r["arena_tag"] or ())
-                live[id(r)] = ops.dequant_block(r["weights"], r["downs"], r["ups"], r["transposed"], arena_tag=tag) \
-                    if with_dequant else filled[id(r)]
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    live[id(r)] = ops.dequant_block(r["weights"], r["downs"], r["ups"], r["transposed"], arena_tag=tag)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                ready[id(r)] = ev
                 continue
+            ev = ready.pop(r["dq"], None)
+            if ev is not None:
+                main.wait_event(ev)
             slots = live[r["dq"]]
             shape, stride, w, bias, down, up, scale, has_res, want_side, backward = r["call"]
             n_out = w.shape[1] if backward else w.shape[0]
@@ -198,8 +212,8 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float
     torch.cuda.synchronize()
 
     def timed(with_dequant: bool) -> tuple[float, int]:
-        side = torch.cuda.Stream()
-        with torch.cuda.stream(side):
+        warm = torch.cuda.Stream()
+        with torch.cuda.stream(warm):
             replay(with_dequant)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -258,8 +272,9 @@ def gemm_roofline(step, ops, torch, replay_here: bool = True, min_seconds: float
                           "frac": fl / (ms_gemm * 1e-3) / 1e12 / peak, "replays": n_gemm,
                           "note": "same replay with the dequantised weights already in their slots"},
             "replays": n_all, "replay_ms": ms_all,
-            "how": "CUDA-graph replay of one step's taped GEMM + batched-dequantisation launches in step order, inputs "
-                   "rotated over 3 buffers per shape, mean over a >= 2 s loop; frac INCLUDES the dequantisation launches"}
+            "how": "CUDA-graph replay of one step's taped GEMM + batched-dequantisation launches as the step issues them (the "
+                   "dequantisation of block i+1 on a side stream while block i's GEMMs run), inputs rotated over 3 buffers per "
+                   "shape, mean over a >= 2 s loop; frac INCLUDES the dequantisation launches"}
 
 
 # ------------------------------------------------------------------------------------------------ reference legs

@@ -220,3 +220,32 @@ def test_trainer_with_radam_schedulefree(tmp_path, use_graph):
         tr2.train_step(*a)
     tr2.train()
     assert (tr2.state.flat.param.float() - y.float()).abs().max() <= 2 ** -6 * y.float().abs().max()
+
+
+def test_prefetched_input_pipeline_is_bit_identical():
+    """train_step(batch, prefetch=next) (H2D of the next batch on a copy stream into a staging slot, device-to-device copy
+    into the graph's inputs) trains exactly like the plain call (H2D on the main stream): same graph, same parameters."""
+    _, plain = _trainer(True, seed=5)
+    T, pref = _trainer(True, seed=5)
+    shapes = [(8, 64, 64), (8, 64, 128)]
+    batches = [T.synthetic_batch(B, H, W, num_classes=10, max_token_length=16, seed=i) for i, (B, H, W) in enumerate(shapes)]
+    order = [0, 1, 1, 0, 0, 1]
+    for tr in (plain, pref):
+        tr.precapture(shapes)
+    torch.manual_seed(77)
+    for i in order:
+        plain.train_step(*batches[i])
+    torch.cuda.synchronize()
+    torch.manual_seed(77)
+    pref.prefetch(*batches[order[0]])
+    losses = []
+    for n, i in enumerate(order):
+        nxt = batches[order[n + 1]] if n + 1 < len(order) else None
+        pref.train_step(*batches[i], prefetch=nxt)
+        if n > 0:
+            losses.append(pref.read_loss(1))
+    losses.append(pref.read_loss(0))
+    torch.cuda.synchronize()
+    assert torch.equal(plain.state.flat.param, pref.state.flat.param)
+    assert torch.equal(plain.state.exp_avg, pref.state.exp_avg) and plain.global_step == pref.global_step == len(order)
+    assert len(losses) == len(order) and all(l == l and l > 0 for l in losses)
