@@ -212,7 +212,9 @@ def _linear_ok(layer: nn.Module) -> bool:
 
 
 class JiTBlockFn(torch.autograd.Function):
-    """One JiTBlock (reference denoiser.py:633-649) as 13 forward / 25 backward kernel launches.
+    """One JiTBlock (reference denoiser.py:633-649) as a fixed sequence of about 11 forward / 16 backward kernel launches
+    (q | k | v one sectioned GEMM, SwiGLU in the w_2 / w_3-dX epilogues, the batched NF4 dequantisation prefetched on a side
+    stream, LoRA parameter gradients of the whole block in one launch).
 
     Gradients: the residual stream and the LoRA matrices.  Everything else in the block is frozen on this path."""
 
