@@ -451,12 +451,29 @@ def run_ours(args) -> None:
     # while (14.6 -> 15.2 ms/step over the first ~100 steps of JiT-B, profiles/r2c_e2e_variants.txt); `value` and `e2e` are
     # both taken in that steady state, so neither is flattered by a cold board and they can be compared with each other
     t_settle = time.perf_counter()
-    n_settle = 0
-    while time.perf_counter() - t_settle < args.settle_s:
-        for _ in range(5):
+    n_settle, prev_ms, calm = 0, None, 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while True:
+        ev0.record()
+        for _ in range(25):
             step.run()
+        ev1.record()
         torch.cuda.synchronize()
-        n_settle += 5
+        n_settle += 25
+        cur = ev0.elapsed_time(ev1) / 25
+        calm = calm + 1 if (prev_ms is not None and abs(cur - prev_ms) <= 0.0025 * prev_ms) else 0
+        prev_ms = cur
+        spent = time.perf_counter() - t_settle
+        # at least --settle-s; then until two consecutive 25-step chunks agree within 0.25 % (the clock has stopped sinking)
+        # or 3 x --settle-s have passed
+        more = not (spent >= args.settle_s and (calm >= 2 or spent >= 3 * args.settle_s))
+        if world > 1:                   # the ranks leave together: every step holds a collective, so the chunk count must agree
+            flag = torch.tensor([1 if more else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            more = bool(flag.item())
+        if not more:
+            break
+    settle_s = time.perf_counter() - t_settle
     launches_per_step = step.kernel_launches
 
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
@@ -552,7 +569,7 @@ def run_ours(args) -> None:
                        "global_batch": world * args.batch, "parallelism": f"dp{world}",
                        "cuda_graph": not args.no_graph, "gradient_checkpointing": bool(args.checkpointing),
                        "l2": "no flush: one step streams far more than the 126 MB L2 (saved activations of every block)",
-                       "settle": f"{n_settle} untimed steps ({args.settle_s} s) after the {max(args.warmup, 3)} warm-up steps, until the power-capped clock is steady",
+                       "settle": f"{n_settle} untimed steps ({settle_s:.1f} s) after the {max(args.warmup, 3)} warm-up steps: until two 25-step chunks agree within 0.25 % (power-capped clock steady)",
                        "optimizer": ("AdamW" if args.optimizer == "adamw" else "schedulefree.RAdamScheduleFree")
                                     + " over the flat LoRA buffer, clip_grad_norm 1.0", "loss": loss_target,
                        "exchange": (f"chunked NCCL all-reduce of the flat LoRA gradients, {len(step._chunks) if world > 1 else 0} chunks, "
