@@ -218,11 +218,13 @@ class JiTQLoRATrainStep:
       image [B,3,H,W] fp16 (the dataset emits fp16, src/dataset/text_to_image.py:152), class_ids [B,T] int64,
       attention_mask [B,T] int64 (leading ones).  Output: `loss` (fp32 device scalar of the last step).
 
-    Data parallelism (world > 1): the LoRA-gradient all-reduce is part of the captured graph (`nccl_in_graph`, so a step is
-    ONE graph launch) and is split into `overlap_chunks` pieces: the gradient slices of the last blocks are final long
-    before backward ends, so their all-reduce is issued on a side stream as soon as backward has passed them and runs under
-    the remaining backward.  No collective is ever issued by a warm-up or a capture: ranks may capture new (H, W) buckets
-    at different times without their collectives falling out of step."""
+    Data parallelism (world > 1): for a step captured in lock-step on every rank (`capture(in_lockstep=True)`,
+    JiTQLoRATrainer.precapture) the LoRA-gradient all-reduce is part of the captured graph (`nccl_in_graph`: a step is ONE
+    graph launch); a step captured lazily by one rank keeps it between two graphs.  `overlap_chunks` > 1 splits the
+    exchange so that the gradient ranges of the last blocks -- final long before backward ends -- are reduced on a side
+    stream under the remaining backward (measured slower than one exchange at the end: the default is 1).  No collective
+    is ever issued by a warm-up or a capture: ranks may capture new (H, W) buckets at different times without their
+    collectives falling out of step."""
 
     def __init__(self, model: Denoiser, batch: int, height: int, width: int, num_classes: int = 1000,
                  max_token_length: int = 64, hp: TrainHParams | None = None, process_group=None, use_graph: bool = True,
