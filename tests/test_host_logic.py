@@ -224,3 +224,49 @@ def test_gradient_chunk_plan_follows_block_order():
             inside = [int(names[id(p)].split(".")[1]) for p, off in zip(flat.params, flat.offsets) if lo <= off < hi]
             assert min(inside) == fb
     assert JiTQLoRATrainStep._chunk_plan(stub, 4) == [(0, 0, flat.numel)]   # fewer than 2 blocks per chunk: one exchange
+
+
+def test_flat_lora_keeps_qkv_adapters_adjacent_and_stacked_views_are_zero_copy():
+    """train.FlatLoRA lays the q / k / v lora_down matrices (then the three lora_up matrices) back to back, so the fused
+    block's single q | k | v GEMM takes them as two views of the flat buffer (ops.stacked); unrelated tensors are copied."""
+    from vision_pt_b200 import ops
+    from vision_pt_b200.jit import Denoiser, DenoiserConfig
+    from vision_pt_b200.modules.peft import LoRAConfig, PeftTargetConfig
+    from vision_pt_b200.train import LORA_TARGET, FlatLoRA
+    cfg = DenoiserConfig(patch_size=16, hidden_size=128, depth=2, num_heads=2, bottleneck_dim=32, context_dim=64)
+    net = Denoiser(cfg).to(torch.bfloat16)
+    net.requires_grad_(False)
+    PeftTargetConfig(include_keys=[LORA_TARGET], config=LoRAConfig(rank=16, alpha=16.0)).replace_to_peft_layer(net)
+    for n, p in net.named_parameters():
+        p.requires_grad_(".lora_" in n)
+    before = {n: p.detach().clone() for n, p in net.named_parameters() if ".lora_" in n}
+    flat = FlatLoRA(net)
+    for n, p in net.named_parameters():                      # re-pointing the parameters into the flat buffer keeps their values
+        if ".lora_" in n:
+            assert torch.equal(p.detach(), before[n]), n
+    attn = net.blocks[1].attn
+    downs = [m.lora_down.weight for m in (attn.to_q, attn.to_k, attn.to_v)]
+    ups = [m.lora_up.weight for m in (attn.to_q, attn.to_k, attn.to_v)]
+    d, u = ops.stacked([t.detach() for t in downs]), ops.stacked([t.detach() for t in ups])
+    assert d.shape == (48, 128) and u.shape == (384, 16)
+    assert d.data_ptr() == downs[0].data_ptr() and u.data_ptr() == ups[0].data_ptr()          # views, not copies
+    assert torch.equal(d, torch.cat([t.detach() for t in downs])) and torch.equal(u, torch.cat([t.detach() for t in ups]))
+    mixed = ops.stacked([downs[0].detach(), downs[2].detach()])                                 # not adjacent: a copy
+    assert mixed.data_ptr() != downs[0].data_ptr() and torch.equal(mixed, torch.cat([downs[0].detach(), downs[2].detach()]))
+    # every trainable matrix is in the buffer exactly once, slices do not overlap
+    spans = sorted((off, off + p.numel()) for p, off in zip(flat.params, flat.offsets))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and len(spans) == 2 * 7 * cfg.depth
+
+
+def test_fused_rows_view_needs_gap_free_slots():
+    from vision_pt_b200 import ops
+    n, k = 128, 64
+    need = n * k * 2
+    arena = torch.zeros(3 * need + 512, dtype=torch.uint8)
+    slots = [arena[i * need:(i + 1) * need] for i in range(3)]
+    v = ops.fused_rows_view(slots, n, k)
+    assert v is not None and v.shape == (3 * n, k) and v.dtype == torch.bfloat16 and v.data_ptr() == arena.data_ptr()
+    v[n, 0] = 1.0                                              # row n of the view is row 0 of the second slot
+    assert slots[1].view(torch.bfloat16)[0] == 1.0
+    gapped = [arena[0:need], arena[need + 256:2 * need + 256]]
+    assert ops.fused_rows_view(gapped, n, k) is None
