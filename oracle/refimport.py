@@ -1,5 +1,5 @@
-"""Imports the reference's own modules of the hot path from oracle/_ref (staged by oracle/make_ref.py) or, in the build
-container, straight from /root/reference.  TEST INFRASTRUCTURE ONLY (see oracle/nf4.py for the import rule).
+"""Imports the reference's own modules of the hot path from the archive oracle/_ref/reference_src.tar.gz (packed by
+oracle/make_ref.py, unpacked into the temp directory) or, in the build container, straight from /root/reference.  TEST INFRASTRUCTURE ONLY (see oracle/nf4.py for the import rule).
 
 The package __init__ files of src.models.{jit,cogview4,sdxl} import their pipelines (accelerate, bitsandbytes, ... --
 absent from this image), so those packages are pre-registered as bare namespace modules and only the files that compute
@@ -16,11 +16,34 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _loaded_root: str | None = None
 
 
+def _unpacked_archive() -> str | None:
+    """oracle/_ref/reference_src.tar.gz (oracle/make_ref.py) unpacked once per archive version into the temp directory."""
+    import hashlib
+    import tarfile
+    import tempfile
+    arc = os.path.join(HERE, "_ref", "reference_src.tar.gz")
+    if not os.path.exists(arc):
+        return None
+    tag = hashlib.sha1(f"{os.path.getsize(arc)}-{int(os.path.getmtime(arc))}-{os.getuid()}".encode()).hexdigest()[:12]
+    root = os.path.join(tempfile.gettempdir(), f"vpt_reference_{tag}")
+    if not os.path.isdir(os.path.join(root, "src", "models", "jit")):
+        tmp = f"{root}.{os.getpid()}"
+        with tarfile.open(arc, "r:gz") as tar:
+            tar.extractall(tmp, filter="data")
+        try:
+            os.rename(tmp, root)
+        except OSError:                       # another process unpacked it meanwhile
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    return root
+
+
 def reference_root() -> str | None:
-    for cand in (os.path.join(HERE, "_ref"), os.environ.get("VPT_REFERENCE_ROOT", "/root/reference")):
-        if os.path.isdir(os.path.join(cand, "src", "models", "jit")):
-            return cand
-    return None
+    root = _unpacked_archive()
+    if root is not None:
+        return root
+    cand = os.environ.get("VPT_REFERENCE_ROOT", "/root/reference")
+    return cand if os.path.isdir(os.path.join(cand, "src", "models", "jit")) else None
 
 
 def available() -> bool:
