@@ -92,7 +92,10 @@ def main() -> None:
                                      "buckets": len(bks), "tokens_per_sample": tokens, "optimizer": args.optimizer},
                           "ms_per_step_by_bucket": per_bucket, "graphs": len(tr.buckets)}))
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that hold the captured all-reduce go first; tearing the communicator down under them blocks (trainer.close)
+        tr.close()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
