@@ -282,6 +282,17 @@ int vpt_flow_loss(const void* pred, const void* clean, const void* noisy, int in
                   int64_t batch, int64_t per_sample, int32_t mode, float clamp_eps, float* loss_out, void* dpred,
                   vpt_stream_t stream);
 
+/* prepare_scaled_noised_latents (src/modules/loss/flow_match.py:60-74) in one pass: noisy = t*x + (1-t)*(randn*noise_scale)
+ * (clean_at_zero: the two weights swapped) with the rounding of each of the reference's five elementwise ops in the tensors'
+ * dtype (VPT_BF16/F16/F32), so the result is bit-identical to the op-by-op form.  latents / randn / noisy: [batch, per_sample]
+ * of `dtype`; timestep [batch] fp32 (rounded to `dtype` first, as `timestep.to(latents.dtype)` does); noisy_bf16 (may be
+ * NULL): the bf16 copy the denoiser consumes (ABI 7). */
+int vpt_noise_mix(const void* latents, const void* randn, int dtype, const float* timestep, int64_t batch, int64_t per_sample,
+                  float noise_scale, int32_t clean_at_zero, void* noisy, void* noisy_bf16, vpt_stream_t stream);
+/* y = bf16(x * bf16(scalar[0])), x / y bf16 [n], scalar fp32 on the device: the upstream gradient of the scalar loss applied
+ * to vpt_flow_loss' dpred (autograd's `dpred * dloss`) (ABI 7). */
+int vpt_scale_by_scalar(const void* x, const float* scalar, void* y, int64_t n, vpt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

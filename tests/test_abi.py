@@ -25,7 +25,7 @@ def test_python_binding_covers_header(lib_built):
     bound = set(_lib.SIGNATURES) | {"vpt_last_error", "vpt_abi_version", "vpt_linear_scratch_bytes", "vpt_linear_scratch_bytes_dir"}
     assert bound == set(_declared())
     lib = _lib.load()
-    assert lib.vpt_abi_version() == 6
+    assert lib.vpt_abi_version() == 7
     assert lib.vpt_linear_scratch_bytes(768, 2048) >= 2 * 768 * 2048
 
 

@@ -196,3 +196,51 @@ def test_layernorm_affine(rows, D, affine):
     assert rel_err(y, yr) <= 1e-2 and rel_err(xg.grad, xr.grad) <= 2e-2
     if affine:
         assert rel_err(wg.grad, wr.grad) <= 2e-2 and rel_err(bg.grad, br.grad) <= 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape,noise_scale,clean_at_zero", [((5, 3, 64, 64), 1.0, False), ((3, 3, 32, 48), 0.7, False),
+                                                             ((4, 1, 7, 9), 1.3, True)])
+def test_noise_mix_is_bit_identical_to_the_reference_ops(dtype, shape, noise_scale, clean_at_zero):
+    """One kernel == prepare_scaled_noised_latents (reference src/modules/loss/flow_match.py:60-74), bit for bit: the
+    reference's own function when its modules are staged (oracle/_ref), and always the op-by-op restatement."""
+    from oracle import refimport
+    from vision_pt_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).to(dtype).to(dev)
+    t = torch.rand(shape[0], generator=g).to(dev)                       # fp32, as the trainer's sigmoid(randn) is
+    tv = t.view(-1, 1, 1, 1).to(dtype)
+    torch.manual_seed(77)
+    z = torch.randn_like(x)
+    noise = z * noise_scale
+    want = (1 - tv) * x + tv * noise if clean_at_zero else tv * x + (1 - tv) * noise
+    got, got_bf16 = ops.noise_mix(x, z, t, noise_scale, clean_at_zero=clean_at_zero)
+    assert got.dtype == dtype and torch.equal(got, want)
+    assert got_bf16.dtype == torch.bfloat16 and torch.equal(got_bf16, want.to(torch.bfloat16))
+    if refimport.available():
+        refimport.load()
+        from src.modules.loss.flow_match import prepare_scaled_noised_latents
+        torch.manual_seed(77)                                           # the reference draws its noise itself
+        ref = prepare_scaled_noised_latents(x, tv, noise_scale=noise_scale, clean_at_zero=clean_at_zero)
+        assert torch.equal(got, ref.noisy_latents)
+
+
+def test_flow_loss_backward_applies_the_upstream_gradient():
+    """d(3 * loss)/d pred == 3 * d loss/d pred with autograd's bf16 rounding (`dpred * dloss.to(bf16)`), both loss targets."""
+    from vision_pt_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    pred0 = torch.randn(4, 3, 32, 40, device=dev).to(torch.bfloat16)
+    clean = torch.randn(4, 3, 32, 40, device=dev).to(torch.float16)
+    noisy = torch.randn(4, 3, 32, 40, device=dev).to(torch.float16)
+    t = torch.rand(4, device=dev)
+    for target in ("image", "velocity"):
+        grads = []
+        for k in (1.0, 3.0, 0.3):
+            pred = pred0.clone().requires_grad_(True)
+            (ops.flow_loss(pred, clean, noisy, t, loss_target=target) * k).backward()
+            grads.append(pred.grad)
+        for k, gk in zip((3.0, 0.3), grads[1:]):
+            want = grads[0] * torch.tensor(k, device=dev).to(torch.bfloat16)
+            assert torch.equal(gk, want)

@@ -9,6 +9,8 @@ VPT_CPU_BUDGET_S=40 timeout 400 python bench.py --impl reference --steps 3 --war
 timeout 300 python tools/bench_membound.py > gpurun_out/final_membound.txt 2>&1; echo "membound rc=$?"
 python tools/profile_step.py > gpurun_out/final_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_pair -s 20 -c 8 -o gpurun_out/final_gemm python tools/profile_step.py > gpurun_out/final_ncu.log 2>&1; echo "gemm capture rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/final_step_launches.csv python tools/profile_step.py > gpurun_out/final_launches.log 2>&1; echo "launch list rc=$?"
+python tools/summarize_launches.py gpurun_out/final_step_launches.csv > gpurun_out/final_step_launches_summary.txt 2>&1; head -12 gpurun_out/final_step_launches_summary.txt
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/final_bench.json"))

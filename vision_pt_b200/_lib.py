@@ -86,6 +86,8 @@ SIGNATURES: dict[str, list] = {
     "vpt_radam_schedulefree_step": [_P, _P, _P, _P, _I64, _D, _D, _D, _F, _F, _D, _D, _I32, _F, _P, _F, _P, _P, _I32, _P],
     "vpt_radam_schedulefree_swap": [_P, _P, _I64, _F, _I32, _P],
     "vpt_flow_loss": [_P, _P, _P, C.c_int, _P, _I64, _I64, _I32, _F, _P, _P, _P],
+    "vpt_noise_mix": [_P, _P, C.c_int, _P, _I64, _I64, _F, _I32, _P, _P, _P],
+    "vpt_scale_by_scalar": [_P, _P, _P, _I64, _P],
 }
 
 _lib = None

@@ -23,7 +23,7 @@ static inline unsigned blocks_for(long n, int per_block, long cap = 1 << 20) {
 }
 
 extern "C" const char* vpt_last_error(void) { return last_error().c_str(); }
-extern "C" int vpt_abi_version(void) { return 6; }
+extern "C" int vpt_abi_version(void) { return 7; }
 
 // ---------------------------------------------------------------------------------------------------- NF4
 extern "C" int vpt_nf4_dequant(const vpt_nf4_weight* w, int64_t n, int out_dtype, void* out, vpt_stream_t stream) {
@@ -584,6 +584,23 @@ extern "C" int vpt_radam_schedulefree_swap(void* param, const float* z, int64_t 
   VPT_REQUIRE(param && z && n > 0 && beta1 > 0.f, "vpt_radam_schedulefree_swap: bad arguments");
   const float w = to_eval ? 1.f - 1.f / beta1 : 1.f - beta1;
   radam_sf_swap_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(BFM(param), z, static_cast<long>(n), w);
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_noise_mix(const void* latents, const void* randn, int dtype, const float* timestep, int64_t batch,
+                             int64_t per_sample, float noise_scale, int32_t clean_at_zero, void* noisy, void* noisy_bf16,
+                             vpt_stream_t stream) {
+  VPT_REQUIRE(latents && randn && timestep && noisy && batch > 0 && per_sample > 0 && dtype >= 0 && dtype <= 2,
+              "vpt_noise_mix: bad arguments");
+  const long total = static_cast<long>(batch) * per_sample;
+  noise_mix_kernel<<<blocks_for(total / 8 + 1, 256, 148 * 8), 256, 0, S(stream)>>>(latents, randn, dtype, timestep, per_sample, total,
+                                                                                   noise_scale, clean_at_zero, noisy, BFM(noisy_bf16));
+  VPT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int vpt_scale_by_scalar(const void* x, const float* scalar, void* y, int64_t n, vpt_stream_t stream) {
+  VPT_REQUIRE(x && scalar && y && n > 0, "vpt_scale_by_scalar: bad arguments");
+  scale_by_scalar_kernel<<<blocks_for(n / 8 + 1, 256, 148 * 8), 256, 0, S(stream)>>>(BF(x), scalar, BFM(y), static_cast<long>(n));
   VPT_CUDA_OK(cudaGetLastError());
   return 0;
 }

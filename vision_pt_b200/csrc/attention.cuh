@@ -475,30 +475,48 @@ struct AttnDeltaParams {
   long o_sb, o_sl, o_sh, do_sb, do_sl, do_sh;
   float* delta;                // [B, H, Lq_pad]
 };
-__global__ void attn_bwd_delta_kernel(const AttnDeltaParams p) {
+// head_dim 64.  CTA = 32 consecutive query rows of one batch entry (blockIdx.y); 8 lanes x 8 elements = one head of one row.
+// The (row, head) items run heads-fastest, i.e. in the memory order of a [B, L, H*64] tensor, two items per lane group and
+// pass so that four 16-byte loads per thread are in flight; no 64-bit division anywhere.
+constexpr int kDeltaRows = 32;
+__global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const AttnDeltaParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  // one 8-lane group per (b, h, q): 8 lanes x 8 elements = 64
-  const long gid = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
-  const long total = static_cast<long>(p.B) * p.H * p.Lq_pad;
-  float acc = 0.f;
-  if (gid < total) {
-    const int q = gid % p.Lq_pad;
-    const int h = (gid / p.Lq_pad) % p.H;
-    const int b = gid / (static_cast<long>(p.Lq_pad) * p.H);
-    if (q < p.Lq) {
-      const uint4 a = *reinterpret_cast<const uint4*>(p.o + b * p.o_sb + static_cast<long>(q) * p.o_sl + h * p.o_sh + sub * 8);
-      const uint4 g = *reinterpret_cast<const uint4*>(p.d_o + b * p.do_sb + static_cast<long>(q) * p.do_sl + h * p.do_sh + sub * 8);
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+  const int b = blockIdx.y, q0 = blockIdx.x * kDeltaRows;
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int items = kDeltaRows * p.H;
+  const __nv_bfloat16* ob = p.o + b * p.o_sb + sub * 8;
+  const __nv_bfloat16* gb = p.d_o + b * p.do_sb + sub * 8;
+  float* drow = p.delta + static_cast<long>(b) * p.H * p.Lq_pad;
+  for (int i0 = grp; i0 < items; i0 += 64) {     // items is a multiple of 32: the trip count is uniform over the CTA
+    uint4 a[2], g[2];
+    int q[2], h[2];
+    bool on[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + 32 * u;
+      const int ql = i / p.H;
+      h[u] = i - ql * p.H;
+      q[u] = q0 + ql;
+      on[u] = i < items;
+      a[u] = g[u] = make_uint4(0, 0, 0, 0);
+      if (on[u] && q[u] < p.Lq) {
+        a[u] = __ldg(reinterpret_cast<const uint4*>(ob + static_cast<long>(q[u]) * p.o_sl + h[u] * p.o_sh));
+        g[u] = __ldg(reinterpret_cast<const uint4*>(gb + static_cast<long>(q[u]) * p.do_sl + h[u] * p.do_sh));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc += bf16lo(aw[i]) * bf16lo(gw[i]) + bf16hi(aw[i]) * bf16hi(gw[i]);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (on[u] && sub == 0) drow[static_cast<long>(h[u]) * p.Lq_pad + q[u]] = acc * p.scale;   // rows >= Lq: zero
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (gid < total && sub == 0) p.delta[gid] = acc * p.scale;
 }
 
 // the same for any head_dim that is a multiple of 8: one thread per (b, h, q) row

@@ -79,7 +79,8 @@ inline int launch_attn_bwd_t(const AttnTensor& q, const AttnTensor& k, const Att
   dp.scale = scale;
   const long groups = static_cast<long>(B) * H * dp.Lq_pad;
   if (HD == 64) {
-    VPT_CUDA_OK(launch_pdl(attn_bwd_delta_kernel, dim3(static_cast<unsigned>((groups * 8 + 255) / 256)), dim3(256), 0, stream, dp));
+    if (B > 65535) return 1;   // batch entries ride on gridDim.y
+    VPT_CUDA_OK(launch_pdl(attn_bwd_delta_kernel, dim3(static_cast<unsigned>(dp.Lq_pad / kDeltaRows), static_cast<unsigned>(B)), dim3(256), 0, stream, dp));
   } else {
     VPT_CUDA_OK(launch_pdl(attn_bwd_delta_row_kernel<HD>, dim3(static_cast<unsigned>((groups + 255) / 256)), dim3(256), 0, stream, dp));
   }

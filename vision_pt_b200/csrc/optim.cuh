@@ -263,4 +263,91 @@ flow_loss_kernel(const __nv_bfloat16* __restrict__ pred, const void* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ noised latents
+// prepare_scaled_noised_latents (reference src/modules/loss/flow_match.py:60-74) as ONE pass with the rounding points of its
+// five elementwise ops in the tensors' dtype T (bf16 / fp16 / fp32):
+//   n = T(randn * noise_scale);  tv = T(timestep[b]);  noisy = T( T(tv * x) + T( T(1 - tv) * n ) )     (clean_at_zero swaps
+// the two weights).  Besides `noisy` (T) it writes the bf16 copy the denoiser takes.  __fmul_rn / __fadd_rn: never
+// contracted into an FMA, so the fp32 variant rounds like the separate kernels too.
+__device__ __forceinline__ float round_as(float x, int dtype) {
+  if (dtype == 0) return __bfloat162float(__float2bfloat16_rn(x));
+  if (dtype == 1) return __half2float(__float2half_rn(x));
+  return x;
+}
+__device__ __forceinline__ float noised_value(float x, float z, float tv, float omt, float noise_scale, int dtype, int clean_at_zero) {
+  const float n = round_as(__fmul_rn(z, noise_scale), dtype);
+  const float wx = clean_at_zero ? omt : tv, wn = clean_at_zero ? tv : omt;
+  return round_as(__fadd_rn(round_as(__fmul_rn(wx, x), dtype), round_as(__fmul_rn(wn, n), dtype)), dtype);
+}
+__device__ __forceinline__ void noised_store(void* p, int dtype, long i, float v) {
+  if (dtype == 0) static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else if (dtype == 1) static_cast<__half*>(p)[i] = __float2half_rn(v);
+  else static_cast<float*>(p)[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+noise_mix_kernel(const void* __restrict__ latents, const void* __restrict__ randn, int dtype, const float* __restrict__ timestep,
+                 long per_sample, long total, float noise_scale, int clean_at_zero, void* __restrict__ noisy,
+                 __nv_bfloat16* __restrict__ noisy_bf16) {
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(latents) | reinterpret_cast<uintptr_t>(randn) | reinterpret_cast<uintptr_t>(noisy) |
+                         reinterpret_cast<uintptr_t>(noisy_bf16)) & 15) == 0;
+  if (dtype != 2 && (per_sample & 7) == 0 && aligned) {
+    for (long i8 = tid; i8 < (total >> 3); i8 += nthreads) {
+      float xf[8], zf[8], o[8];
+      loss_load8(latents, dtype, i8, xf);
+      loss_load8(randn, dtype, i8, zf);
+      const float tv = round_as(__ldg(timestep + (i8 << 3) / per_sample), dtype);
+      const float omt = round_as(__fadd_rn(1.f, -tv), dtype);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = noised_value(xf[e], zf[e], tv, omt, noise_scale, dtype, clean_at_zero);
+      uint32_t w[4], wb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+        wb[k] = *reinterpret_cast<const uint32_t*>(&b2);
+        if (dtype == 1) {
+          const __half2 h2 = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+          w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+        } else {
+          w[k] = wb[k];
+        }
+      }
+      reinterpret_cast<uint4*>(noisy)[i8] = make_uint4(w[0], w[1], w[2], w[3]);
+      if (noisy_bf16 != nullptr) reinterpret_cast<uint4*>(noisy_bf16)[i8] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+    }
+  } else {
+    for (long i = tid; i < total; i += nthreads) {
+      const float tv = round_as(__ldg(timestep + i / per_sample), dtype);
+      const float omt = round_as(__fadd_rn(1.f, -tv), dtype);
+      const float v = noised_value(loss_load(latents, dtype, i), loss_load(randn, dtype, i), tv, omt, noise_scale, dtype, clean_at_zero);
+      noised_store(noisy, dtype, i, v);
+      if (noisy_bf16 != nullptr) noisy_bf16[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// y = bf16( x * bf16(s[0]) ) for a device scalar s: the upstream gradient of a scalar loss applied to d loss / d pred
+// (16-byte accesses; a broadcast multiply by a 0-dim CUDA tensor runs torch's strided kernel at a third of the bandwidth)
+__global__ void __launch_bounds__(256)
+scale_by_scalar_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s, __nv_bfloat16* __restrict__ y, long n) {
+  const float sc = __bfloat162float(__float2bfloat16_rn(__ldg(s)));
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const long n8 = aligned ? n >> 3 : 0;
+  for (long i8 = tid; i8 < n8; i8 += nthreads) {
+    float f[8];
+    loss_load8(x, 0, i8, f);
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(__fmul_rn(f[2 * k], sc), __fmul_rn(f[2 * k + 1], sc));
+      w[k] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    reinterpret_cast<uint4*>(y)[i8] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (long i = (n8 << 3) + tid; i < n; i += nthreads) y[i] = __float2bfloat16_rn(__fmul_rn(__bfloat162float(x[i]), sc));
+}
+
 }  // namespace vpt

@@ -860,12 +860,37 @@ class FlowLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         (dpred,) = ctx.saved_tensors
-        return dpred * dloss.to(dpred.dtype), None, None, None, None, None
+        if dloss.numel() != 1:
+            return dpred * dloss.to(dpred.dtype), None, None, None, None, None
+        out = torch.empty_like(dpred)          # = dpred * dloss.to(bf16), without the strided broadcast kernel
+        _lib.call("vpt_scale_by_scalar", _p(dpred), _p(dloss.detach().float().reshape(1)), _p(out), dpred.numel(), _stream())
+        return out, None, None, None, None, None
 
 
 def flow_loss(pred, clean, noisy=None, timestep=None, loss_target: str = "image", clamp_eps: float = 0.05):
     _need_cuda(pred, clean)
     return FlowLossFn.apply(pred, clean, noisy, timestep, 1 if loss_target == "velocity" else 0, clamp_eps)
+
+
+def noise_mix(latents: torch.Tensor, randn: torch.Tensor, timestep: torch.Tensor, noise_scale: float = 1.0,
+              clean_at_zero: bool = False, want_bf16: bool = True):
+    """prepare_scaled_noised_latents (reference src/modules/loss/flow_match.py:60-74) for a given `randn =
+    torch.randn_like(latents)`, one kernel instead of five elementwise passes, bit-identical to the op-by-op form
+    (`timestep` is rounded to the latents' dtype first, as a caller passing `timestep.to(latents.dtype)` would).
+    Returns (noisy in the latents' dtype, its bf16 copy for the denoiser -- the same tensor when the latents are bf16)."""
+    _need_cuda(latents, randn, timestep)
+    if latents.dtype not in _DT or randn.dtype != latents.dtype or randn.shape != latents.shape:
+        raise TypeError("noise_mix: latents / randn of one shape and dtype (bf16, fp16 or fp32)")
+    x, z = latents.contiguous(), randn.contiguous()
+    B = x.shape[0]
+    if timestep.numel() != B:
+        raise ValueError("noise_mix: one timestep per sample")
+    t32 = timestep.reshape(B).float().contiguous()
+    noisy = torch.empty_like(x)
+    as_bf16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 and x.dtype != torch.bfloat16 else None
+    _lib.call("vpt_noise_mix", _p(x), _p(z), _DT[x.dtype], _p(t32), B, x.numel() // B, float(noise_scale), int(clean_at_zero),
+              _p(noisy), _p(as_bf16), _stream())
+    return noisy, (as_bf16 if as_bf16 is not None else noisy)
 
 
 def grad_sumsq(grad32: torch.Tensor, scale: float, out: torch.Tensor) -> None:

@@ -337,10 +337,9 @@ class JiTQLoRATrainStep:
         with torch.no_grad():
             context = self.class_encoder(self.class_ids)
             t = (torch.randn(B, device=self.device) * hp.ts_std + hp.ts_mean).sigmoid()
-            noise = torch.randn_like(images) * hp.noise_scale
-            tv = t.view(B, 1, 1, 1).to(images.dtype)
-            noisy = tv * images + (1 - tv) * noise
-        pred = self.model(image=noisy.to(torch.bfloat16), timestep=t.to(torch.bfloat16), context=context,
+            # prepare_scaled_noised_latents (reference flow_match.py:60-74) as one kernel, same roundings
+            noisy, noisy_bf16 = ops.noise_mix(images, torch.randn_like(images), t, hp.noise_scale)
+        pred = self.model(image=noisy_bf16, timestep=t.to(torch.bfloat16), context=context,
                           original_size=self.size_info, target_size=self.size_info, crop_coords=self.crop,
                           context_mask=self.attention_mask)
         loss = ops.flow_loss(pred, images, noisy, t, loss_target=hp.loss_target, clamp_eps=hp.timestep_eps)
