@@ -244,3 +244,22 @@ def test_flow_loss_backward_applies_the_upstream_gradient():
         for k, gk in zip((3.0, 0.3), grads[1:]):
             want = grads[0] * torch.tensor(k, device=dev).to(torch.bfloat16)
             assert torch.equal(gk, want)
+
+
+@pytest.mark.parametrize("B,L,n,D", [(3, 50, 37, 128), (64, 330, 256, 768), (2, 9, 9, 64), (2, 11, 5, 12)])
+def test_token_prefix_equals_the_slice(B, L, n, D):
+    """ops.token_prefix(x, n) == x[:, :n] forward and backward (the patch tokens JiT.forward hands to the final layer,
+    reference denoiser.py:1115-1124); ops.packed_tokens == .contiguous() for a slice of a wider token buffer."""
+    from vision_pt_b200 import ops
+    torch.manual_seed(L)
+    x = torch.randn(B, L, D).to(torch.bfloat16).cuda().requires_grad_(True)
+    w = torch.randn(B, n, D).to(torch.bfloat16).cuda()
+    y = ops.token_prefix(x, n)
+    assert y.is_contiguous() and torch.equal(y, x[:, :n])
+    (y * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    (xr[:, :n] * w).sum().backward()
+    assert torch.equal(x.grad, xr.grad)
+    for lo, hi in ((0, n), (L - n, L)):
+        view = x.detach()[:, lo:hi]
+        assert torch.equal(ops.packed_tokens(view), view.contiguous()) and ops.packed_tokens(view).is_contiguous()

@@ -196,7 +196,8 @@ def test_full_size_jit_b_linear(K, N):
         assert torch.equal(y0, yb)
 
 
-@pytest.mark.parametrize("M,K,N", [(300, 3413, 1280), (17568, 3413, 1280), (21120, 2730, 1024), (130, 341, 128)])
+@pytest.mark.parametrize("M,K,N", [(300, 3413, 1280), (17568, 3413, 1280), (21120, 2730, 1024), (130, 341, 128),
+                                   (300, 1280, 3413), (16384, 1024, 2730), (130, 128, 341), (16384, 768, 768)])
 def test_frozen_bf16_linear_with_ragged_in_features(M, K, N):
     """The final layer's SwiGLU w_3 of JiT-H / JiT-L (frozen bf16, in_features 3413 / 2730: not a multiple of 8) runs the
     tcgen05 kernels through a row-padded view of the weight (ops.padded_weight) in both directions, small and large M."""
@@ -216,6 +217,16 @@ def test_frozen_bf16_linear_with_ragged_in_features(M, K, N):
     assert rel_err(y, yr) <= TOL and rel_err(x.grad, xr.grad) <= TOL
     pw = ops.padded_weight(w)
     assert pw.shape == (N, K) and pw.stride(0) % 8 == 0 and torch.equal(pw, w) and ops.padded_weight(w) is pw   # cached
+    # the input gradient ran as a forward call on the cached transpose (CTA-pair kernel); the 1-CTA backward kernel agrees
+    tw = ops.transposed_weight(pw)
+    assert tw.shape == (K, N) and tw.stride(0) % 8 == 0 and torch.equal(tw, w.t()) and ops.transposed_weight(pw) is tw
+    ops.DENSE_BWD_VIA_TRANSPOSE = False
+    try:
+        x2 = x.detach().clone().requires_grad_(True)
+        _kernel_linear(x2, w, b).backward(dy)
+    finally:
+        ops.DENSE_BWD_VIA_TRANSPOSE = True
+    assert rel_err(x2.grad, xr.grad) <= TOL and rel_err(x2.grad, x.grad) <= TOL
 
 
 @pytest.mark.parametrize("M,D,F", [(2640, 768, 2048), (1320, 1024, 2730), (1100, 1280, 3413), (21120, 768, 2048)])

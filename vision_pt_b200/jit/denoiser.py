@@ -225,9 +225,7 @@ class JiTBlockFn(torch.autograd.Function):
         lins, n1w, n2w, qnw, knw, H, eps, tail, n_keep, _, block_index, nxt, _, qkv_bias = spec
         B, L, D = x.shape
         M = B * L
-        x2 = x.reshape(M, D)
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
+        x2 = ops.packed_tokens(x).reshape(M, D)
         pads = [ops._pad_rank(l.down, l.up) for l in lins]
 
         # all seven NF4 weights of the block dequantised by one launch into L2-resident slots -- by the previous block's
@@ -300,9 +298,7 @@ class JiTBlockFn(torch.autograd.Function):
         B, L, D = ctx.dims
         M = B * L
         dev = dy.device
-        dy2 = dy.reshape(M, D)
-        if not dy2.is_contiguous():
-            dy2 = dy2.contiguous()
+        dy2 = ops.packed_tokens(dy).reshape(M, D)      # e.g. the [:, :pre_ctx] slice the context concatenation hands back
         grads: list = [None] * 14
 
         slots = None
@@ -587,7 +583,7 @@ class JiT(nn.Module):
             if not cfg.do_context_fuse and i >= cfg.context_start_block and not keep_slots:
                 tokens = tokens[:, :-ctx_len, :]
         ops.PREFETCH.reset()
-        patches = self.final_layer(tokens[:, :n_patch, :])
+        patches = self.final_layer(ops.token_prefix(tokens, n_patch) if tokens.is_cuda else tokens[:, :n_patch, :])
         return self.unpatchify(patches, height=height, width=width)
 
 

@@ -27,6 +27,9 @@ FUSE_SWIGLU = os.environ.get("VPT_FUSE_SWIGLU", "1") != "0"
 # q | k | v of the fused block as ONE forward GEMM over the stacked dequantised weights (three 25 us launches -> one);
 # VPT_FUSE_QKV=0 = three calls
 FUSE_QKV = os.environ.get("VPT_FUSE_QKV", "1") != "0"
+# input gradient of a dense frozen bf16 linear (patch embed, final layer) as a forward call on the cached transposed weight
+# (CTA-pair kernel) instead of the 1-CTA backward kernel
+DENSE_BWD_VIA_TRANSPOSE = os.environ.get("VPT_DENSE_BWD_TRANSPOSE", "1") != "0"
 _SCRATCH: dict[tuple, torch.Tensor] = {}
 
 
@@ -208,6 +211,66 @@ def padded_weight(w: torch.Tensor) -> torch.Tensor:
         hit = (w._version, buf[:, :K], w.data_ptr())
         w._vpt_padded = hit
     return hit[1]
+
+
+def transposed_weight(w: torch.Tensor) -> torch.Tensor:
+    """[K, N] view (row pitch = N rounded up to 8, zero padding) of the transpose of a frozen bf16 [N, K] weight: with it the
+    input gradient dX = dY W of a dense frozen linear is a FORWARD call of the CTA-pair kernel (a K-major operand, as the
+    transposed dequantisation gives the NF4 weights) instead of the 1-CTA backward kernel.  Cached on the weight object
+    like padded_weight."""
+    N, K = w.shape
+    hit = getattr(w, "_vpt_transposed", None)
+    if hit is None or hit[0] != w._version or hit[1].device != w.device or hit[2] != w.data_ptr():
+        buf = torch.zeros((K, (N + 7) // 8 * 8), dtype=w.dtype, device=w.device)
+        buf[:, :N] = w.detach().t()
+        hit = (w._version, buf[:, :N], w.data_ptr())
+        w._vpt_transposed = hit
+    return hit[1]
+
+
+def packed_tokens(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous copy of a [B, n, D] slice of a wider token buffer (rows contiguous inside a batch entry, any batch pitch)
+    as one 16-byte-vectorised launch; anything else goes through torch."""
+    if x.is_contiguous():
+        return x
+    es = x.element_size()
+    if (x.dim() == 3 and x.is_cuda and x.stride(2) == 1 and x.stride(1) == x.shape[2] and x.stride(0) >= x.shape[1] * x.shape[2]
+            and (x.shape[1] * x.shape[2] * es) % 16 == 0 and (x.stride(0) * es) % 16 == 0 and x.data_ptr() % 16 == 0):
+        B, n, D = x.shape
+        out = torch.empty((B, n, D), dtype=x.dtype, device=x.device)
+        _lib.call("vpt_copy_rows", _p(out), n * D * es, _p(x), x.stride(0) * es, B, n * D * es, _stream())
+        return out
+    return x.contiguous()
+
+
+class TokenPrefixFn(torch.autograd.Function):
+    """x[:, :n] of a [B, L, D] token buffer as a contiguous tensor (JiT.forward: the patch tokens handed to the final layer,
+    reference denoiser.py:1115-1124); backward = the gradient in a zero-tailed [B, L, D] buffer.  Two vectorised launches
+    where the slice + reshape pair costs torch a strided copy each way plus a fill."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.L = x.shape[1]
+        return packed_tokens(x[:, :n])
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, n, D = dy.shape
+        dyc = dy.contiguous()
+        dx = torch.empty((B, ctx.L, D), dtype=dy.dtype, device=dy.device)
+        es = dy.element_size()
+        if dy.is_cuda and (n * D * es) % 16 == 0 and (ctx.L * D * es) % 16 == 0:
+            _lib.call("vpt_copy_rows", _p(dx), ctx.L * D * es, _p(dyc), n * D * es, B, n * D * es, _stream())
+        else:
+            dx[:, :n] = dyc
+        copy_token_slots(dx, n, None)
+        return dx, None
+
+
+def token_prefix(x: torch.Tensor, n: int) -> torch.Tensor:
+    if n == x.shape[1]:
+        return x
+    return TokenPrefixFn.apply(x, n)
 
 
 # ------------------------------------------------------------------------------------------------------- NF4
@@ -482,7 +545,13 @@ class NF4LoRALinearFn(torch.autograd.Function):
         lora = dpad is not None
         need_lora_grad = lora and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
         dside = None
-        if ctx.needs_input_grad[0] or need_lora_grad:
+        if ctx.needs_input_grad[0] and not lora and isinstance(ctx.w, torch.Tensor) and DENSE_BWD_VIA_TRANSPOSE \
+                and not ctx.w.requires_grad:
+            dx2, _ = linear_raw(dy2, transposed_weight(ctx.w), None, None, None, 1.0, None)      # dX = dY (W^T)^T
+            dx = dx2.reshape(*dy.shape[:-1], x2.shape[1])
+            if ctx.in_dtype != torch.bfloat16:
+                dx = dx.to(ctx.in_dtype)
+        elif ctx.needs_input_grad[0] or need_lora_grad:
             dx2, dside = linear_raw(dy2, ctx.w, None, dpad, upad, ctx.scale, None, want_side=lora, backward=True)
             if ctx.needs_input_grad[0]:
                 dx = dx2.reshape(*dy.shape[:-1], x2.shape[1])
