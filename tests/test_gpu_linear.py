@@ -290,3 +290,38 @@ def test_lora_rank_above_16_takes_the_composition(rank):
     yr.backward(dy.float())
     assert rel_err(y, yr) <= TOL and rel_err(xg.grad, xr.grad) <= TOL
     assert rel_err(layer.lora_down.weight.grad, down.grad) <= TOL and rel_err(layer.lora_up.weight.grad, up.grad) <= TOL
+
+
+@pytest.mark.parametrize("M,D,F", [(300, 128, 341), (16384, 768, 2048), (4000, 1024, 2730), (1100, 1280, 3413)])
+def test_dense_swiglu_fused_equals_composed(M, D, F):
+    """The final layer's MLP (three frozen bf16 linears, reference jit/denoiser.py:498-506, 535-543) with the gate in the GEMM
+    epilogues (ops.dense_swiglu) against the composition linear -> swiglu kernel -> linear and against fp32 torch, forward
+    and input gradient; ragged F as in JiT-L / JiT-H."""
+    from vision_pt_b200 import ops
+    from vision_pt_b200.jit.denoiser import SwiGLU
+    torch.manual_seed(M + F)
+    mlp = SwiGLU(D, int(F * 3 / 2) + 1, bias=True)
+    assert mlp.w_1.out_features == F
+    for p in mlp.parameters():
+        p.data.normal_(0, 0.05)
+    mlp = mlp.to(torch.bfloat16).cuda().requires_grad_(False)
+    x = torch.randn(M, D).to(torch.bfloat16).cuda().requires_grad_(True)
+    dy = torch.randn(M, D).to(torch.bfloat16).cuda()
+    assert ops.FUSE_SWIGLU
+    y = mlp(x)
+    y.backward(dy)
+    ops.FUSE_SWIGLU = False
+    try:
+        xc = x.detach().clone().requires_grad_(True)
+        yc = mlp(xc)
+        yc.backward(dy)
+    finally:
+        ops.FUSE_SWIGLU = True
+    xr = x.detach().float().requires_grad_(True)
+    w = {k: v.float() for k, v in mlp.state_dict().items()}
+    g = xr @ w["w_1.weight"].t() + w["w_1.bias"]
+    u = xr @ w["w_2.weight"].t() + w["w_2.bias"]
+    yr = (torch.nn.functional.silu(g) * u) @ w["w_3.weight"].t() + w["w_3.bias"]
+    yr.backward(dy.float())
+    assert rel_err(y, yr) <= TOL and rel_err(x.grad, xr.grad) <= TOL
+    assert rel_err(y, yc) <= 1e-2 and rel_err(x.grad, xc.grad) <= 1e-2

@@ -163,7 +163,10 @@ static int linear_common(const vpt_linear_args* a, bool bwd, cudaStream_t stream
     g.out2 = a->out2; g.ldd2 = static_cast<int>(a->ld_out2);
     g.in2 = a->in2; g.ldr2 = static_cast<int>(a->ld_in2);
     if (a->epilogue != 0) {
-      VPT_REQUIRE((a->epilogue == 1 && !bwd) || (a->epilogue == 2 && bwd), "vpt_nf4lora_linear: epilogue 1 is a forward mode, 2 a backward mode");
+      // (a dense bf16 weight has no backward on this route: its caller passes the transposed weight to the forward entry
+      // point, so mode 2 is accepted there)
+      VPT_REQUIRE((a->epilogue == 1 && !bwd) || (a->epilogue == 2 && (bwd || a->w_bf16 != nullptr)),
+                  "vpt_nf4lora_linear: epilogue 1 is a forward mode, 2 a backward mode");
       VPT_REQUIRE(a->residual && a->out2 && a->ld_out2 % 8 == 0 && a->ld_res % 8 == 0 && (a->epilogue == 1 || (a->in2 && a->ld_in2 % 8 == 0)),
                   "vpt_nf4lora_linear: fused SwiGLU epilogue needs residual (g), out2 (and in2 = u in mode 2) with pitches that are multiples of 8");
     }

@@ -152,6 +152,11 @@ class SwiGLU(nn.Module):
         return layer(x)
 
     def forward(self, hidden_states):
+        if all(type(l) is nn.Linear for l in (self.w_1, self.w_2, self.w_3)) and self.ffn_dropout.p == 0.0:
+            y = ops.dense_swiglu(hidden_states, self.w_1.weight, self.w_1.bias, self.w_2.weight, self.w_2.bias,
+                                 self.w_3.weight, self.w_3.bias)
+            if y is not None:
+                return y
         a = ops.swiglu(self._lin(self.w_1, hidden_states), self._lin(self.w_2, hidden_states))
         return self._lin(self.w_3, self.ffn_dropout(a))
 

@@ -440,7 +440,7 @@ def linear_raw(x2: torch.Tensor, w: Nf4Tensors | torch.Tensor, bias, down, up, s
     args.tile_n = tile_n
     out2 = None
     if epilogue:
-        if scratch is None or residual is None or (epilogue == 2 and in2 is None):
+        if (scratch is None and isinstance(w, Nf4Tensors)) or residual is None or (epilogue == 2 and in2 is None):
             raise ValueError("fused SwiGLU epilogue: needs the scratch (CTA-pair) route, residual = g and, in mode 2, in2 = u")
         out2_full = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x2.device)
         out2 = out2_full[:, :n_out] if ld_out != n_out else out2_full
@@ -782,6 +782,44 @@ class SwiGLUFn(torch.autograd.Function):
 
 def swiglu(g, u):
     return SwiGLUFn.apply(g, u)
+
+
+class DenseSwiGLUFn(torch.autograd.Function):
+    """w_3(silu(w_1 x) * (w_2 x)) for three FROZEN bf16 linears (the final layer's MLP, reference jit/denoiser.py:498-506,
+    535-543) with the gate in the epilogues of the CTA-pair GEMMs, like the fused block: forward = w_1, w_2 (+ SwiGLU
+    forward), w_3; backward = w_3^T (+ SwiGLU backward), w_1^T, w_2^T (+ the sum of the two input gradients as its residual)
+    -- six launches, no stand-alone gate / add kernels.  Weights come as padded_weight views, the backward uses their cached
+    transposes."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3):
+        x2 = _rows(x)
+        g, _ = linear_raw(x2, w1, b1, None, None, 1.0)
+        a, u, _ = linear_raw(x2, w2, b2, None, None, 1.0, g, epilogue=1)
+        y, _ = linear_raw(a, w3, b3, None, None, 1.0)
+        ctx.weights = (w1, w2, w3)
+        ctx.save_for_backward(g, u)
+        return y.reshape(*x.shape[:-1], y.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        g, u = ctx.saved_tensors
+        w1, w2, w3 = ctx.weights
+        dy2 = _rows(dy)
+        dg, du, _ = linear_raw(dy2, transposed_weight(w3), None, None, None, 1.0, g, epilogue=2, in2=u)
+        dx, _ = linear_raw(dg, transposed_weight(w1), None, None, None, 1.0)
+        dx, _ = linear_raw(du, transposed_weight(w2), None, None, None, 1.0, dx)
+        return dx.reshape(*dy.shape[:-1], dx.shape[1]), None, None, None, None, None, None
+
+
+def dense_swiglu(x, w1, b1, w2, b2, w3, b3):
+    """None when the three linears do not qualify (trainable, not bf16 on a CUDA device): the caller composes the ops."""
+    ws, bs = (w1, w2, w3), (b1, b2, b3)
+    if not (FUSE_SWIGLU and x.is_cuda and x.dtype == torch.bfloat16
+            and all(w.dtype == torch.bfloat16 and not w.requires_grad for w in ws)
+            and all(b is None or (b.dtype == torch.bfloat16 and not b.requires_grad) for b in bs)):
+        return None
+    return DenseSwiGLUFn.apply(x, padded_weight(w1), b1, padded_weight(w2), b2, padded_weight(w3), b3)
 
 
 # ------------------------------------------------------------------------------------------------------- adaLN
