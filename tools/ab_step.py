@@ -26,6 +26,7 @@ VARIANTS = {
     "separate swiglu kernels": {"FUSE_SWIGLU": False},
     "no dequant prefetch": {"PREFETCH_DEQUANT": False},
     "separate q / k / v GEMMs": {"FUSE_QKV": False},
+    "ATen glue (noise, slices, dense final layer)": {"FUSED_GLUE": False},
 }
 net = T.build_jit_qlora(args.model, device="cuda", seed=42)
 state = T.TrainState(net)

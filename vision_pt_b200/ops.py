@@ -30,6 +30,10 @@ FUSE_QKV = os.environ.get("VPT_FUSE_QKV", "1") != "0"
 # input gradient of a dense frozen bf16 linear (patch embed, final layer) as a forward call on the cached transposed weight
 # (CTA-pair kernel) instead of the 1-CTA backward kernel
 DENSE_BWD_VIA_TRANSPOSE = os.environ.get("VPT_DENSE_BWD_TRANSPOSE", "1") != "0"
+# the step's glue as library kernels: noise preparation (noise_mix), the patch-token slice (token_prefix / packed_tokens), the
+# upstream-gradient scaling of the loss, the final layer's MLP through the SwiGLU epilogues; off = the ATen ops these
+# replaced (A/B measurements, VPT_FUSED_GLUE=0)
+FUSED_GLUE = os.environ.get("VPT_FUSED_GLUE", "1") != "0"
 _SCRATCH: dict[tuple, torch.Tensor] = {}
 
 
@@ -234,7 +238,7 @@ def packed_tokens(x: torch.Tensor) -> torch.Tensor:
     if x.is_contiguous():
         return x
     es = x.element_size()
-    if (x.dim() == 3 and x.is_cuda and x.stride(2) == 1 and x.stride(1) == x.shape[2] and x.stride(0) >= x.shape[1] * x.shape[2]
+    if (FUSED_GLUE and x.dim() == 3 and x.is_cuda and x.stride(2) == 1 and x.stride(1) == x.shape[2] and x.stride(0) >= x.shape[1] * x.shape[2]
             and (x.shape[1] * x.shape[2] * es) % 16 == 0 and (x.stride(0) * es) % 16 == 0 and x.data_ptr() % 16 == 0):
         B, n, D = x.shape
         out = torch.empty((B, n, D), dtype=x.dtype, device=x.device)
@@ -270,6 +274,8 @@ class TokenPrefixFn(torch.autograd.Function):
 def token_prefix(x: torch.Tensor, n: int) -> torch.Tensor:
     if n == x.shape[1]:
         return x
+    if not FUSED_GLUE:
+        return x[:, :n]
     return TokenPrefixFn.apply(x, n)
 
 
@@ -545,7 +551,7 @@ class NF4LoRALinearFn(torch.autograd.Function):
         lora = dpad is not None
         need_lora_grad = lora and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
         dside = None
-        if ctx.needs_input_grad[0] and not lora and isinstance(ctx.w, torch.Tensor) and DENSE_BWD_VIA_TRANSPOSE \
+        if ctx.needs_input_grad[0] and not lora and isinstance(ctx.w, torch.Tensor) and DENSE_BWD_VIA_TRANSPOSE and FUSED_GLUE \
                 and not ctx.w.requires_grad:
             dx2, _ = linear_raw(dy2, transposed_weight(ctx.w), None, None, None, 1.0, None)      # dX = dY (W^T)^T
             dx = dx2.reshape(*dy.shape[:-1], x2.shape[1])
@@ -815,7 +821,7 @@ class DenseSwiGLUFn(torch.autograd.Function):
 def dense_swiglu(x, w1, b1, w2, b2, w3, b3):
     """None when the three linears do not qualify (trainable, not bf16 on a CUDA device): the caller composes the ops."""
     ws, bs = (w1, w2, w3), (b1, b2, b3)
-    if not (FUSE_SWIGLU and x.is_cuda and x.dtype == torch.bfloat16
+    if not (FUSE_SWIGLU and FUSED_GLUE and x.is_cuda and x.dtype == torch.bfloat16
             and all(w.dtype == torch.bfloat16 and not w.requires_grad for w in ws)
             and all(b is None or (b.dtype == torch.bfloat16 and not b.requires_grad) for b in bs)):
         return None
@@ -967,7 +973,7 @@ class FlowLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         (dpred,) = ctx.saved_tensors
-        if dloss.numel() != 1:
+        if dloss.numel() != 1 or not FUSED_GLUE:
             return dpred * dloss.to(dpred.dtype), None, None, None, None, None
         out = torch.empty_like(dpred)          # = dpred * dloss.to(bf16), without the strided broadcast kernel
         _lib.call("vpt_scale_by_scalar", _p(dpred), _p(dloss.detach().float().reshape(1)), _p(out), dpred.numel(), _stream())

@@ -338,7 +338,13 @@ class JiTQLoRATrainStep:
             context = self.class_encoder(self.class_ids)
             t = (torch.randn(B, device=self.device) * hp.ts_std + hp.ts_mean).sigmoid()
             # prepare_scaled_noised_latents (reference flow_match.py:60-74) as one kernel, same roundings
-            noisy, noisy_bf16 = ops.noise_mix(images, torch.randn_like(images), t, hp.noise_scale)
+            if ops.FUSED_GLUE:
+                noisy, noisy_bf16 = ops.noise_mix(images, torch.randn_like(images), t, hp.noise_scale)
+            else:
+                noise = torch.randn_like(images) * hp.noise_scale
+                tv = t.view(B, 1, 1, 1).to(images.dtype)
+                noisy = tv * images + (1 - tv) * noise
+                noisy_bf16 = noisy.to(torch.bfloat16)
         pred = self.model(image=noisy_bf16, timestep=t.to(torch.bfloat16), context=context,
                           original_size=self.size_info, target_size=self.size_info, crop_coords=self.crop,
                           context_mask=self.attention_mask)
