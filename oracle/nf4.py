@@ -10,7 +10,7 @@ and self-consistency).  What follows restates the published bitsandbytes algorit
 (``bitsandbytes/functional.py``: quantize_4bit / dequantize_4bit / quantize_blockwise / create_dynamic_map /
 QuantState.as_dict and ``csrc/kernels.cu``: kQuantizeBlockwise, kDequantizeBlockwise, dQuantizeNF4, dQuantize)
 as called from the reference at src/modules/quant/bnb.py:37-129 and src/modules/quant/functional.py:342-371.
-The NF4 code table was re-derived with scipy (see tests/test_oracle_nf4.py) and matches bit-for-bit.
+The NF4 code table was re-derived with scipy (tests/test_oracle_golden.py: create_normal_map) and matches bit-for-bit.
 """
 from __future__ import annotations
 
