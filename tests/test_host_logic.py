@@ -270,3 +270,37 @@ def test_fused_rows_view_needs_gap_free_slots():
     assert slots[1].view(torch.bfloat16)[0] == 1.0
     gapped = [arena[0:need], arena[need + 256:2 * need + 256]]
     assert ops.fused_rows_view(gapped, n, k) is None
+
+
+def test_transposed_weight_copy_is_cached_on_the_weight_and_padded():
+    """ops.transposed_weight: the [K, N] operand the dense frozen linears' input gradient runs on (rows padded to 8 elements,
+    zeros in the padding), cached on the weight object and rebuilt after an in-place modification."""
+    from vision_pt_b200 import ops
+    w = torch.randn(5, 13).to(torch.bfloat16)                # N = 5 (ragged), K = 13
+    tw = ops.transposed_weight(w)
+    assert tw.shape == (13, 5) and tw.stride() == (8, 1) and torch.equal(tw, w.t())
+    assert ops.transposed_weight(w) is tw
+    w.mul_(2)
+    tw2 = ops.transposed_weight(w)
+    assert tw2 is not tw and torch.equal(tw2, w.t())
+    # through the padded view of a ragged weight: the cache sits on that view, which the weight keeps alive
+    pw = ops.padded_weight(w)
+    assert ops.transposed_weight(pw) is ops.transposed_weight(ops.padded_weight(w))
+
+
+def test_token_prefix_and_packed_tokens_without_a_device():
+    """The slice helpers fall back to torch for tensors the row-copy kernel does not take (here: CPU tensors) with the same
+    values and gradients; noise_mix, like every kernel wrapper, refuses CPU tensors instead of computing on the host."""
+    from vision_pt_b200 import ops
+    x = torch.randn(2, 7, 6, requires_grad=True)
+    y = ops.token_prefix(x, 4)
+    assert torch.equal(y, x[:, :4]) and y.is_contiguous()
+    y.sum().backward()
+    want = torch.zeros(2, 7, 6)
+    want[:, :4] = 1
+    assert torch.equal(x.grad, want)
+    assert ops.token_prefix(x, 7) is x
+    v = x.detach()[:, 2:5]
+    assert torch.equal(ops.packed_tokens(v), v) and ops.packed_tokens(v).is_contiguous()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.noise_mix(torch.zeros(2, 3, 4, 4), torch.zeros(2, 3, 4, 4), torch.zeros(2))
