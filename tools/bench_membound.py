@@ -130,6 +130,19 @@ case("token_gather     [64, 256 -> 128, 768]", 4 * 64 * 128 * 768, [lambda t=t: 
 q4 = [rnd(2, 4160, 32, 128) for _ in range(ROT)]
 cos, sin = torch.randn(4096, 128, device=dev), torch.randn(4096, 128, device=dev)
 case("rope_half        [2, 4160, 32, 128] (64 text tokens)", 4 * q4[0].numel(), [lambda t=t: ops.rope_half(t, cos, sin, 64) for t in q4])
+# the step's glue (JiT-B batch): noise preparation, the patch-token slice and its gradient, the loss's upstream gradient
+ims = [rnd(64, 3, 256, 256, dtype=torch.float16) for _ in range(ROT)]
+zs = [rnd(64, 3, 256, 256, dtype=torch.float16) for _ in range(ROT)]
+ts = torch.rand(64, device=dev)
+n_img = ims[0].numel()
+case("noise_mix        fp16 [64, 3, 256, 256] (+ bf16 copy)", 8 * n_img, [lambda a=a, z=z: ops.noise_mix(a, z, ts, 1.0) for a, z in zip(ims, zs)])
+tok = [rnd(64, 330, 768) for _ in range(ROT)]
+case("token_prefix     [64, 330 -> 256, 768]", 4 * 64 * 256 * 768, [lambda t=t: ops.packed_tokens(t[:, :256]) for t in tok])
+dps = [rnd(64, 3, 256, 256) for _ in range(ROT)]
+one = torch.ones(1, device=dev)
+outs = [torch.empty_like(d) for d in dps]
+case("scale_by_scalar  bf16 [64, 3, 256, 256]", 4 * n_img,
+     [lambda d=d, o=o: ops._lib.call("vpt_scale_by_scalar", ops._p(d), ops._p(one), ops._p(o), d.numel(), ops._stream()) for d, o in zip(dps, outs)])
 if rows_out:
     json.dump([{"kernel": n, "bytes": b, "us": u, "gbs": g, "frac": g / PEAK} for n, b, u, g in rows_out],
               open(os.path.join(ROOT, "gpurun_out", "membound.json"), "w"), indent=1)

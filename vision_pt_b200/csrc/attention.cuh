@@ -475,10 +475,12 @@ struct AttnDeltaParams {
   long o_sb, o_sl, o_sh, do_sb, do_sl, do_sh;
   float* delta;                // [B, H, Lq_pad]
 };
-// head_dim 64.  CTA = 32 consecutive query rows of one batch entry (blockIdx.y); 8 lanes x 8 elements = one head of one row.
+// head_dim 64.  CTA = 8 consecutive query rows of one batch entry (blockIdx.y); 8 lanes x 8 elements = one head of one row.
 // The (row, head) items run heads-fastest, i.e. in the memory order of a [B, L, H*64] tensor, two items per lane group and
-// pass so that four 16-byte loads per thread are in flight; no 64-bit division anywhere.
-constexpr int kDeltaRows = 32;
+// pass so that four 16-byte loads per thread are in flight; no 64-bit division anywhere.  Small CTAs: a CTA is done after
+// one or two passes, so nearly all of the kernel's loads are in flight at once (32 rows per CTA: 16.0 us, six serial passes).
+constexpr int kDeltaRows = 8;
+static_assert(kDeltaRows % 4 == 0, "the pass count must be uniform over a warp (four lane groups)");
 __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const AttnDeltaParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const AttnDeltaPara
   const __nv_bfloat16* ob = p.o + b * p.o_sb + sub * 8;
   const __nv_bfloat16* gb = p.d_o + b * p.do_sb + sub * 8;
   float* drow = p.delta + static_cast<long>(b) * p.H * p.Lq_pad;
-  for (int i0 = grp; i0 < items; i0 += 64) {     // items is a multiple of 32: the trip count is uniform over the CTA
+  for (int i0 = grp; i0 < items; i0 += 64) {     // items is a multiple of 4 lane groups: the trip count is uniform over a warp
     uint4 a[2], g[2];
     int q[2], h[2];
     bool on[2];
