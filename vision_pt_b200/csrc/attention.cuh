@@ -477,8 +477,8 @@ struct AttnDeltaParams {
 };
 // head_dim 64.  CTA = 8 consecutive query rows of one batch entry (blockIdx.y); 8 lanes x 8 elements = one head of one row.
 // The (row, head) items run heads-fastest, i.e. in the memory order of a [B, L, H*64] tensor, two items per lane group and
-// pass so that four 16-byte loads per thread are in flight; no 64-bit division anywhere.  Small CTAs: a CTA is done after
-// one or two passes, so nearly all of the kernel's loads are in flight at once (32 rows per CTA: 16.0 us, six serial passes).
+// pass so that four 16-byte loads per thread are in flight; no 64-bit division anywhere.  CTA size does not matter
+// (8 rows: 16.8 us, 32 rows: 16.0 us at the JiT-B shape; the (b, h, q)-ordered form with 64-bit index math took 18.8 us).
 constexpr int kDeltaRows = 8;
 static_assert(kDeltaRows % 4 == 0, "the pass count must be uniform over a warp (four lane groups)");
 __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const AttnDeltaParams p) {
