@@ -563,7 +563,8 @@ def run_ours(args) -> None:
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3) + n_settle,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "settle_steps": n_settle,     # further untimed steps after the W warm-up steps (config.settle says why)
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": workload_name(model_name, args.batch, args.res, args.rank),
